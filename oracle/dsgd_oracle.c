@@ -1,0 +1,332 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- see dsgd_oracle.h for the role of this file and the parity status.
+ *
+ * fp64 array-based restatement of the reference's sync / async SGD arithmetic.  The reference keeps
+ * every vector as an immutable Map[Int, Number] whose constructor drops entries with |v| <= 1e-20
+ * (math/Sparse.scala:108-118); here a dense double[dim] plays the map and "v == 0.0" plays "key absent",
+ * and the filter is re-applied wherever the reference builds a new Sparse.
+ */
+#include "dsgd_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define EPS 1e-20 /* math/Sparse.scala:104 */
+
+static inline double filt(double v) { return fabs(v) > EPS ? v : 0.0; }
+
+/* x . w  = (x * w).sum  (math/Vec.scala:58; math/Sparse.scala:46,20-31): the product map is built first,
+ * which drops products with |x_j w_j| <= 1e-20, then folded.  Fold order here is index order (the
+ * reference's is HashMap order, not reproducible without a JVM -- SURVEY.md 2.3). */
+static inline double row_dot(const dsgd_oracle_csr *a, int64_t r, const double *w) {
+  double s = 0.0;
+  for (int64_t p = a->row_ptr[r]; p < a->row_ptr[r + 1]; ++p) {
+    double xv = filt((double)a->val[p]); /* the row itself is a Sparse: tiny entries are absent */
+    s += filt(xv * w[a->col[p]]);
+  }
+  return s;
+}
+
+static inline double signum(double v) { return (double)((v > 0.0) - (v < 0.0)); }
+
+static int check_idx(const dsgd_oracle_csr *a, const int32_t *idx, int64_t n) {
+  for (int64_t i = 0; i < n; ++i)
+    if (idx[i] < 0 || idx[i] >= a->n_rows) return -2;
+  return 0;
+}
+
+int dsgd_oracle_forward(const dsgd_oracle_csr *a, const double *w, const int32_t *idx, int64_t n, double *preds) {
+  if (check_idx(a, idx, n)) return -2;
+  for (int64_t i = 0; i < n; ++i) preds[i] = signum(row_dot(a, idx[i], w)) * -1.0; /* SparseSVM.scala:14 */
+  return 0;
+}
+
+static double norm_squared(const double *w, int32_t dim) { /* math/Vec.scala:55 */
+  double s = 0.0;
+  for (int32_t j = 0; j < dim; ++j) s += w[j] * w[j];
+  return s;
+}
+
+int dsgd_oracle_loss_acc(const dsgd_oracle_csr *a, double lambda, const double *w, const int32_t *idx,
+                         int64_t begin, int64_t n, double *loss, double *acc) {
+  if (n <= 0) return -3; /* reduce on an empty collection throws in the reference */
+  if (idx && check_idx(a, idx, n)) return -2;
+  if (!idx && (begin < 0 || begin + n > a->n_rows)) return -2;
+  double total = 0.0;
+  int64_t correct = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    int64_t r = idx ? idx[i] : begin + i;
+    double p = signum(row_dot(a, r, w)) * -1.0;    /* SparseSVM.scala:14 */
+    double y = (double)a->label[r];
+    double l = 1.0 - y * p;                        /* SparseSVM.scala:16 */
+    total += l > 0.0 ? l : 0.0;
+    correct += (p == y);                           /* core/Master.scala:102 */
+  }
+  if (loss) *loss = lambda * norm_squared(w, a->dim) + total / (double)n; /* SparseSVM.scala:20-23 */
+  if (acc) *acc = (double)correct / (double)n;
+  return 0;
+}
+
+/* c = lambda * 2.0 * w.dot(dimSparsity)  (SparseSVM.scala:31) */
+static double reg_scalar(double lambda, const double *w, const double *d, int32_t dim) {
+  double s = 0.0;
+  for (int32_t j = 0; j < dim; ++j) s += filt(w[j] * d[j]);
+  return lambda * 2.0 * s;
+}
+
+/* Accumulate sum_i backward(w, x_i, y_i) into g (dense, caller-zeroed), recording first-touch columns in
+ * `touched` (capacity dim).  Returns via *hinge the sum of per-sample losses of the batch.
+ * Vec.sum is a left fold of `+`, each of which re-filters its result (math/Vec.scala:128-131;
+ * math/Sparse.scala:33,108-118). */
+static void accumulate_batch(const dsgd_oracle_csr *a, const double *w, const int32_t *idx, int64_t n, double *g,
+                             int32_t *touched, int32_t *n_touched, uint8_t *mark, double *hinge) {
+  double h = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    int64_t r = idx[i];
+    double y = (double)a->label[r];
+    double dot = row_dot(a, r, w);
+    double p = signum(dot) * -1.0;
+    double l = 1.0 - y * p;
+    h += l > 0.0 ? l : 0.0;
+    double activity = y * dot;         /* SparseSVM.scala:27 */
+    if (activity < 0.0) continue;      /* SparseSVM.scala:28: zerosLike, adds nothing */
+    for (int64_t p2 = a->row_ptr[r]; p2 < a->row_ptr[r + 1]; ++p2) {
+      int32_t j = a->col[p2];
+      double gv = filt(filt((double)a->val[p2]) * y); /* x * y: mapValues + constructor filter */
+      if (gv == 0.0) continue;
+      if (!mark[j]) { mark[j] = 1; touched[(*n_touched)++] = j; }
+      g[j] = filt(g[j] + gv);
+    }
+  }
+  if (hinge) *hinge = h;
+}
+
+typedef struct {
+  int32_t *touched;
+  uint8_t *mark;
+  double *g;
+} scratch_t;
+
+static int scratch_init(scratch_t *s, int32_t dim) {
+  s->touched = (int32_t *)malloc(sizeof(int32_t) * (size_t)dim);
+  s->mark = (uint8_t *)calloc((size_t)dim, 1);
+  s->g = (double *)calloc((size_t)dim, sizeof(double));
+  return (s->touched && s->mark && s->g) ? 0 : -1;
+}
+static void scratch_free(scratch_t *s) { free(s->touched); free(s->mark); free(s->g); }
+
+/* Worker request body on scratch: leaves r = regularize(sum, w) in s->g on the touched set. */
+static void worker_gradient(const dsgd_oracle_csr *a, double c, const double *w, const int32_t *idx, int64_t n,
+                            scratch_t *s, int32_t *n_touched, double *hinge) {
+  *n_touched = 0;
+  accumulate_batch(a, w, idx, n, s->g, s->touched, n_touched, s->mark, hinge);
+  /* regularize: grad + grad.valueLike(c): c lands on the keys that SURVIVED the filter (Vec.scala:65-75) */
+  if (c != 0.0 && fabs(c) > EPS) {
+    for (int32_t t = 0; t < *n_touched; ++t) {
+      int32_t j = s->touched[t];
+      if (s->g[j] != 0.0) s->g[j] = filt(s->g[j] + c);
+    }
+  }
+}
+
+static void scratch_reset(scratch_t *s, int32_t n_touched) {
+  for (int32_t t = 0; t < n_touched; ++t) { s->g[s->touched[t]] = 0.0; s->mark[s->touched[t]] = 0; }
+}
+
+int dsgd_oracle_gradient(const dsgd_oracle_csr *a, double lambda, const double *d, const double *w,
+                         const int32_t *idx, int64_t n, double *r_out, double *c_out) {
+  if (n <= 0) return -3; /* Vec.sum on an empty list throws (math/Vec.scala:129, quirk Q7) */
+  if (check_idx(a, idx, n)) return -2;
+  scratch_t s;
+  if (scratch_init(&s, a->dim)) return -1;
+  double c = reg_scalar(lambda, w, d, a->dim);
+  int32_t nt = 0;
+  worker_gradient(a, c, w, idx, n, &s, &nt, NULL);
+  memcpy(r_out, s.g, sizeof(double) * (size_t)a->dim);
+  if (c_out) *c_out = c;
+  scratch_free(&s);
+  return 0;
+}
+
+/* ---- synchronous step(s) ------------------------------------------------------------------------- */
+
+typedef struct {
+  const dsgd_oracle_csr *a;
+  const double *w;
+  double c;
+  const int32_t *idx;
+  int64_t n;
+  scratch_t *s;
+  int32_t n_touched;
+  double hinge;
+} worker_job;
+
+static void *worker_thread(void *p) {
+  worker_job *j = (worker_job *)p;
+  worker_gradient(j->a, j->c, j->w, j->idx, j->n, j->s, &j->n_touched, &j->hinge);
+  return NULL;
+}
+
+typedef struct {
+  int32_t K;
+  scratch_t *ws;      /* per worker */
+  scratch_t sum;      /* cross-worker sum, touched union */
+  worker_job *jobs;
+  pthread_t *tids;
+} step_ctx;
+
+static int step_ctx_init(step_ctx *sc, int32_t K, int32_t dim) {
+  sc->K = K;
+  sc->ws = (scratch_t *)calloc((size_t)K, sizeof(scratch_t));
+  sc->jobs = (worker_job *)calloc((size_t)K, sizeof(worker_job));
+  sc->tids = (pthread_t *)calloc((size_t)K, sizeof(pthread_t));
+  if (!sc->ws || !sc->jobs || !sc->tids) return -1;
+  for (int32_t k = 0; k < K; ++k)
+    if (scratch_init(&sc->ws[k], dim)) return -1;
+  return scratch_init(&sc->sum, dim);
+}
+static void step_ctx_free(step_ctx *sc) {
+  for (int32_t k = 0; k < sc->K; ++k) scratch_free(&sc->ws[k]);
+  scratch_free(&sc->sum);
+  free(sc->ws); free(sc->jobs); free(sc->tids);
+}
+
+static int one_sync_step(step_ctx *sc, const dsgd_oracle_csr *a, double lambda, const double *d, double *w,
+                         const int32_t *idx, const int32_t *counts, double lr, double *loss_out, int32_t threads) {
+  const int32_t K = sc->K;
+  /* every request carries the same weights, so c is the same for every worker (Master.scala:186-188) */
+  const double c = reg_scalar(lambda, w, d, a->dim);
+  int64_t off = 0, total = 0;
+  for (int32_t k = 0; k < K; ++k) {
+    if (counts[k] <= 0) return -3; /* empty slice => Vec.sum throws => fit fails (quirk Q7) */
+    worker_job *j = &sc->jobs[k];
+    j->a = a; j->w = w; j->c = c; j->idx = idx + off; j->n = counts[k]; j->s = &sc->ws[k];
+    off += counts[k]; total += counts[k];
+  }
+  if (threads > 1 && K > 1) {
+    for (int32_t k = 1; k < K; ++k) pthread_create(&sc->tids[k], NULL, worker_thread, &sc->jobs[k]);
+    worker_thread(&sc->jobs[0]);
+    for (int32_t k = 1; k < K; ++k) pthread_join(sc->tids[k], NULL);
+  } else {
+    for (int32_t k = 0; k < K; ++k) worker_thread(&sc->jobs[k]);
+  }
+  if (loss_out) {
+    double h = 0.0;
+    for (int32_t k = 0; k < K; ++k) h += sc->jobs[k].hinge;
+    *loss_out = lambda * norm_squared(w, a->dim) + h / (double)total; /* SparseSVM.scala:20-23 on w_before */
+  }
+  /* Vec.mean(res) = (r_0 + r_1 + ... ) / K  -- left fold in worker order, filter after every + (Master.scala:194) */
+  scratch_t *S = &sc->sum;
+  int32_t nts = 0;
+  for (int32_t k = 0; k < K; ++k) {
+    scratch_t *s = &sc->ws[k];
+    for (int32_t t = 0; t < sc->jobs[k].n_touched; ++t) {
+      int32_t j = s->touched[t];
+      if (s->g[j] == 0.0) continue;
+      if (!S->mark[j]) { S->mark[j] = 1; S->touched[nts++] = j; }
+      S->g[j] = filt(S->g[j] + s->g[j]);
+    }
+    scratch_reset(s, sc->jobs[k].n_touched);
+  }
+  /* w - learningRate * grad  (Master.scala:197): (sum / K) filtered, * lr filtered, subtraction filtered */
+  for (int32_t t = 0; t < nts; ++t) {
+    int32_t j = S->touched[t];
+    double mean = filt(S->g[j] / (double)K);
+    double step = filt(mean * lr);
+    w[j] = filt(w[j] - step);
+  }
+  scratch_reset(S, nts);
+  return 0;
+}
+
+int dsgd_oracle_sync_steps(const dsgd_oracle_csr *a, double lambda, const double *d, double *w,
+                           const int32_t *idx, const int32_t *counts, int32_t n_workers, double lr,
+                           int64_t n_steps, double *losses_out, int32_t threads) {
+  if (n_workers <= 0) return -3;
+  int64_t per_step = 0;
+  for (int32_t k = 0; k < n_workers; ++k) per_step += counts[k];
+  if (check_idx(a, idx, per_step * n_steps)) return -2;
+  step_ctx sc;
+  if (step_ctx_init(&sc, n_workers, a->dim)) return -1;
+  int rc = 0;
+  for (int64_t s = 0; s < n_steps && rc == 0; ++s)
+    rc = one_sync_step(&sc, a, lambda, d, w, idx + s * per_step, counts, lr, losses_out ? losses_out + s : NULL,
+                       threads);
+  step_ctx_free(&sc);
+  return rc;
+}
+
+int dsgd_oracle_sync_step(const dsgd_oracle_csr *a, double lambda, const double *d, double *w,
+                          const int32_t *idx, const int32_t *counts, int32_t n_workers, double lr,
+                          double *loss_out, int32_t threads) {
+  return dsgd_oracle_sync_steps(a, lambda, d, w, idx, counts, n_workers, lr, 1, loss_out, threads);
+}
+
+/* ---- asynchronous worker ------------------------------------------------------------------------- */
+
+/* delta on scratch: lr * regularize(mean, w_snapshot); returns touched count (core/Slave.scala:92-99). */
+static void async_delta_scratch(const dsgd_oracle_csr *a, double lambda, const double *d, const double *w,
+                                const int32_t *idx, int64_t n, double lr, scratch_t *s, int32_t *nt) {
+  *nt = 0;
+  accumulate_batch(a, w, idx, n, s->g, s->touched, nt, s->mark, NULL);
+  const double c = reg_scalar(lambda, w, d, a->dim);
+  const int add_c = (c != 0.0 && fabs(c) > EPS);
+  for (int32_t t = 0; t < *nt; ++t) {
+    int32_t j = s->touched[t];
+    double m = filt(s->g[j] / (double)n);       /* Vec.mean = sum / size (math/Vec.scala:139) */
+    if (m != 0.0 && add_c) m = filt(m + c);     /* regularize on the surviving keys */
+    s->g[j] = filt(m * lr);                     /* learningRate * (...) */
+  }
+}
+
+int dsgd_oracle_async_delta(const dsgd_oracle_csr *a, double lambda, const double *d, const double *w_snapshot,
+                            const int32_t *idx, int64_t n, double lr, double *delta_out) {
+  if (n <= 0) return -3;
+  if (check_idx(a, idx, n)) return -2;
+  scratch_t s;
+  if (scratch_init(&s, a->dim)) return -1;
+  int32_t nt = 0;
+  async_delta_scratch(a, lambda, d, w_snapshot, idx, n, lr, &s, &nt);
+  memcpy(delta_out, s.g, sizeof(double) * (size_t)a->dim);
+  scratch_free(&s);
+  return 0;
+}
+
+int dsgd_oracle_async_run(const dsgd_oracle_csr *a, double lambda, const double *d, double *w,
+                          const int32_t *idx, int32_t batch, int64_t n_updates, double lr) {
+  if (batch <= 0) return -3;
+  if (check_idx(a, idx, (int64_t)batch * n_updates)) return -2;
+  scratch_t s;
+  if (scratch_init(&s, a->dim)) return -1;
+  for (int64_t u = 0; u < n_updates; ++u) {
+    int32_t nt = 0;
+    async_delta_scratch(a, lambda, d, w, idx + u * batch, batch, lr, &s, &nt);
+    for (int32_t t = 0; t < nt; ++t) {          /* weights.transform(_ - gradUpdate)  (Slave.scala:101) */
+      int32_t j = s.touched[t];
+      w[j] = filt(w[j] - s.g[j]);
+    }
+    scratch_reset(&s, nt);
+  }
+  scratch_free(&s);
+  return 0;
+}
+
+/* ---- dimSparsity ---------------------------------------------------------------------------------- */
+
+int dsgd_oracle_dim_sparsity(const dsgd_oracle_csr *a, int64_t n_train, double *d_out) {
+  if (n_train < 0 || n_train > a->n_rows) return -2;
+  int64_t *df = (int64_t *)calloc((size_t)a->dim, sizeof(int64_t));
+  if (!df) return -1;
+  for (int64_t p = a->row_ptr[0]; p < a->row_ptr[n_train]; ++p)
+    if (fabs((double)a->val[p]) > EPS) df[a->col[p]] += 1; /* keys of the row's map (Main.scala:57-60) */
+  for (int32_t c = 0; c < a->dim; ++c) {
+    /* reference d key c holds 1/(df_c + 1) (Main.scala:61-63); weight column c carries reference key c+1,
+     * so in the dot product it meets d key c+1 (quirk Q3). */
+    int32_t src = c + 1;
+    d_out[c] = (src < a->dim && df[src] != 0) ? 1.0 / ((double)df[src] + 1.0) : 0.0;
+  }
+  free(df);
+  return 0;
+}
