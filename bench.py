@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- SGD samples/sec on RCV1-shaped synthetic sparse data (BASELINE.json's metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch 256] [--mode sync]
+
+Workload (BASELINE.json configs[1]/[2]): sync mode, RCV1-shaped synthetic rows (47 236 features, 700 000
+rows of which the first 80 % train -- Main.scala:52 --, ~0.2 % non-zeros), batch 256 per GPU, lambda 1e-5,
+lr 0.5 (resources/application.conf).  One bench "step" is one pass of the hot path over one epoch-sized
+slice of the reference's fit loop (core/Master.scala:179): SGD_STEPS consecutive mini-batch steps
+(gradient -> aggregate -> update), every one on weights produced by the previous one.  samples/sec counts
+the samples all GPUs consumed.
+
+Numbers on the JSON line:
+  value        device-resident: sample ids staged in HBM before the timed region; CUDA events on the
+               launch stream; max over ranks.
+  e2e          the same work through the public C-ABI call with HOST buffers (dsgd_sync_steps): per bench
+               step the sample ids go host->device from pinned memory and the per-batch losses come back.
+  roofline     the gradient kernel: algorithmic bytes (8*nnz + 16 per sample) per launch /
+               its mean duration (CUDA events around sampled launches), against MEASURED_PEAKS.json.
+  cpu_baseline the fp64 CPU oracle (array restatement of the Scala path -- the reference itself needs a
+               JVM, which this image lacks) timed on this host on a bounded sample of the same workload.
+--impl reference times that CPU restatement as the reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DIM = 47236
+N_ROWS = 700_000
+TRAIN_FRAC = 0.8
+LAMBDA = 1e-5
+LR = 0.5
+METRIC = "sgd_samples_per_sec"
+UNIT = "samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="samples per GPU per SGD step")
+    ap.add_argument("--mode", default="sync", choices=["sync"])
+    ap.add_argument("--rows", type=int, default=N_ROWS)
+    ap.add_argument("--sgd-steps", type=int, default=0, help="SGD steps per bench step (0: one epoch at 1 worker)")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_data(args):
+    from distributed_sgd_b200.utils import synthetic_rcv1
+    data = synthetic_rcv1(n_rows=args.rows, dim=DIM, seed=args.seed)
+    n_train = int(data.n_rows * TRAIN_FRAC)  # Main.scala:52
+    return data, n_train
+
+
+def draw_batches(rng, lo: int, hi: int, batch: int, n_steps: int) -> np.ndarray:
+    """n_steps uniform draws without replacement of `batch` rows from [lo, hi) -- what a slice of a freshly
+    shuffled worker range is (core/Master.scala:184-187)."""
+    out = np.empty((n_steps, batch), dtype=np.int32)
+    for s in range(n_steps):
+        out[s] = lo + rng.choice(hi - lo, size=batch, replace=False)
+    return out
+
+
+def cpu_leg(data, n_train, d, batch, workers, budget_s, threads, seed):
+    """Times the oracle's sync steps (K logical workers) on a bounded sample; returns (samples/s, description)."""
+    from oracle.oracle import Oracle
+    orc = Oracle(data.row_ptr, data.col, data.val, data.label, data.dim, LAMBDA)
+    orc.set_dim_sparsity(d)
+    rng = np.random.default_rng(seed + 17)
+    per = n_train // workers
+    probe = 40
+    def run(n_steps, w):
+        idx = np.concatenate([draw_batches(rng, k * per, (k + 1) * per, batch, n_steps)[:, None, :] for k in range(workers)],
+                             axis=1).reshape(-1)
+        t = time.perf_counter()
+        w, _ = orc.sync_steps(w, idx, [batch] * workers, LR, n_steps=n_steps, threads=threads)
+        return time.perf_counter() - t, w
+    dt, w = run(probe, np.zeros(data.dim))
+    n_steps = int(max(probe, min(20000, budget_s / max(dt / probe, 1e-9))))
+    dt, w = run(n_steps, w)
+    return n_steps * batch * workers / dt, f"{n_steps} sync SGD steps x {workers} worker(s) x batch {batch}, {dt:.1f} s"
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and "WORLD_SIZE" in os.environ:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        data, n_train = make_data(args)
+        from oracle.oracle import Oracle
+        d = Oracle(data.row_ptr, data.col, data.val, data.label, data.dim, LAMBDA).dim_sparsity(n_train)
+        workers = args.gpus
+        threads = min(workers, os.cpu_count() or 1)
+        vals = []
+        desc = ""
+        for i in range(args.warmup + args.steps):
+            v, desc = cpu_leg(data, n_train, d, args.batch, workers, max(2.0, 60.0 / (args.warmup + args.steps)), threads,
+                              args.seed + i)
+            if i >= args.warmup:
+                vals.append(v)
+        value = float(np.mean(vals))
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"sync SGD, RCV1-shaped synthetic ({DIM} feats, {args.rows} rows, ~0.2% nnz), batch "
+                                   f"{args.batch} per worker, {workers} worker(s)", "mode": "sync", "batch": args.batch},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": desc + " per step; fp64 array restatement of the Scala path (no JVM in this image)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from distributed_sgd_b200.core import Group
+    from distributed_sgd_b200.native import NativeCtx
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", local_rank))
+    group = Group()
+
+    data, n_train = make_data(args)
+    ctx = NativeCtx(local_rank, data.dim, LAMBDA, rank=rank, world=world)
+    ctx.load_csr(data.row_ptr, data.col, data.val, data.label)   # every slave holds every row (quirk Q13)
+    d = ctx.compute_dim_sparsity(n_train)
+    if world > 1:
+        uid = NativeCtx.comm_unique_id() if rank == 0 else b""
+        ctx.comm_init(group.broadcast_bytes(uid, 0))
+
+    B = args.batch
+    S = args.sgd_steps or -(-n_train // B)            # one epoch of the 1-worker fit loop: ceil(560000 / 256) = 2188
+    per = n_train // world                             # SplitStrategy.vanilla: contiguous range per worker
+    lo, hi = rank * per, (rank + 1) * per
+    rng = np.random.default_rng(args.seed * 1000 + rank)
+    total_steps = args.warmup + args.steps
+    samples_np = draw_batches(rng, lo, hi, B, S * total_steps).reshape(total_steps, S * B)
+    pinned = torch.empty((total_steps, S * B), dtype=torch.int32).pin_memory()
+    pinned.numpy()[:] = samples_np
+    alg_bytes_per_step = [data.algorithmic_bytes(samples_np[i]) for i in range(total_steps)]
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        group.barrier()
+
+    # ---- leg 1: device-resident (value) ---------------------------------------------------------------
+    ctx.set_weights(np.zeros(data.dim))
+    ctx.stage_samples(samples_np.reshape(-1))
+    for i in range(args.warmup):
+        ctx.sync_steps_staged(i * S * B, B, S, LR, want_losses=True)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = ctx.launch_count()
+    ctx.timer_start()
+    for i in range(args.warmup, total_steps):
+        ctx.sync_steps_staged(i * S * B, B, S, LR, want_losses=True)
+    ms = ctx.timer_stop()
+    launches = ctx.launch_count() - launches0
+    barrier()
+    clock_info = clocks.stop() if rank == 0 else None
+    ms = group.all_reduce_max(ms)
+    samples_total = args.steps * S * B * world
+    value = samples_total / (ms * 1e-3)
+    w_after = ctx.get_weights()
+    last_losses = ctx.read_losses(S)
+
+    # ---- leg 2: end to end through the C-ABI call with host buffers (e2e) --------------------------------
+    ctx.set_weights(np.zeros(data.dim))
+    for i in range(args.warmup):
+        ctx.sync_steps(pinned[i].numpy(), B, S, LR, want_losses=True)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.warmup, total_steps):
+        losses_host = ctx.sync_steps(pinned[i].numpy(), B, S, LR, want_losses=True)
+    ctx.synchronize()
+    e2e_s = group.all_reduce_max(time.perf_counter() - t0)
+    barrier()
+    e2e_value = samples_total / e2e_s
+    # both legs walked the same batches from the same start: identical results expected
+    same = bool(np.array_equal(ctx.get_weights(), w_after)) if world == 1 else None
+
+    # ---- leg 3: mean duration of the dominant kernel (gradient) over the same work -----------------------
+    ctx.set_weights(np.zeros(data.dim))
+    ctx.profile_begin(sample_every=8)
+    for i in range(args.warmup, total_steps):
+        ctx.sync_steps_staged(i * S * B, B, S, LR, want_losses=False)
+    k_ms, k_n = ctx.profile_end()
+    barrier()
+    hbm_peak, peak_src = peaks()
+    alg_per_launch = float(np.mean(alg_bytes_per_step[args.warmup:])) / S
+    achieved = alg_per_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    step_frac = (float(np.mean(alg_bytes_per_step[args.warmup:])) * args.steps / (ms * 1e-3) / 1e9) / hbm_peak
+
+    # ---- leg 4: CPU baseline on this host (rank 0, N = 1 only) -------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1:
+        v, desc = cpu_leg(data, n_train, d, B, 1, args.cpu_seconds, 1, args.seed)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": desc + "; fp64 array restatement of the Scala path, one thread per worker like the reference "
+                                "(core/Slave.scala:142); host has %d cores" % (os.cpu_count() or 0)}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"sync SGD (configs[{1 if world == 1 else 2}]): RCV1-shaped synthetic, {DIM} feats, "
+                                   f"{args.rows} rows ({n_train} train), ~0.2% nnz, batch {B} per GPU",
+                       "mode": "sync", "batch_per_gpu": B, "sgd_steps_per_bench_step": S, "lambda": LAMBDA, "lr": LR,
+                       "parallelism": f"dp{world}", "l2": "inputs (train CSR 0.43 GB) larger than the 126 MB L2; rows drawn at random",
+                       "values": "fp32", "state": "fp64"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(S * B * 4), "d2h_bytes_per_step": int(S * 8),
+                    "api": "dsgd_sync_steps (C ABI, pinned host buffers)", "matches_device_leg": same},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_rows<scatter> (gradient)", "achieved": achieved, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_per_launch, "kernel_ms": k_ms, "launches_sampled": int(k_n),
+                         "whole_step_frac": step_frac},
+            "cpu_baseline": cpu,
+            "clocks": clock_info,
+            "final_batch_loss": float(last_losses[-1]),
+        }
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

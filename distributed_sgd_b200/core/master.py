@@ -1,0 +1,202 @@
+"""core/Master.scala, MasterSync.scala, MasterAsync.scala -- the coordination loop.
+
+The reference master is a separate process that shuffles index ranges, fans `gradient` RPCs out to K
+slaves, averages the replies and updates the weights (core/Master.scala:120-218).  Here the master
+logic runs SPMD: every rank executes the same loop with the same seed, so all ranks draw the same
+batches; each rank feeds ITS slice to its GPU and the replies are summed on the devices (NCCL over
+NVLink inside libdsgd.so).  Weights never leave the GPUs during `fit`.  What remains on the host is
+control flow over a handful of scalars per epoch (losses, accuracies, the stopping rule).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+from ..ml import split_strategy as SplitStrategy  # noqa: N812
+from ..ml.grad_state import GradState
+from ..ml.sparse_svm import SparseSVM
+from ..native import NativeCtx
+from ..utils.dataset import Data
+from .group import Group
+from .slave import Slave
+
+EarlyStopping = Callable[[Sequence[float]], bool]
+Split = Callable[[int, int], List[range]]
+
+
+class Master:
+    """core/Master.scala:19-255 (abstract).  `Master.apply` (Master.scala:259-271) is `Master.create`."""
+
+    def __init__(self, node: int, data: Data, test_data: Data, model: SparseSVM, expected_node_count: int, *,
+                 slave: Slave, group: Optional[Group] = None, seed: int = 0, log: Optional[Callable[[str], None]] = None):
+        self.node, self.model, self.expected_node_count = node, model, expected_node_count
+        self.n_train, self.n_test = data.n_rows, test_data.n_rows
+        self.dim = data.dim
+        self.slave = slave
+        self.ctx: NativeCtx = slave.ctx
+        self.group = group or Group()
+        if self.group.world != slave.world:
+            raise ValueError("process group size and Slave world size differ")
+        if slave.n_test != self.n_test or slave.n_train != self.n_train:
+            raise ValueError("the Slave must hold the same train/test rows as the Master")
+        # Random.setSeed(0) (Main.scala:32): one stream, identical on every rank
+        self.rng = np.random.default_rng(seed)
+        self.log = log or (lambda s: None)
+        if self.group.world > 1 and not slave.is_async:
+            uid = NativeCtx.comm_unique_id() if self.group.rank == 0 else b""
+            self.ctx.comm_init(self.group.broadcast_bytes(uid, 0))
+
+    @staticmethod
+    def create(node, data, test_data, model, is_async, node_count, **kw) -> "Master":
+        """Master.apply (core/Master.scala:259-271)."""
+        return (MasterAsync if is_async else MasterSync)(node, data, test_data, model, node_count, **kw)
+
+    # ---- evaluation ------------------------------------------------------------------------------------
+    def _eval_rows(self, weights, begin: int, end: int):
+        """Row-sharded pass: each rank evaluates a contiguous share, integer counters are summed."""
+        W, r = self.group.world, self.group.rank
+        n = end - begin
+        lo, hi = begin + (n * r) // W, begin + (n * (r + 1)) // W
+        if hi > lo:
+            h, c, n2 = self.ctx.eval_counts(lo, hi, weights)
+        else:
+            h, c, n2 = 0, 0, 0.0
+        hs, cs = self.group.all_reduce_sum([h, c])
+        n2 = self.group.all_reduce_max(n2)  # identical on every rank that evaluated; 0 on idle ranks
+        return self.model.lam * n2 + hs / n, cs / n
+
+    def local_loss(self, weights=None, test_data: bool = False) -> float:
+        """Master.localLoss (core/Master.scala:105-107)."""
+        b, e = (self.n_train, self.n_train + self.n_test) if test_data else (0, self.n_train)
+        return self._eval_rows(weights, b, e)[0]
+
+    def local_accuracy(self, weights=None, test_data: bool = False) -> float:
+        """Master.localAccuracy (core/Master.scala:100-103)."""
+        b, e = (self.n_train, self.n_train + self.n_test) if test_data else (0, self.n_train)
+        return self._eval_rows(weights, b, e)[1]
+
+    def local_loss_accuracy(self, weights=None, test_data: bool = False):
+        b, e = (self.n_train, self.n_train + self.n_test) if test_data else (0, self.n_train)
+        return self._eval_rows(weights, b, e)
+
+    def predict(self, weights, split_strategy: Split = SplitStrategy.vanilla) -> dict:
+        """Master.predict (core/Master.scala:61-75): idx -> prediction over the training rows; each worker
+        answers for its split group."""
+        groups = split_strategy(self.n_train, self.group.world)
+        mine = groups[self.group.rank] if self.group.rank < len(groups) else range(0)
+        idx = np.fromiter(mine, dtype=np.int32, count=len(mine))
+        preds = self.slave.forward(idx, weights) if len(idx) else np.zeros(0)
+        import pickle
+        parts = self.group.all_gather_bytes(pickle.dumps((idx, preds)))
+        out = {}
+        for blob in parts:
+            i, p = pickle.loads(blob)
+            out.update(zip(i.tolist(), p.tolist()))
+        return out
+
+    def distributed_accuracy(self, weights, split_strategy: Split = SplitStrategy.vanilla) -> float:
+        """Master.distributedAccuracy (core/Master.scala:77-85)."""
+        return self._distributed(weights, split_strategy)[1]
+
+    def distributed_loss(self, weights, split_strategy: Split = SplitStrategy.vanilla) -> float:
+        """Master.distributedLoss (core/Master.scala:87-98)."""
+        return self._distributed(weights, split_strategy)[0]
+
+    def _distributed(self, weights, split_strategy: Split):
+        # same numbers as predict + host-side counting, without shipping N predictions around
+        groups = split_strategy(self.n_train, self.group.world)
+        mine = groups[self.group.rank] if self.group.rank < len(groups) else range(0)
+        if len(mine):
+            h, c, n2 = self.ctx.eval_counts(mine.start, mine.stop, weights)
+        else:
+            h, c, n2 = 0, 0, 0.0
+        hs, cs, ns = self.group.all_reduce_sum([h, c, len(mine)])
+        n2 = self.group.all_reduce_max(n2)
+        return self.model.lam * n2 + hs / ns, cs / ns
+
+
+class MasterSync(Master):
+    """core/MasterSync.scala + the sync `fit` of core/Master.scala:120-218."""
+
+    def update_grad(self, grad_update):  # MasterSync.scala:16-17
+        raise NotImplementedError("Synchronous master cannot perform async operation update grad")
+
+    def draw_epoch(self, groups: List[range], batch_size: int, virtual_workers: int = 1):
+        """Sample ids of one epoch: for every step (`0 until maxSamples by batchSize`, Master.scala:179) and
+        every worker a fresh shuffle of its range, sliced at [batch, batch + batchSize) (Master.scala:
+        184-187, quirk Q5).  A slice of a fresh permutation is a uniform draw without replacement of
+        min(batchSize, len - batch) elements.  Returns a list of steps, each a list of per-worker arrays."""
+        max_samples = max(len(g) for g in groups)
+        steps = []
+        for batch in range(0, max_samples, batch_size):
+            per_worker = []
+            for g in groups:
+                m = max(0, min(batch_size, len(g) - batch))
+                per_worker.append((g.start + self.rng.choice(len(g), size=m, replace=False)).astype(np.int32))
+            steps.append(per_worker)
+        return steps
+
+    def fit(self, initial_weights: np.ndarray, max_epochs: int, batch_size: int, learning_rate: float,
+            stopping_criterion: EarlyStopping, split_strategy: Split = SplitStrategy.vanilla, *,
+            virtual_workers: int = 1, on_epoch: Optional[Callable[[int, dict], None]] = None) -> GradState:
+        """Master.fit (core/Master.scala:120-218).
+
+        virtual_workers (extension): logical reference workers per GPU, so that `node-count` can exceed the
+        number of GPUs (K = world * virtual_workers).
+        """
+        W, r, V = self.group.world, self.group.rank, virtual_workers
+        K = W * V
+        groups = split_strategy(self.n_train, K)             # Master.scala:136 (may hold fewer than K groups)
+        k_total = len(groups)                                 # workers.zip(split): extra workers get no request
+        my_groups = [k for k in range(r * V, (r + 1) * V) if k < k_total]
+        self.ctx.set_weights(initial_weights)
+        state = GradState.start_state(np.asarray(initial_weights, dtype=np.float64))
+        losses: List[float] = []
+        accs: List[float] = []
+        test_losses: List[float] = []
+        test_accs: List[float] = []
+        self.step_losses: List[np.ndarray] = []
+        epoch = 0
+        while True:
+            if losses:
+                self.log(f"loss after epoch {epoch}: {losses[0]}")
+                self.log(f"acc after epoch {epoch}: {accs[0]}")
+            if epoch >= max_epochs or stopping_criterion(test_losses):   # Master.scala:154,166
+                self.log("Reached max number of epochs: stopping computation" if epoch >= max_epochs
+                         else "Converged to target: stopping computation")
+                self.history = {"losses": losses[::-1], "test_losses": test_losses[::-1], "accs": accs[::-1],
+                                "test_accs": test_accs[::-1]}
+                # `losses.head` throws on an empty list in the reference (max_epochs == 0)
+                return state.finish(losses[0])
+            steps = self.draw_epoch(groups, batch_size)
+            # consecutive steps with identical per-worker counts go to the device in one call
+            i = 0
+            while i < len(steps):
+                shape = [len(steps[i][k]) for k in my_groups]
+                j = i
+                while j < len(steps) and [len(steps[j][k]) for k in my_groups] == shape:
+                    j += 1
+                if any(len(steps[i][k]) == 0 for k in range(k_total)):
+                    raise ValueError("Cannot sum an empty list of vectors")  # Vec.scala:129 via Master.scala:187 (Q7)
+                flat = (np.concatenate([np.concatenate([steps[s][k] for k in my_groups]) for s in range(i, j)])
+                        if my_groups else np.zeros(0, dtype=np.int32))
+                self.ctx.set_workers(shape, k_total)
+                ls = self.ctx.sync_steps(flat, int(sum(shape)), j - i, learning_rate, want_losses=True)
+                self.step_losses.append(ls)
+                i = j
+            w = None  # evaluate the resident weights
+            tl, ta = self.local_loss_accuracy(w, test_data=False)        # Master.scala:206-207
+            vl, va = self.local_loss_accuracy(w, test_data=True)         # Master.scala:208-209
+            losses.insert(0, tl); accs.insert(0, ta); test_losses.insert(0, vl); test_accs.insert(0, va)
+            epoch += 1
+            state = state.replace_grad(self.ctx.get_weights())          # Master.scala:205
+            if on_epoch:
+                on_epoch(epoch, {"loss": tl, "acc": ta, "test_loss": vl, "test_acc": va})
+
+
+class MasterAsync(Master):
+    """core/MasterAsync.scala -- filled in with the async device path."""
+
+    def fit(self, *a, **kw) -> GradState:
+        raise NotImplementedError("async fit is not built yet")

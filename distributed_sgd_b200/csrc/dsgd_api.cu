@@ -1,0 +1,727 @@
+// dsgd_api.cu -- the C ABI declared in include/dsgd.h over the sm_100a kernels in dsgd_kernels.cuh.
+// There is no CPU path in this library: without a usable GPU dsgd_create fails with DSGD_ERR_CUDA.
+#include "../../include/dsgd.h"
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dsgd_kernels.cuh"
+
+using namespace dsgd;
+
+struct dsgd_ctx {
+  int device = 0;
+  int32_t dim = 0;
+  double lambda = 0.0;
+  int rank = 0, world = 1;
+  uint32_t flags = 0;
+  int sm_count = 0;
+  std::string dev_name;
+
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t launches = 0;
+
+  // rows
+  int64_t n_rows = 0, nnz = 0, n_pairs = 0;
+  uint32_t *rp16 = nullptr;
+  uint2 *pairs = nullptr;
+  int8_t *label = nullptr;
+
+  // state (fp64, L2 resident) -- g has dim + 2 slots (hinge sum and batch size ride in the allreduce)
+  double *w = nullptr, *g = nullptr, *d = nullptr, *w_req = nullptr;
+  float *w32 = nullptr;
+  double *scal = nullptr;
+  unsigned long long *cnt = nullptr;
+  double *partial = nullptr;  // 2 doubles per k_update block
+  double *out2 = nullptr;     // loss, acc, hinge sum, correct count, ||w||^2
+  double *gsum = nullptr;     // master-side running sum of worker replies (dim + 2)
+  std::vector<int32_t> worker_counts;  // logical workers on this ctx (empty: one worker, whole slice)
+  int32_t n_local = 1, k_total = 0;    // k_total == 0: world
+  bool have_d = false;
+
+  // staged sample indices / per-step losses
+  int32_t *samples = nullptr;
+  int64_t samples_cap = 0, samples_n = 0;
+  double *losses = nullptr;
+  int64_t losses_cap = 0;
+  double *preds = nullptr;
+  int64_t preds_cap = 0;
+
+  ncclComm_t comm = nullptr;
+
+  // sampled per-launch timing of the gradient kernel
+  int32_t prof_every = 0;
+  int64_t prof_seen = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  size_t prof_used = 0;
+
+  mutable std::string err;
+  mutable std::string info;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(const dsgd_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf; else g_create_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      return fail(ctx, DSGD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                  __LINE__);                                                                            \
+  } while (0)
+#define NC(call)                                                                                         \
+  do {                                                                                                   \
+    ncclResult_t r_ = (call);                                                                            \
+    if (r_ != ncclSuccess)                                                                               \
+      return fail(ctx, DSGD_ERR_NCCL, "%s failed: %s (%s:%d)", #call, ncclGetErrorString(r_), __FILE__, \
+                  __LINE__);                                                                             \
+  } while (0)
+#define NEED(cond, code, ...) \
+  do {                        \
+    if (!(cond)) return fail(ctx, code, __VA_ARGS__); \
+  } while (0)
+#define LAUNCHED() (++ctx->launches)
+
+// returns the event pair to bracket this gradient launch with, or nullptr
+static std::pair<cudaEvent_t, cudaEvent_t> *prof_slot(dsgd_ctx *ctx) {
+  if (ctx->prof_every <= 0) return nullptr;
+  if ((ctx->prof_seen++ % ctx->prof_every) != 0) return nullptr;
+  if (ctx->prof_used == ctx->prof_events.size()) {
+    if (ctx->prof_events.size() >= 8192) return nullptr;
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return nullptr;
+    ctx->prof_events.emplace_back(a, b);
+  }
+  return &ctx->prof_events[ctx->prof_used++];
+}
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- lifecycle ---------------------------------------------------------------------------------------
+
+extern "C" int dsgd_create(dsgd_ctx **out, int device, int32_t dim, double lambda, int rank, int world, uint32_t flags) {
+  dsgd_ctx *ctx = nullptr;
+  if (!out) return fail(nullptr, DSGD_ERR_INVALID, "dsgd_create: out is NULL");
+  *out = nullptr;
+  if (dim <= 0) return fail(nullptr, DSGD_ERR_INVALID, "dsgd_create: dim must be positive (got %d)", dim);
+  if (world <= 0 || rank < 0 || rank >= world)
+    return fail(nullptr, DSGD_ERR_INVALID, "dsgd_create: bad rank/world %d/%d", rank, world);
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return fail(nullptr, DSGD_ERR_CUDA, "dsgd_create: no usable CUDA device (%s); this library has no CPU path",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n_dev)
+    return fail(nullptr, DSGD_ERR_INVALID, "dsgd_create: device %d out of range [0,%d)", device, n_dev);
+  ctx = new dsgd_ctx();
+  ctx->device = device; ctx->dim = dim; ctx->lambda = lambda; ctx->rank = rank; ctx->world = world; ctx->flags = flags;
+  auto bail = [&](const char *what, cudaError_t err) {
+    int rc = fail(nullptr, DSGD_ERR_CUDA, "dsgd_create: %s: %s", what, cudaGetErrorString(err));
+    delete ctx;
+    return rc;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->dev_name = prop.name;
+  if (prop.major != 10)
+    { int rc = fail(nullptr, DSGD_ERR_CUDA, "dsgd_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, prop.major, prop.minor); delete ctx; return rc; }
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  ctx->stream = ctx->own_stream;
+  if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("event", e);
+  if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("event", e);
+  const size_t vd = sizeof(double) * (size_t)(dim + 2);
+  const int upd_blocks = cdiv(dim, 256);
+  if ((e = cudaMalloc(&ctx->w, vd)) != cudaSuccess) return bail("cudaMalloc w", e);
+  if ((e = cudaMalloc(&ctx->g, vd)) != cudaSuccess) return bail("cudaMalloc g", e);
+  if ((e = cudaMalloc(&ctx->d, vd)) != cudaSuccess) return bail("cudaMalloc d", e);
+  if ((e = cudaMalloc(&ctx->w_req, vd)) != cudaSuccess) return bail("cudaMalloc w_req", e);
+  if ((e = cudaMalloc(&ctx->w32, sizeof(float) * (size_t)(dim + 2))) != cudaSuccess) return bail("cudaMalloc w32", e);
+  if ((e = cudaMalloc(&ctx->scal, sizeof(double) * kNumScal)) != cudaSuccess) return bail("cudaMalloc scal", e);
+  if ((e = cudaMalloc(&ctx->cnt, sizeof(unsigned long long) * kNumCnt)) != cudaSuccess) return bail("cudaMalloc cnt", e);
+  if ((e = cudaMalloc(&ctx->partial, sizeof(double) * 2 * (size_t)upd_blocks)) != cudaSuccess) return bail("cudaMalloc partial", e);
+  if ((e = cudaMalloc(&ctx->out2, sizeof(double) * 8)) != cudaSuccess) return bail("cudaMalloc out2", e);
+  if ((e = cudaMalloc(&ctx->gsum, vd)) != cudaSuccess) return bail("cudaMalloc gsum", e);
+  cudaMemsetAsync(ctx->gsum, 0, vd, ctx->stream);
+  cudaMemsetAsync(ctx->w, 0, vd, ctx->stream);
+  cudaMemsetAsync(ctx->g, 0, vd, ctx->stream);
+  cudaMemsetAsync(ctx->d, 0, vd, ctx->stream);
+  cudaMemsetAsync(ctx->w_req, 0, vd, ctx->stream);
+  cudaMemsetAsync(ctx->w32, 0, sizeof(float) * (size_t)(dim + 2), ctx->stream);
+  cudaMemsetAsync(ctx->scal, 0, sizeof(double) * kNumScal, ctx->stream);
+  cudaMemsetAsync(ctx->cnt, 0, sizeof(unsigned long long) * kNumCnt, ctx->stream);
+  if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail("init memset", e);
+  *out = ctx;
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_destroy(dsgd_ctx *ctx) {
+  if (!ctx) return DSGD_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  if (ctx->comm) ncclCommDestroy(ctx->comm);
+  void *ptrs[] = {ctx->rp16, ctx->pairs, ctx->label, ctx->w, ctx->g, ctx->d, ctx->w_req, ctx->w32, ctx->scal,
+                  ctx->cnt, ctx->partial, ctx->out2, ctx->gsum, ctx->samples, ctx->losses, ctx->preds};
+  for (void *p : ptrs) if (p) cudaFree(p);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (auto &pe : ctx->prof_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return DSGD_OK;
+}
+
+extern "C" const char *dsgd_last_error(const dsgd_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+extern "C" const char *dsgd_info(const dsgd_ctx *ctx) {
+  if (!ctx) return "{}";
+  char buf[512];
+  snprintf(buf, sizeof buf,
+           "{\"device\": %d, \"name\": \"%s\", \"sm_count\": %d, \"arch\": \"sm_100a\", \"dim\": %d, \"rank\": %d, "
+           "\"world\": %d, \"n_rows\": %lld, \"nnz\": %lld, \"state_dtype\": \"f64\", \"value_dtype\": \"f32\"}",
+           ctx->device, ctx->dev_name.c_str(), ctx->sm_count, ctx->dim, ctx->rank, ctx->world, (long long)ctx->n_rows,
+           (long long)ctx->nnz);
+  ctx->info = buf;
+  return ctx->info.c_str();
+}
+
+extern "C" int dsgd_set_stream(dsgd_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_synchronize(dsgd_ctx *ctx) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_timer_start(dsgd_ctx *ctx) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventRecord(ctx->ev0, ctx->stream));
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_timer_stop(dsgd_ctx *ctx, float *elapsed_ms) {
+  if (!ctx || !elapsed_ms) return DSGD_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventRecord(ctx->ev1, ctx->stream));
+  CU(cudaEventSynchronize(ctx->ev1));
+  CU(cudaEventElapsedTime(elapsed_ms, ctx->ev0, ctx->ev1));
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_launch_count(const dsgd_ctx *ctx, int64_t *count) {
+  if (!ctx || !count) return DSGD_ERR_INVALID;
+  *count = ctx->launches;
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_profile_begin(dsgd_ctx *ctx, int32_t sample_every) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(sample_every > 0, DSGD_ERR_INVALID, "dsgd_profile_begin: sample_every must be positive");
+  ctx->prof_every = sample_every;
+  ctx->prof_seen = 0;
+  ctx->prof_used = 0;
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_profile_end(dsgd_ctx *ctx, float *mean_ms, int64_t *n_sampled) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  double tot = 0.0;
+  for (size_t i = 0; i < ctx->prof_used; ++i) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ctx->prof_events[i].first, ctx->prof_events[i].second));
+    tot += ms;
+  }
+  if (mean_ms) *mean_ms = ctx->prof_used ? (float)(tot / (double)ctx->prof_used) : 0.f;
+  if (n_sampled) *n_sampled = (int64_t)ctx->prof_used;
+  ctx->prof_every = 0;
+  ctx->prof_used = 0;
+  return DSGD_OK;
+}
+
+// ---- data --------------------------------------------------------------------------------------------
+
+extern "C" int dsgd_load_csr(dsgd_ctx *ctx, int64_t n_rows, int64_t nnz, const int64_t *row_ptr, const int32_t *col,
+                             const float *val, const int8_t *label) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(n_rows > 0 && nnz >= 0 && row_ptr && label && (nnz == 0 || (col && val)), DSGD_ERR_INVALID,
+       "dsgd_load_csr: bad arguments (n_rows=%lld nnz=%lld)", (long long)n_rows, (long long)nnz);
+  NEED(n_rows < (int64_t)INT32_MAX, DSGD_ERR_INVALID, "dsgd_load_csr: sample ids are int32; n_rows too large");
+  NEED(row_ptr[0] == 0 && row_ptr[n_rows] == nnz, DSGD_ERR_INVALID, "dsgd_load_csr: row_ptr[0] != 0 or row_ptr[n] != nnz");
+  // validate + build 16-byte window offsets (host side of the data load, like Dataset.rcv1 building the Map per row)
+  std::vector<uint32_t> rp16((size_t)n_rows + 1);
+  uint64_t acc = 0;
+  for (int64_t r = 0; r < n_rows; ++r) {
+    const int64_t len = row_ptr[r + 1] - row_ptr[r];
+    NEED(len >= 0, DSGD_ERR_INVALID, "dsgd_load_csr: row_ptr not monotone at row %lld", (long long)r);
+    NEED(label[r] == 1 || label[r] == -1, DSGD_ERR_INVALID, "dsgd_load_csr: label of row %lld is %d, expected +1/-1",
+         (long long)r, (int)label[r]);
+    rp16[(size_t)r] = (uint32_t)acc;
+    acc += (uint64_t)((len + 1) / 2);
+    NEED(acc < (1ull << 32), DSGD_ERR_INVALID, "dsgd_load_csr: too many non-zeros for 32-bit window offsets");
+  }
+  rp16[(size_t)n_rows] = (uint32_t)acc;
+  for (int64_t k = 0; k < nnz; ++k)
+    NEED(col[k] >= 0 && col[k] < ctx->dim, DSGD_ERR_RANGE, "dsgd_load_csr: column %d at position %lld outside [0,%d)",
+         col[k], (long long)k, ctx->dim);
+  CU(cudaSetDevice(ctx->device));
+  for (void *p : {(void *)ctx->rp16, (void *)ctx->pairs, (void *)ctx->label}) if (p) CU(cudaFree(p));
+  ctx->rp16 = nullptr; ctx->pairs = nullptr; ctx->label = nullptr;
+  const int64_t n_pairs = (int64_t)acc * 2;
+  CU(cudaMalloc(&ctx->rp16, sizeof(uint32_t) * ((size_t)n_rows + 1)));
+  CU(cudaMalloc(&ctx->pairs, sizeof(uint2) * (size_t)std::max<int64_t>(n_pairs, 1)));
+  CU(cudaMalloc(&ctx->label, (size_t)n_rows));
+  int64_t *d_rp = nullptr; int32_t *d_col = nullptr; float *d_val = nullptr;
+  CU(cudaMalloc(&d_rp, sizeof(int64_t) * ((size_t)n_rows + 1)));
+  CU(cudaMalloc(&d_col, sizeof(int32_t) * (size_t)std::max<int64_t>(nnz, 1)));
+  CU(cudaMalloc(&d_val, sizeof(float) * (size_t)std::max<int64_t>(nnz, 1)));
+  CU(cudaMemcpyAsync(d_rp, row_ptr, sizeof(int64_t) * ((size_t)n_rows + 1), cudaMemcpyHostToDevice, ctx->stream));
+  if (nnz) {
+    CU(cudaMemcpyAsync(d_col, col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_val, val, sizeof(float) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CU(cudaMemcpyAsync(ctx->rp16, rp16.data(), sizeof(uint32_t) * ((size_t)n_rows + 1), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->label, label, (size_t)n_rows, cudaMemcpyHostToDevice, ctx->stream));
+  const int blocks = std::min<int64_t>(cdiv(n_rows, 8), (int64_t)ctx->sm_count * 16);
+  k_repack<<<blocks, 256, 0, ctx->stream>>>(d_rp, d_col, d_val, ctx->rp16, n_rows, ctx->pairs);
+  LAUNCHED();
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaFree(d_rp)); CU(cudaFree(d_col)); CU(cudaFree(d_val));
+  ctx->n_rows = n_rows; ctx->nnz = nnz; ctx->n_pairs = n_pairs;
+  return DSGD_OK;
+}
+
+// recompute c and ||w||^2 of the resident weights, refresh the fp32 shadow
+static int refresh_resident(dsgd_ctx *ctx) {
+  k_prepare<1024><<<1, 1024, 0, ctx->stream>>>(ctx->w, ctx->d, ctx->dim, ctx->lambda, ctx->scal + kScalC,
+                                                ctx->scal + kScalNrm2);
+  LAUNCHED();
+  k_to_f32<<<cdiv(ctx->dim, 256), 256, 0, ctx->stream>>>(ctx->w, ctx->w32, ctx->dim);
+  LAUNCHED();
+  CU(cudaGetLastError());
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_set_dim_sparsity(dsgd_ctx *ctx, const double *d) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(d, DSGD_ERR_INVALID, "dsgd_set_dim_sparsity: d is NULL");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(ctx->d, d, sizeof(double) * (size_t)ctx->dim, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->have_d = true;
+  int rc = refresh_resident(ctx);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_compute_dim_sparsity(dsgd_ctx *ctx, int64_t n_train, double *d_out) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(ctx->pairs, DSGD_ERR_STATE, "dsgd_compute_dim_sparsity: no rows loaded");
+  NEED(n_train >= 0 && n_train <= ctx->n_rows, DSGD_ERR_RANGE, "dsgd_compute_dim_sparsity: n_train %lld outside [0,%lld]",
+       (long long)n_train, (long long)ctx->n_rows);
+  CU(cudaSetDevice(ctx->device));
+  unsigned *df = nullptr;
+  CU(cudaMalloc(&df, sizeof(unsigned) * (size_t)ctx->dim));
+  CU(cudaMemsetAsync(df, 0, sizeof(unsigned) * (size_t)ctx->dim, ctx->stream));
+  uint32_t end16 = 0;
+  CU(cudaMemcpyAsync(&end16, ctx->rp16 + n_train, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  const int64_t n_pairs = (int64_t)end16 * 2;
+  if (n_pairs > 0) {
+    const int blocks = std::min<int64_t>(cdiv(n_pairs, 256), (int64_t)ctx->sm_count * 16);
+    k_col_hist<<<blocks, 256, 0, ctx->stream>>>(ctx->pairs, n_pairs, df);
+    LAUNCHED();
+  }
+  k_dim_sparsity<<<cdiv(ctx->dim, 256), 256, 0, ctx->stream>>>(df, ctx->dim, ctx->d);
+  LAUNCHED();
+  CU(cudaGetLastError());
+  ctx->have_d = true;
+  int rc = refresh_resident(ctx);
+  if (rc) return rc;
+  if (d_out) CU(cudaMemcpyAsync(d_out, ctx->d, sizeof(double) * (size_t)ctx->dim, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaFree(df));
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_set_weights(dsgd_ctx *ctx, const double *w) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(w, DSGD_ERR_INVALID, "dsgd_set_weights: w is NULL");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(ctx->w, w, sizeof(double) * (size_t)ctx->dim, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = refresh_resident(ctx);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_get_weights(dsgd_ctx *ctx, double *w) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(w, DSGD_ERR_INVALID, "dsgd_get_weights: w is NULL");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(w, ctx->w, sizeof(double) * (size_t)ctx->dim, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return DSGD_OK;
+}
+
+// ---- sample staging ----------------------------------------------------------------------------------
+
+static int ensure_i32(dsgd_ctx *ctx, int32_t **buf, int64_t *cap, int64_t n) {
+  if (*cap >= n) return DSGD_OK;
+  if (*buf) CU(cudaFree(*buf));
+  *buf = nullptr; *cap = 0;
+  const int64_t want = std::max<int64_t>(n, 1024);
+  CU(cudaMalloc(buf, sizeof(int32_t) * (size_t)want));
+  *cap = want;
+  return DSGD_OK;
+}
+static int ensure_f64(dsgd_ctx *ctx, double **buf, int64_t *cap, int64_t n) {
+  if (*cap >= n) return DSGD_OK;
+  if (*buf) CU(cudaFree(*buf));
+  *buf = nullptr; *cap = 0;
+  const int64_t want = std::max<int64_t>(n, 1024);
+  CU(cudaMalloc(buf, sizeof(double) * (size_t)want));
+  *cap = want;
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_stage_samples(dsgd_ctx *ctx, const int32_t *samples, int64_t n) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(ctx->pairs, DSGD_ERR_STATE, "dsgd_stage_samples: no rows loaded");
+  NEED(n >= 0 && (n == 0 || samples), DSGD_ERR_INVALID, "dsgd_stage_samples: bad arguments");
+  for (int64_t i = 0; i < n; ++i)
+    NEED(samples[i] >= 0 && samples[i] < ctx->n_rows, DSGD_ERR_RANGE, "sample index %d at position %lld outside [0,%lld)",
+         samples[i], (long long)i, (long long)ctx->n_rows);
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_i32(ctx, &ctx->samples, &ctx->samples_cap, n);
+  if (rc) return rc;
+  if (n) CU(cudaMemcpyAsync(ctx->samples, samples, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->samples_n = n;
+  return DSGD_OK;
+}
+
+// weights to use for a request: NULL -> resident; else copy into w_req and compute its scalars
+static int request_weights(dsgd_ctx *ctx, const double *w, const double **w_dev, const double **c_dev,
+                           const double **nrm_dev) {
+  if (!w) {
+    *w_dev = ctx->w; *c_dev = ctx->scal + kScalC; *nrm_dev = ctx->scal + kScalNrm2;
+    return DSGD_OK;
+  }
+  CU(cudaMemcpyAsync(ctx->w_req, w, sizeof(double) * (size_t)ctx->dim, cudaMemcpyHostToDevice, ctx->stream));
+  k_prepare<1024><<<1, 1024, 0, ctx->stream>>>(ctx->w_req, ctx->d, ctx->dim, ctx->lambda, ctx->scal + kScalReqC,
+                                                ctx->scal + kScalReqNrm2);
+  LAUNCHED();
+  CU(cudaGetLastError());
+  *w_dev = ctx->w_req; *c_dev = ctx->scal + kScalReqC; *nrm_dev = ctx->scal + kScalReqNrm2;
+  return DSGD_OK;
+}
+
+static inline int rows_grid(const dsgd_ctx *ctx, int64_t n) {
+  return (int)std::min<int64_t>(std::max<int64_t>(cdiv(n, 8), 1), (int64_t)ctx->sm_count * 8);
+}
+
+// ---- forward / gradient / eval -------------------------------------------------------------------------
+
+extern "C" int dsgd_forward(dsgd_ctx *ctx, const double *w, const int32_t *samples, int64_t n, double *preds_out) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(n >= 0 && (n == 0 || (samples && preds_out)), DSGD_ERR_INVALID, "dsgd_forward: bad arguments");
+  if (n == 0) return DSGD_OK;
+  int rc = dsgd_stage_samples(ctx, samples, n);
+  if (rc) return rc;
+  rc = ensure_f64(ctx, &ctx->preds, &ctx->preds_cap, n);
+  if (rc) return rc;
+  const double *wd, *cd, *nd;
+  if ((rc = request_weights(ctx, w, &wd, &cd, &nd))) return rc;
+  k_rows<false, true><<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(ctx->rp16, ctx->pairs, ctx->label, ctx->samples, 0, n,
+                                                                  wd, nullptr, ctx->preds, ctx->cnt);
+  LAUNCHED();
+  CU(cudaGetLastError());
+  CU(cudaMemsetAsync(ctx->cnt, 0, sizeof(unsigned long long) * 2, ctx->stream));
+  CU(cudaMemcpyAsync(preds_out, ctx->preds, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_gradient(dsgd_ctx *ctx, const double *w, const int32_t *samples, int64_t n, double *grad_out,
+                             double *loss_out) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(n >= 0 && grad_out, DSGD_ERR_INVALID, "dsgd_gradient: bad arguments");
+  NEED(n > 0, DSGD_ERR_EMPTY, "dsgd_gradient: empty batch (Vec.sum of an empty list throws in the reference)");
+  NEED(samples, DSGD_ERR_INVALID, "dsgd_gradient: samples is NULL");
+  NEED(ctx->have_d, DSGD_ERR_STATE, "dsgd_gradient: dimSparsity not set");
+  int rc = dsgd_stage_samples(ctx, samples, n);
+  if (rc) return rc;
+  const double *wd, *cd, *nd;
+  if ((rc = request_weights(ctx, w, &wd, &cd, &nd))) return rc;
+  k_rows<true, false><<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(ctx->rp16, ctx->pairs, ctx->label, ctx->samples, 0, n,
+                                                                  wd, ctx->g, nullptr, ctx->cnt);
+  LAUNCHED();
+  k_finish<<<cdiv(ctx->dim + 1, 256), 256, 0, ctx->stream>>>(ctx->g, ctx->dim, cd, ctx->cnt, (double)n);
+  LAUNCHED();
+  k_loss_scalar<<<1, 1, 0, ctx->stream>>>(nd, ctx->cnt, ctx->lambda, (double)n, ctx->out2);
+  LAUNCHED();
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(grad_out, ctx->g, sizeof(double) * (size_t)ctx->dim, cudaMemcpyDeviceToHost, ctx->stream));
+  double out2[2];
+  CU(cudaMemcpyAsync(out2, ctx->out2, sizeof out2, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemsetAsync(ctx->g, 0, sizeof(double) * (size_t)(ctx->dim + 2), ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (loss_out) *loss_out = out2[0];
+  return DSGD_OK;
+}
+
+static int eval_impl(dsgd_ctx *ctx, const double *w, int64_t row_begin, int64_t row_end, double out[5]) {
+  NEED(ctx->pairs, DSGD_ERR_STATE, "dsgd_eval: no rows loaded");
+  NEED(row_begin >= 0 && row_end <= ctx->n_rows && row_begin <= row_end, DSGD_ERR_RANGE,
+       "dsgd_eval: rows [%lld,%lld) outside [0,%lld)", (long long)row_begin, (long long)row_end, (long long)ctx->n_rows);
+  NEED(row_end > row_begin, DSGD_ERR_EMPTY, "dsgd_eval: empty range (reduce on an empty collection throws in the reference)");
+  CU(cudaSetDevice(ctx->device));
+  const int64_t n = row_end - row_begin;
+  const double *wd, *cd, *nd;
+  int rc;
+  if ((rc = request_weights(ctx, w, &wd, &cd, &nd))) return rc;
+  k_rows<false, false><<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(ctx->rp16, ctx->pairs, ctx->label, nullptr, row_begin, n,
+                                                                   wd, nullptr, nullptr, ctx->cnt);
+  LAUNCHED();
+  k_loss_scalar<<<1, 1, 0, ctx->stream>>>(nd, ctx->cnt, ctx->lambda, (double)n, ctx->out2);
+  LAUNCHED();
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, ctx->out2, sizeof(double) * 5, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_eval(dsgd_ctx *ctx, const double *w, int64_t row_begin, int64_t row_end, double *loss_out,
+                         double *acc_out) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  double out[5];
+  int rc = eval_impl(ctx, w, row_begin, row_end, out);
+  if (rc) return rc;
+  if (loss_out) *loss_out = out[0];
+  if (acc_out) *acc_out = out[1];
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_eval_counts(dsgd_ctx *ctx, const double *w, int64_t row_begin, int64_t row_end, int64_t *hinge_sum,
+                                int64_t *correct, double *norm_squared) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  double out[5];
+  int rc = eval_impl(ctx, w, row_begin, row_end, out);
+  if (rc) return rc;
+  if (hinge_sum) *hinge_sum = (int64_t)out[2];
+  if (correct) *correct = (int64_t)out[3];
+  if (norm_squared) *norm_squared = out[4];
+  return DSGD_OK;
+}
+
+// ---- sync mode -------------------------------------------------------------------------------------------
+
+extern "C" int dsgd_comm_unique_id(uint8_t id[DSGD_UNIQUE_ID_BYTES]) {
+  static_assert(sizeof(ncclUniqueId) == DSGD_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  if (!id) return DSGD_ERR_INVALID;
+  ncclUniqueId u;
+  ncclResult_t r = ncclGetUniqueId(&u);
+  if (r != ncclSuccess) return fail(nullptr, DSGD_ERR_NCCL, "ncclGetUniqueId: %s", ncclGetErrorString(r));
+  memcpy(id, &u, sizeof u);
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_comm_init(dsgd_ctx *ctx, const uint8_t id[DSGD_UNIQUE_ID_BYTES]) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(id, DSGD_ERR_INVALID, "dsgd_comm_init: id is NULL");
+  NEED(!ctx->comm, DSGD_ERR_STATE, "dsgd_comm_init: communicator already initialised");
+  CU(cudaSetDevice(ctx->device));
+  ncclUniqueId u;
+  memcpy(&u, id, sizeof u);
+  NC(ncclCommInitRank(&ctx->comm, ctx->world, u, ctx->rank));
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_set_workers(dsgd_ctx *ctx, int32_t n_local, const int32_t *counts, int32_t k_total) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(n_local >= 0 && k_total >= 0, DSGD_ERR_INVALID, "dsgd_set_workers: negative count");
+  NEED(n_local <= 1 || counts, DSGD_ERR_INVALID, "dsgd_set_workers: counts is NULL");
+  std::vector<int32_t> c;
+  if (counts)
+    for (int32_t v = 0; v < n_local; ++v) {
+      NEED(counts[v] > 0, DSGD_ERR_EMPTY, "dsgd_set_workers: worker %d has an empty batch (Vec.sum of an empty list throws)", v);
+      c.push_back(counts[v]);
+    }
+  ctx->worker_counts = c;
+  ctx->n_local = n_local;
+  ctx->k_total = k_total;
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_sync_steps_staged(dsgd_ctx *ctx, int64_t first, int64_t n_per_step, int64_t n_steps, double lr,
+                                      int want_losses) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(!(ctx->flags & DSGD_FLAG_ASYNC), DSGD_ERR_STATE, "sync step on a ctx created in async mode");
+  NEED(ctx->have_d, DSGD_ERR_STATE, "dsgd_sync_steps: dimSparsity not set");
+  NEED(n_steps >= 0 && first >= 0, DSGD_ERR_INVALID, "dsgd_sync_steps: bad arguments");
+  NEED(n_per_step >= 0, DSGD_ERR_INVALID, "dsgd_sync_steps: bad arguments");
+  NEED(first + n_per_step * n_steps <= ctx->samples_n, DSGD_ERR_RANGE, "dsgd_sync_steps: staged samples exhausted");
+  NEED(ctx->world == 1 || ctx->comm, DSGD_ERR_STATE, "dsgd_sync_steps: world > 1 but dsgd_comm_init was not called");
+  if (ctx->n_local == 0) {
+    NEED(n_per_step == 0, DSGD_ERR_INVALID, "dsgd_sync_steps: a bystander rank (n_local == 0) takes no samples");
+  } else {
+    NEED(n_per_step > 0, DSGD_ERR_EMPTY, "dsgd_sync_steps: empty batch (Vec.sum of an empty list throws in the reference)");
+    if (!ctx->worker_counts.empty()) {
+      int64_t tot = 0;
+      for (int32_t c : ctx->worker_counts) tot += c;
+      NEED(tot == n_per_step, DSGD_ERR_INVALID, "dsgd_sync_steps: n_per_step %lld != sum of worker counts %lld",
+           (long long)n_per_step, (long long)tot);
+    }
+  }
+  CU(cudaSetDevice(ctx->device));
+  if (want_losses) {
+    int rc = ensure_f64(ctx, &ctx->losses, &ctx->losses_cap, n_steps);
+    if (rc) return rc;
+  }
+  const int upd_blocks = cdiv(ctx->dim, 256);
+  const int fin_blocks = cdiv(ctx->dim + 1, 256);
+  const int32_t k_total = ctx->k_total > 0 ? ctx->k_total : ctx->world;
+  const bool single = (ctx->world == 1 && ctx->n_local == 1 && k_total == 1);
+  for (int64_t s = 0; s < n_steps; ++s) {
+    const int32_t *smp = ctx->samples + first + s * n_per_step;
+    double *loss_dev = want_losses ? ctx->losses + s : nullptr;
+    if (single) {
+      // one worker, one GPU: gradient -> (regularize + update) fused, two launches per step
+      auto *pe = prof_slot(ctx);
+      if (pe) cudaEventRecord(pe->first, ctx->stream);
+      k_rows<true, false><<<rows_grid(ctx, n_per_step), 256, 0, ctx->stream>>>(ctx->rp16, ctx->pairs, ctx->label, smp, 0,
+                                                                               n_per_step, ctx->w, ctx->g, nullptr, ctx->cnt);
+      if (pe) cudaEventRecord(pe->second, ctx->stream);
+      LAUNCHED();
+      k_update<true><<<upd_blocks, 256, 0, ctx->stream>>>(ctx->w, ctx->w32, ctx->g, ctx->d, ctx->dim, ctx->lambda, lr, 1.0,
+                                                          ctx->scal, ctx->cnt, ctx->partial, (double)n_per_step, loss_dev);
+      LAUNCHED();
+      continue;
+    }
+    int64_t off = 0;
+    for (int32_t v = 0; v < ctx->n_local; ++v) {
+      const int64_t nv = ctx->worker_counts.empty() ? n_per_step : ctx->worker_counts[(size_t)v];
+      auto *pe = prof_slot(ctx);
+      if (pe) cudaEventRecord(pe->first, ctx->stream);
+      k_rows<true, false><<<rows_grid(ctx, nv), 256, 0, ctx->stream>>>(ctx->rp16, ctx->pairs, ctx->label, smp + off, 0, nv,
+                                                                       ctx->w, ctx->g, nullptr, ctx->cnt);
+      if (pe) cudaEventRecord(pe->second, ctx->stream);
+      LAUNCHED();
+      k_finish_acc<<<fin_blocks, 256, 0, ctx->stream>>>(ctx->g, ctx->gsum, ctx->dim, ctx->scal + kScalC, ctx->cnt, (double)nv,
+                                                        v == 0 ? 1 : 0);
+      LAUNCHED();
+      off += nv;
+    }
+    if (ctx->n_local == 0) CU(cudaMemsetAsync(ctx->gsum, 0, sizeof(double) * (size_t)(ctx->dim + 2), ctx->stream));
+    if (ctx->world > 1)
+      NC(ncclAllReduce(ctx->gsum, ctx->gsum, (size_t)ctx->dim + 2, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    k_update<false><<<upd_blocks, 256, 0, ctx->stream>>>(ctx->w, ctx->w32, ctx->gsum, ctx->d, ctx->dim, ctx->lambda, lr,
+                                                         (double)k_total, ctx->scal, ctx->cnt, ctx->partial, 0.0, loss_dev);
+    LAUNCHED();
+  }
+  CU(cudaGetLastError());
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_read_losses(dsgd_ctx *ctx, double *losses_out, int64_t n_steps) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(losses_out && n_steps >= 0 && n_steps <= ctx->losses_cap, DSGD_ERR_INVALID, "dsgd_read_losses: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  if (n_steps)
+    CU(cudaMemcpyAsync(losses_out, ctx->losses, sizeof(double) * (size_t)n_steps, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_sync_steps(dsgd_ctx *ctx, const int32_t *samples, int64_t n_per_step, int64_t n_steps, double lr,
+                               double *losses_out) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(n_steps >= 0 && n_per_step >= 0, DSGD_ERR_INVALID, "dsgd_sync_steps: bad arguments");
+  NEED(n_per_step > 0 || ctx->n_local == 0, DSGD_ERR_EMPTY,
+       "dsgd_sync_steps: empty batch (Vec.sum of an empty list throws in the reference)");
+  int rc = dsgd_stage_samples(ctx, samples, n_per_step * n_steps);
+  if (rc) return rc;
+  if ((rc = dsgd_sync_steps_staged(ctx, 0, n_per_step, n_steps, lr, losses_out != nullptr))) return rc;
+  if (losses_out) return dsgd_read_losses(ctx, losses_out, n_steps);
+  CU(cudaStreamSynchronize(ctx->stream));
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_sync_step(dsgd_ctx *ctx, const int32_t *samples, int64_t n, double lr, double *loss_out) {
+  return dsgd_sync_steps(ctx, samples, n, 1, lr, loss_out);
+}
+
+// ---- async mode (filled in by dsgd_async.cuh in a later milestone) -----------------------------------------
+
+extern "C" int dsgd_ipc_export(dsgd_ctx *ctx, uint8_t handle[DSGD_IPC_HANDLE_BYTES]) {
+  if (!ctx || !handle) return DSGD_ERR_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == DSGD_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+  CU(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, ctx->w));
+  memcpy(handle, &h, sizeof h);
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_ipc_import(dsgd_ctx *ctx, int peer_rank, const uint8_t handle[DSGD_IPC_HANDLE_BYTES]) {
+  if (!ctx || !handle) return DSGD_ERR_INVALID;
+  (void)peer_rank;
+  return fail(ctx, DSGD_ERR_STATE, "dsgd_ipc_import: async mode is not built yet");
+}
+
+extern "C" int dsgd_start_async(dsgd_ctx *ctx, const double *, const int32_t *, int64_t, int32_t, double, int32_t, int64_t,
+                                uint64_t) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(ctx->flags & DSGD_FLAG_ASYNC, DSGD_ERR_STATE,
+       "Cannot initialize async computation: slave is in synchronous mode.");
+  return fail(ctx, DSGD_ERR_STATE, "dsgd_start_async: async mode is not built yet");
+}
+
+extern "C" int dsgd_stop_async(dsgd_ctx *ctx) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(ctx->flags & DSGD_FLAG_ASYNC, DSGD_ERR_STATE, "Cannot stop async computation: slave is in synchronous mode.");
+  return fail(ctx, DSGD_ERR_STATE, "dsgd_stop_async: async mode is not built yet");
+}
+
+extern "C" int dsgd_update_grad(dsgd_ctx *ctx, const int32_t *idx, const double *val, int64_t nnz) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(ctx->flags & DSGD_FLAG_ASYNC, DSGD_ERR_STATE, "Cannot update gradient: slave is in synchronous mode.");
+  NEED(nnz >= 0 && (nnz == 0 || (idx && val)), DSGD_ERR_INVALID, "dsgd_update_grad: bad arguments");
+  return fail(ctx, DSGD_ERR_STATE, "dsgd_update_grad: async mode is not built yet");
+}
+
+extern "C" int dsgd_async_updates(dsgd_ctx *ctx, int64_t *count) {
+  if (!ctx || !count) return DSGD_ERR_INVALID;
+  *count = 0;
+  return DSGD_OK;
+}

@@ -1,0 +1,169 @@
+/*
+ * dsgd.h -- C ABI of the B200-native data-parallel SGD hot path (libdsgd.so).
+ *
+ * This is the drop-in boundary for zifeo/distributed-sgd's hot path.  The reference has no FFI of its
+ * own (it is 100 % Scala over gRPC); the seams this ABI sits behind are the handlers of
+ * its gRPC `Slave` service and the step body of `Master.fit`.  Every entry point names the reference
+ * interface it replaces (path:line under /root/reference/src/main/).  INTEGRATION.md shows the JNI /
+ * Scala binding a maintainer would add; distributed_sgd_b200/ is the Python host that mirrors the
+ * reference's Slave / Master / SparseSVM surface over this ABI.
+ *
+ * Conventions
+ *  - One opaque dsgd_ctx per GPU == one reference Slave (+ its SparseSVM).  In sync mode every ctx also
+ *    carries the Master's weight vector (weights stay resident on the device; the reference's per-request
+ *    weight broadcast, core/Master.scala:186-188, disappears).
+ *  - Every call returns 0 (DSGD_OK) or a negative DSGD_ERR_*; dsgd_last_error() gives the message.  No
+ *    exception crosses the ABI.  The caller owns all host buffers; they are consumed before the call
+ *    returns.  The ctx owns all device memory.
+ *  - Vectors (weights, gradients, dimSparsity) are dense double[dim]; 0.0 stands for "key absent from the
+ *    reference's Map[Int, Number]".  The reference's wire type is double (protobuf/proto.proto:28-31).
+ *  - Rows are CSR with 0-based int32 columns and fp32 values; CSR column c stands for the reference's
+ *    1-based feature key c+1 (utils/Dataset.scala:30).  Sample indices are row ids into what
+ *    dsgd_load_csr received (the reference addresses a slave by global row id, core/Slave.scala:149).
+ *  - Arithmetic: values fp32 (exactly promoted), every accumulation and all state in fp64, like the
+ *    reference's spire.math.Number over Double.
+ *  - Threading: calls on one ctx are serialised by the caller, except dsgd_update_grad,
+ *    dsgd_get_weights, dsgd_async_updates and dsgd_stop_async, which are safe while the async loop runs
+ *    (the reference serves them from its 8-thread pool concurrently with asyncTask, core/Slave.scala:24-30).
+ */
+#ifndef DSGD_H
+#define DSGD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSGD_OK 0
+#define DSGD_ERR_INVALID (-1) /* bad argument; the reference's require(...) / IllegalArgumentException        */
+#define DSGD_ERR_STATE (-2)   /* wrong mode or state: "slave is in synchronous mode", "already running"        */
+#define DSGD_ERR_EMPTY (-3)   /* empty batch: Vec.sum on an empty list throws (math/Vec.scala:129, quirk Q7)   */
+#define DSGD_ERR_RANGE (-4)   /* sample index outside the loaded rows (ArrayIndexOutOfBounds in the reference)  */
+#define DSGD_ERR_CUDA (-5)    /* CUDA runtime error, or no usable GPU (there is no CPU fallback)                */
+#define DSGD_ERR_NCCL (-6)    /* NCCL error                                                                     */
+#define DSGD_ERR_NOMEM (-7)
+#define DSGD_ERR_TIMEOUT (-8) /* a device-side wait (peer flag, grid barrier) hit its watchdog                  */
+
+#define DSGD_UNIQUE_ID_BYTES 128
+#define DSGD_IPC_HANDLE_BYTES 64
+
+/* dsgd_create flags */
+#define DSGD_FLAG_ASYNC 1u /* the `async` constructor argument of Slave / Master (core/Slave.scala:20) */
+
+typedef struct dsgd_ctx dsgd_ctx;
+
+/* ---- lifecycle: `new Slave(node, master, data, model, async)` + `new SparseSVM(lambda, dimSparsity)`
+ *      (Main.scala:68,138,149; core/Slave.scala:20; core/ml/SparseSVM.scala:11) ------------------------ */
+int dsgd_create(dsgd_ctx **out, int device, int32_t dim, double lambda, int rank, int world, uint32_t flags);
+int dsgd_destroy(dsgd_ctx *ctx);
+/* Message of the last failing call on ctx (ctx == NULL: last failing dsgd_create on this thread). */
+const char *dsgd_last_error(const dsgd_ctx *ctx);
+/* Build / device facts as a JSON string (SM count, arch, kernels compiled). */
+const char *dsgd_info(const dsgd_ctx *ctx);
+/* Use the caller's CUDA stream (a cudaStream_t) for everything the ctx launches; NULL restores the
+ * ctx's own stream.  Lets a host time the ctx's kernels with its own events. */
+int dsgd_set_stream(dsgd_ctx *ctx, void *cuda_stream);
+int dsgd_synchronize(dsgd_ctx *ctx);
+/* CUDA-event stopwatch on the ctx's launch stream (what bench.py times kernels with). */
+int dsgd_timer_start(dsgd_ctx *ctx);
+int dsgd_timer_stop(dsgd_ctx *ctx, float *elapsed_ms);
+/* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
+int dsgd_launch_count(const dsgd_ctx *ctx, int64_t *count);
+
+/* Kernel stopwatch for the roofline figure: between begin and end, every sample_every-th launch of the
+ * gradient kernel (the dominant kernel of a step) is bracketed by CUDA events on the launch stream; end
+ * returns their mean duration and how many launches were sampled. */
+int dsgd_profile_begin(dsgd_ctx *ctx, int32_t sample_every);
+int dsgd_profile_end(dsgd_ctx *ctx, float *mean_ms, int64_t *n_sampled);
+
+/* ---- data: the `data: Array[(Vec, Int)]` constructor argument (core/Slave.scala:20; Main.scala:138,149).
+ *      Rows are repacked on the device into 16-byte aligned (col, val) windows.  label in {-1, +1}. ------ */
+int dsgd_load_csr(dsgd_ctx *ctx, int64_t n_rows, int64_t nnz, const int64_t *row_ptr, const int32_t *col,
+                  const float *val, const int8_t *label);
+
+/* ---- model: SparseSVM.dimSparsity (core/ml/SparseSVM.scala:11).  d is given in the WEIGHT index space. */
+int dsgd_set_dim_sparsity(dsgd_ctx *ctx, const double *d);
+/* Main.scala:54-65 on the device: inverse (document frequency + 1) over rows [0, n_train), including the
+ * reference's off-by-one key shift (quirk Q3).  Installs the result; d_out (optional) receives a copy. */
+int dsgd_compute_dim_sparsity(dsgd_ctx *ctx, int64_t n_train, double *d_out);
+
+/* ---- resident weights: GradState.grad on the master (core/ml/GradState.scala:6), `weights` Ref on an
+ *      async slave (core/Slave.scala:30) ---------------------------------------------------------------- */
+int dsgd_set_weights(dsgd_ctx *ctx, const double *w);
+int dsgd_get_weights(dsgd_ctx *ctx, double *w);
+
+/* ---- SlaveImpl.forward (core/Slave.scala:129-140; SparseSVM.scala:14): preds[i] = -signum(x_i . w).
+ *      w == NULL: use the resident weights. ----------------------------------------------------------------- */
+int dsgd_forward(dsgd_ctx *ctx, const double *w, const int32_t *samples, int64_t n, double *preds_out);
+
+/* ---- SlaveImpl.gradient (core/Slave.scala:142-157; SparseSVM.scala:26-31): grad_out[dim] =
+ *      regularize(sum_i backward(w, x_i, y_i), w).  loss_out (optional) = SparseSVM.loss(w, these samples)
+ *      (SparseSVM.scala:20-23).  w == NULL: resident weights.  n == 0 -> DSGD_ERR_EMPTY. -------------------- */
+int dsgd_gradient(dsgd_ctx *ctx, const double *w, const int32_t *samples, int64_t n, double *grad_out,
+                  double *loss_out);
+
+/* ---- Master.localLoss / localAccuracy over rows [row_begin, row_end) (core/Master.scala:100-107): one
+ *      streaming pass; loss = lambda*||w||^2 + mean hinge, acc = #{pred == y} / n. ------------------------- */
+int dsgd_eval(dsgd_ctx *ctx, const double *w, int64_t row_begin, int64_t row_end, double *loss_out,
+              double *acc_out);
+
+/* Sharded form of the same pass: the exact integer sums (hinge losses are 0, 1 or 2 per sample) and
+ * ||w||^2, so that a host can combine row shards evaluated on different GPUs without rounding. */
+int dsgd_eval_counts(dsgd_ctx *ctx, const double *w, int64_t row_begin, int64_t row_end, int64_t *hinge_sum,
+                     int64_t *correct, double *norm_squared);
+
+/* ---- communicator for sync mode: replaces the gRPC channels between master and slaves
+ *      (core/package.scala:16-21; core/Master.scala:222-243).  Rank 0 makes an id, the host transports it
+ *      (its own RPC), every rank calls dsgd_comm_init.  world == 1 needs neither. -------------------------- */
+int dsgd_comm_unique_id(uint8_t id[DSGD_UNIQUE_ID_BYTES]);
+int dsgd_comm_init(dsgd_ctx *ctx, const uint8_t id[DSGD_UNIQUE_ID_BYTES]);
+
+/* ---- logical workers of a sync step.  Default: this ctx is ONE worker (its whole slice is one
+ *      GradientRequest) and the master averages over `world` results.  With n_local > 1 the slice of every
+ *      following step is cut into n_local consecutive requests of counts[v] samples, each with its own batch
+ *      sum and its own regularize() support, exactly as if n_local slaves had answered (core/Slave.scala:
+ *      147-155); k_total is the number of results the master averages (Vec.mean divisor, core/Master.scala:194
+ *      -- the reference zips workers with split groups, so it can be smaller than the node count).
+ *      n_local == 0: this rank only joins the exchange (a slave without a split group). ---------------- */
+int dsgd_set_workers(dsgd_ctx *ctx, int32_t n_local, const int32_t *counts, int32_t k_total);
+
+/* ---- one synchronous step of Master.fit (core/Master.scala:184-197): this rank's worker computes its
+ *      regularized batch-sum gradient on `samples`, gradients are summed over ranks (allreduce over NVLink
+ *      instead of K gRPC replies), and every rank applies w <- w - lr * (sum / world).  All ranks call it with
+ *      their own slice.  loss_out (optional) = SparseSVM.loss(w_before, all samples of the step). ------------ */
+int dsgd_sync_step(dsgd_ctx *ctx, const int32_t *samples, int64_t n, double lr, double *loss_out);
+/* n_steps consecutive steps (the inner loop of an epoch, core/Master.scala:179): samples holds
+ * n_steps * n_per_step indices, step-major.  losses_out (optional) holds n_steps values. */
+int dsgd_sync_steps(dsgd_ctx *ctx, const int32_t *samples, int64_t n_per_step, int64_t n_steps, double lr,
+                    double *losses_out);
+/* The same split in three, so a host can keep the index stream resident: stage = H2D of the sample slices
+ * (the `samples` field of GradientRequest, protobuf/proto.proto:60-63); run = device only; read = D2H. */
+int dsgd_stage_samples(dsgd_ctx *ctx, const int32_t *samples, int64_t n);
+int dsgd_sync_steps_staged(dsgd_ctx *ctx, int64_t first, int64_t n_per_step, int64_t n_steps, double lr,
+                           int want_losses);
+int dsgd_read_losses(dsgd_ctx *ctx, double *losses_out, int64_t n_steps);
+
+/* ---- async (Hogwild) mode.  Peer replicas are reached by address over NVLink: each rank exports its
+ *      weight replica, the host transports the handles, each rank imports its peers'.  Replaces the
+ *      slave<->slave channels (core/Slave.scala:23; core/Master.scala:229-233). ---------------------------- */
+int dsgd_ipc_export(dsgd_ctx *ctx, uint8_t handle[DSGD_IPC_HANDLE_BYTES]);
+int dsgd_ipc_import(dsgd_ctx *ctx, int peer_rank, const uint8_t handle[DSGD_IPC_HANDLE_BYTES]);
+/* SlaveImpl.startAsync (core/Slave.scala:159-175): weights := w0, then the worker loop (asyncTask,
+ * core/Slave.scala:79-111) runs on the device until dsgd_stop_async or max_updates local updates.
+ * concurrency = number of Hogwild lanes on this GPU (1 = the reference's strictly sequential loop).
+ * seed drives the device-side sampling of `assigned` (core/Slave.scala:84,87). */
+int dsgd_start_async(dsgd_ctx *ctx, const double *w0, const int32_t *assigned, int64_t n_assigned, int32_t batch,
+                     double lr, int32_t concurrency, int64_t max_updates, uint64_t seed);
+/* SlaveImpl.stopAsync (core/Slave.scala:187-195). */
+int dsgd_stop_async(dsgd_ctx *ctx);
+/* SlaveImpl.updateGrad / AsyncMasterGrpcImpl.updateGrad (core/Slave.scala:177-185; core/MasterAsync.scala:
+ * 164-177): weights -= delta for a sparse delta given as (idx, val) pairs. */
+int dsgd_update_grad(dsgd_ctx *ctx, const int32_t *idx, const double *val, int64_t nnz);
+/* GradState.updates as seen by this replica (core/ml/GradState.scala:8; core/MasterAsync.scala:165). */
+int dsgd_async_updates(dsgd_ctx *ctx, int64_t *count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSGD_H */

@@ -1,0 +1,207 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (include/dsgd.h via ctypes), against the
+fp64 oracle on the same seeded inputs.
+
+Stated tolerance (north_star: "within a stated fp32 tolerance"): the device keeps all state and every
+accumulation in fp64 like the reference, so the bounds here are far tighter than fp32:
+  * predictions, gate decisions, gradient support, integer loss/accuracy counters: EXACT;
+  * gradient / weight values: rtol 1e-12 (fp64 summation order differs: atomics and tree reductions);
+  * losses: rtol 1e-12.
+"""
+import numpy as np
+import pytest
+
+from conftest import random_csr
+from helpers import data_from_csr, make_pair
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def synth():
+    from distributed_sgd_b200.utils import synthetic_rcv1
+    return synthetic_rcv1(n_rows=6000, seed=3)
+
+
+def rand_w(rng, dim, density=0.5, scale=1.0):
+    return np.where(rng.random(dim) < density, rng.standard_normal(dim) * scale, 0.0)
+
+
+@pytest.mark.parametrize("seed,dup,empty", [(0, False, False), (1, True, False), (2, True, True), (3, False, True)])
+def test_gradient_forward_small_random(seed, dup, empty):
+    rng = np.random.default_rng(seed)
+    dim, n = 64, 200
+    data = data_from_csr(*random_csr(rng, n, dim, max_nnz=10, allow_empty=empty, dup_values=dup), dim)
+    ctx, orc = make_pair(data, lam=0.05, n_train=150)
+    for trial in range(8):
+        w = rand_w(rng, dim) if trial else np.zeros(dim)
+        idx = rng.integers(0, n, size=int(rng.integers(1, 80))).astype(np.int32)  # with repeats
+        g_ref, c_ref = orc.gradient(w, idx)
+        g, loss = ctx.gradient(idx, w, want_loss=True)
+        assert (g == 0).tolist() == (g_ref == 0).tolist()                      # identical support (quirk Q9)
+        np.testing.assert_allclose(g, g_ref, rtol=RTOL, atol=0)
+        assert loss == pytest.approx(orc.loss_acc(w, idx=idx)[0], rel=RTOL)
+        np.testing.assert_array_equal(ctx.forward(idx, w), orc.forward(w, idx))
+        # resident weights path == request weights path
+        ctx.set_weights(w)
+        np.testing.assert_array_equal(ctx.gradient(idx), g)
+        np.testing.assert_array_equal(ctx.get_weights(), w)
+    ctx.close()
+
+
+@pytest.mark.parametrize("batch", [1, 7, 64, 256, 1024])
+def test_gradient_synthetic_batches(synth, batch):
+    rng = np.random.default_rng(batch)
+    ctx, orc = make_pair(synth, lam=1e-5, n_train=4800)
+    for w in (np.zeros(synth.dim), rand_w(rng, synth.dim, 0.3, 0.1)):
+        idx = rng.choice(4800, size=batch, replace=False).astype(np.int32)
+        g_ref, _ = orc.gradient(w, idx)
+        g = ctx.gradient(idx, w)
+        assert (g == 0).tolist() == (g_ref == 0).tolist()
+        np.testing.assert_allclose(g, g_ref, rtol=RTOL, atol=0)
+        np.testing.assert_array_equal(ctx.forward(idx, w), orc.forward(w, idx))
+    ctx.close()
+
+
+def test_known_answers_through_the_abi():
+    # KA4: x = {key 1 -> 1.0}, y = +1, w0 = 0, lr = 0.5
+    data = data_from_csr([0, 1], [0], [1.0], [1], 4)
+    ctx, orc = make_pair(data, lam=1e-5)
+    assert ctx.eval(0, 1) == (1.0, 0.0)                                   # KA1: loss 1, accuracy 0 at w = 0
+    loss = ctx.sync_step([0], 0.5)
+    assert loss == 1.0
+    np.testing.assert_array_equal(ctx.get_weights(), [-0.5, 0, 0, 0])
+    assert ctx.forward([0])[0] == 1.0 and ctx.eval(0, 1)[1] == 1.0
+    np.testing.assert_array_equal(ctx.gradient([0]), np.zeros(4))          # activity < 0: empty support
+    ctx.sync_step([0], 0.5)
+    np.testing.assert_array_equal(ctx.get_weights(), [-0.5, 0, 0, 0])
+    ctx.close()
+    # KA3: gate inclusive at activity == 0; KA5: exact cancellation leaves the key out of the support
+    data = data_from_csr([0, 2, 4], [0, 1, 0, 2], [0.5, 1.0, 0.5, 1.0], [1, -1], 6)
+    ctx, orc = make_pair(data, lam=0.1)
+    d = np.array([0.5, 0.5, 0.5, 0.5, 0, 0])
+    ctx.set_dim_sparsity(d); orc.set_dim_sparsity(d)
+    w = np.array([0.0, 0.25, -0.125, 0, 0, 1.0])
+    g = ctx.gradient([0, 1], w)
+    c = 0.1 * 2.0 * float(np.dot(w, d))
+    assert g[0] == 0.0 and g[1] == 1.0 + c and g[2] == -1.0 + c
+    np.testing.assert_array_equal(g, orc.gradient(w, [0, 1])[0])
+    ctx.close()
+
+
+def test_eval_matches_oracle(synth):
+    rng = np.random.default_rng(5)
+    ctx, orc = make_pair(synth, lam=1e-5, n_train=4800)
+    for w in (np.zeros(synth.dim), rand_w(rng, synth.dim, 0.5, 0.05)):
+        for b, e in ((0, 4800), (4800, 6000), (17, 18), (0, 6000)):
+            loss, acc = ctx.eval(b, e, w)
+            loss_ref, acc_ref = orc.loss_acc(w, begin=b, n=e - b)
+            assert acc == acc_ref
+            assert loss == pytest.approx(loss_ref, rel=RTOL)
+        h1, c1, n2 = ctx.eval_counts(0, 3000, w)
+        h2, c2, _ = ctx.eval_counts(3000, 6000, w)
+        h, c, _ = ctx.eval_counts(0, 6000, w)
+        assert (h1 + h2, c1 + c2) == (h, c)                                # shards add exactly
+        assert n2 == pytest.approx(float(np.dot(w, w)), rel=RTOL)
+    ctx.close()
+
+
+def test_dim_sparsity_on_device(synth):
+    ctx, orc = make_pair(synth, lam=1e-5, n_train=4800)
+    d_dev = ctx.compute_dim_sparsity(4800)
+    np.testing.assert_array_equal(d_dev, orc.dim_sparsity(4800))           # integer counts -> identical doubles
+    ctx.close()
+
+
+@pytest.mark.parametrize("batch,steps", [(1, 40), (16, 60), (256, 30)])
+def test_sync_trajectory_single_worker(synth, batch, steps):
+    rng = np.random.default_rng(batch)
+    lam, lr = 1e-5, 0.5
+    ctx, orc = make_pair(synth, lam=lam, n_train=4800)
+    idx = np.stack([rng.choice(4800, size=batch, replace=False) for _ in range(steps)]).astype(np.int32)
+    w_ref, losses_ref = orc.sync_steps(np.zeros(synth.dim), idx.reshape(-1), [batch], lr, n_steps=steps)
+    ctx.set_weights(np.zeros(synth.dim))
+    losses = ctx.sync_steps(idx.reshape(-1), batch, steps, lr)
+    w = ctx.get_weights()
+    np.testing.assert_allclose(losses, losses_ref, rtol=RTOL)
+    assert (w == 0).tolist() == (w_ref == 0).tolist()
+    np.testing.assert_allclose(w, w_ref, rtol=1e-11, atol=1e-15)
+    # same trajectory one call per step (the per-batch API) and through the staged split
+    ctx.set_weights(np.zeros(synth.dim))
+    for s in range(steps):
+        assert ctx.sync_step(idx[s], lr) == pytest.approx(losses_ref[s], rel=RTOL)
+    np.testing.assert_array_equal(ctx.get_weights(), w)
+    ctx.set_weights(np.zeros(synth.dim))
+    ctx.stage_samples(idx.reshape(-1))
+    ctx.sync_steps_staged(0, batch, steps, lr, want_losses=True)
+    np.testing.assert_array_equal(ctx.read_losses(steps), losses)
+    np.testing.assert_array_equal(ctx.get_weights(), w)
+    ctx.close()
+
+
+@pytest.mark.parametrize("K,batch", [(2, 10), (3, 64), (4, 5)])
+def test_sync_trajectory_virtual_workers(synth, K, batch):
+    """K reference workers on one GPU: per-worker supports get their own +c."""
+    from distributed_sgd_b200.ml import SplitStrategy
+    rng = np.random.default_rng(K)
+    lam, lr, steps = 0.01, 0.5, 25                                         # large lambda: c matters
+    ctx, orc = make_pair(synth, lam=lam, n_train=4800)
+    groups = SplitStrategy.vanilla(4800, K)
+    idx = np.stack([np.concatenate([g.start + rng.choice(len(g), size=batch, replace=False) for g in groups])
+                    for _ in range(steps)]).astype(np.int32)
+    w_ref, losses_ref = orc.sync_steps(np.zeros(synth.dim), idx.reshape(-1), [batch] * K, lr, n_steps=steps)
+    ctx.set_weights(np.zeros(synth.dim))
+    ctx.set_workers([batch] * K, K)
+    losses = ctx.sync_steps(idx.reshape(-1), batch * K, steps, lr)
+    np.testing.assert_allclose(losses, losses_ref, rtol=RTOL)
+    np.testing.assert_allclose(ctx.get_weights(), w_ref, rtol=1e-11, atol=1e-15)
+    ctx.close()
+
+
+def test_edge_rows_and_errors():
+    from distributed_sgd_b200 import native
+    rng = np.random.default_rng(9)
+    dim = 3000
+    # rows: empty, single, odd, even, and one maximal 2000-nnz row
+    lens = [0, 1, 3, 4, 2000, 0, 33, 64, 65]
+    rp = np.concatenate([[0], np.cumsum(lens)])
+    col = np.concatenate([np.sort(rng.choice(dim, size=l, replace=False)) for l in lens]).astype(np.int32)
+    val = (np.abs(rng.standard_normal(len(col))) + 1e-3).astype(np.float32)
+    lab = rng.choice([-1, 1], size=len(lens)).astype(np.int8)
+    data = data_from_csr(rp, col, val, lab, dim)
+    ctx, orc = make_pair(data, lam=0.01)
+    w = rand_w(rng, dim, 0.7)
+    idx = np.arange(len(lens), dtype=np.int32)
+    np.testing.assert_allclose(ctx.gradient(idx, w), orc.gradient(w, idx)[0], rtol=RTOL, atol=0)
+    np.testing.assert_array_equal(ctx.forward(idx, w), orc.forward(w, idx))
+    assert ctx.forward([0], w)[0] == 0.0                                   # empty row: dot 0 -> prediction 0
+    with pytest.raises(native.DsgdEmpty):
+        ctx.gradient(np.zeros(0, np.int32), w)                             # Vec.sum(empty) throws (Q7)
+    with pytest.raises(native.DsgdRange):
+        ctx.gradient([len(lens)], w)
+    with pytest.raises(native.DsgdRange):
+        ctx.forward([-1], w)
+    with pytest.raises(native.DsgdEmpty):
+        ctx.eval(3, 3)
+    ctx.close()
+
+
+def test_error_invalid_column_is_range():
+    from distributed_sgd_b200 import native
+    ctx = native.NativeCtx(0, 8, 0.1)
+    with pytest.raises(native.DsgdRange):
+        ctx.load_csr([0, 1], [8], [1.0], [1])
+    with pytest.raises(native.DsgdInvalid):
+        ctx.load_csr([0, 1], [0], [1.0], [0])                              # label must be +/-1
+    ctx.close()
+    actx = native.NativeCtx(0, 8, 0.1, is_async=True)
+    actx.load_csr([0, 1], [0], [1.0], [1])
+    actx.set_dim_sparsity(np.zeros(8))
+    with pytest.raises(native.DsgdState):
+        actx.sync_step([0], 0.5)                                           # sync step on an async slave
+    actx.close()
+    sctx = native.NativeCtx(0, 8, 0.1)
+    with pytest.raises(native.DsgdState):
+        sctx.update_grad([0], [1.0])                                       # "slave is in synchronous mode"
+    sctx.close()
