@@ -255,6 +255,7 @@ def main():
 
     # ---- leg 3: mean duration of the dominant kernel (gradient) over the same work -----------------------
     ctx.set_weights(np.zeros(data.dim))
+    ctx.stage_samples(samples_np.reshape(-1))   # leg 2 re-staged one bench step at a time
     ctx.profile_begin(sample_every=8)
     for i in range(args.warmup, total_steps):
         ctx.sync_steps_staged(i * S * B, B, S, LR, want_losses=False)
