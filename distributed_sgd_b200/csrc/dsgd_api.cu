@@ -13,6 +13,8 @@
 #include <vector>
 
 #include "dsgd_kernels.cuh"
+#include "dsgd_persistent.cuh"
+#include <cstdlib>
 
 using namespace dsgd;
 
@@ -57,6 +59,16 @@ struct dsgd_ctx {
   int64_t preds_cap = 0;
 
   ncclComm_t comm = nullptr;
+
+  // persistent sync kernel resources (allocated on first use)
+  double *p_wbuf[2] = {nullptr, nullptr};
+  double *p_gbuf[3] = {nullptr, nullptr, nullptr};
+  double *p_partial = nullptr;
+  unsigned *p_hinge = nullptr;
+  int64_t p_hinge_cap = 0;
+  unsigned *p_bar = nullptr;   // [0]: barrier counter, [1]: abort flag
+  bool p_ready = false;
+  long long *p_tl = nullptr;   // debug timeline (DSGD_PERSIST_TIMELINE)
 
   // sampled per-launch timing of the gradient kernel
   int32_t prof_every = 0;
@@ -105,7 +117,7 @@ static std::pair<cudaEvent_t, cudaEvent_t> *prof_slot(dsgd_ctx *ctx) {
   if (ctx->prof_every <= 0) return nullptr;
   if ((ctx->prof_seen++ % ctx->prof_every) != 0) return nullptr;
   if (ctx->prof_used == ctx->prof_events.size()) {
-    if (ctx->prof_events.size() >= 8192) return nullptr;
+    if (ctx->prof_events.size() >= 16384) return nullptr;
     cudaEvent_t a, b;
     if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return nullptr;
     ctx->prof_events.emplace_back(a, b);
@@ -181,7 +193,8 @@ extern "C" int dsgd_destroy(dsgd_ctx *ctx) {
   cudaDeviceSynchronize();
   if (ctx->comm) ncclCommDestroy(ctx->comm);
   void *ptrs[] = {ctx->rp16, ctx->pairs, ctx->label, ctx->w, ctx->g, ctx->d, ctx->w_req, ctx->w32, ctx->scal,
-                  ctx->cnt, ctx->partial, ctx->out2, ctx->gsum, ctx->samples, ctx->losses, ctx->preds};
+                  ctx->cnt, ctx->partial, ctx->out2, ctx->gsum, ctx->p_wbuf[0], ctx->p_wbuf[1], ctx->p_gbuf[0],
+                  ctx->p_gbuf[1], ctx->p_gbuf[2], ctx->p_partial, ctx->p_hinge, ctx->p_bar, ctx->samples, ctx->losses, ctx->preds};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -567,6 +580,95 @@ extern "C" int dsgd_comm_init(dsgd_ctx *ctx, const uint8_t id[DSGD_UNIQUE_ID_BYT
   return DSGD_OK;
 }
 
+// ---- persistent single-worker loop ------------------------------------------------------------------------
+constexpr int kPRowWarps = 8, kPUpdWarps = 8, kPSlots = 8, kPCap = 256;
+using PSmem = PersistSmem<kPRowWarps, kPUpdWarps, kPSlots, kPCap>;
+
+static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
+  if (!ctx->p_ready) {
+    const size_t vd = sizeof(double) * (size_t)(ctx->dim + 2);
+    for (int i = 0; i < 2; ++i) CU(cudaMalloc(&ctx->p_wbuf[i], vd));
+    for (int i = 0; i < 3; ++i) {
+      CU(cudaMalloc(&ctx->p_gbuf[i], vd));
+      CU(cudaMemsetAsync(ctx->p_gbuf[i], 0, vd, ctx->stream));
+    }
+    CU(cudaMalloc(&ctx->p_partial, sizeof(double) * 2 * 2 * (size_t)ctx->sm_count));
+    CU(cudaMalloc(&ctx->p_bar, sizeof(unsigned) * 4));
+    CU(cudaFuncSetAttribute(k_sync_persistent<kPRowWarps, kPUpdWarps, kPSlots, kPCap>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
+    ctx->p_ready = true;
+  }
+  if (ctx->p_hinge_cap < n_steps) {
+    if (ctx->p_hinge) CU(cudaFree(ctx->p_hinge));
+    ctx->p_hinge = nullptr;
+    const int64_t want = std::max<int64_t>(n_steps, 4096);
+    CU(cudaMalloc(&ctx->p_hinge, sizeof(unsigned) * (size_t)want));
+    ctx->p_hinge_cap = want;
+  }
+  return DSGD_OK;
+}
+
+static int persist_grid(const dsgd_ctx *ctx, int64_t batch) {
+  if (const char *e = getenv("DSGD_PERSIST_CTAS")) {
+    const int g = atoi(e);
+    if (g > 0) return std::min(g, ctx->sm_count);
+  }
+  return (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(cdiv(batch, kPRowWarps), 32));
+}
+
+static int persist_run(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t n_per_step, int64_t n_steps, double lr,
+                       double *losses_dev) {
+  int rc = persist_prepare(ctx, n_steps);
+  if (rc) return rc;
+  const int G = persist_grid(ctx, n_per_step);
+  NEED((uint64_t)G * (uint64_t)(n_steps + 2) < (1ull << 32), DSGD_ERR_INVALID, "dsgd_sync_steps: too many steps for one launch");
+  const size_t vd = sizeof(double) * (size_t)ctx->dim;
+  CU(cudaMemcpyAsync(ctx->p_wbuf[1], ctx->w, vd, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemsetAsync(ctx->p_hinge, 0, sizeof(unsigned) * (size_t)n_steps, ctx->stream));
+  CU(cudaMemsetAsync(ctx->p_bar, 0, sizeof(unsigned) * 4, ctx->stream));
+  PersistParams pp;
+  pp.rp16 = ctx->rp16; pp.pairs = ctx->pairs; pp.label = ctx->label; pp.samples = samples_dev;
+  pp.n_steps = n_steps; pp.batch = (int32_t)n_per_step; pp.dim = ctx->dim;
+  pp.wbuf[0] = ctx->p_wbuf[0]; pp.wbuf[1] = ctx->p_wbuf[1];
+  for (int i = 0; i < 3; ++i) pp.gbuf[i] = ctx->p_gbuf[i];
+  pp.d = ctx->d; pp.partial = ctx->p_partial; pp.hinge = ctx->p_hinge; pp.losses = losses_dev;
+  pp.w_out = ctx->w; pp.w32_out = ctx->w32; pp.scal = ctx->scal;
+  pp.bar = ctx->p_bar; pp.abort_flag = reinterpret_cast<int *>(ctx->p_bar + 1);
+  pp.lambda = ctx->lambda; pp.lr = lr; pp.k_den = 1.0;
+  pp.tl = nullptr;
+  if (getenv("DSGD_PERSIST_TIMELINE")) {
+    if (!ctx->p_tl) CU(cudaMalloc(&ctx->p_tl, sizeof(long long) * 256 * 16));
+    CU(cudaMemsetAsync(ctx->p_tl, 0, sizeof(long long) * 256 * 16, ctx->stream));
+    pp.tl = ctx->p_tl;
+  }
+  pp.timeout_cycles = 4000000000ll;  // ~2 s at 1.9 GHz: a healthy barrier takes well under a microsecond
+  void *args[] = {&pp};
+  auto *pe = prof_slot(ctx);
+  if (pe) cudaEventRecord(pe->first, ctx->stream);
+  CU(cudaLaunchCooperativeKernel((void *)k_sync_persistent<kPRowWarps, kPUpdWarps, kPSlots, kPCap>, dim3(G),
+                                 dim3((kPRowWarps + kPUpdWarps) * 32), args, sizeof(PSmem), ctx->stream));
+  if (pe) cudaEventRecord(pe->second, ctx->stream);
+  LAUNCHED();
+  return DSGD_OK;
+}
+
+static int persist_check(dsgd_ctx *ctx) {  // after a stream sync: did a device-side wait hit its watchdog?
+  if (!ctx->p_ready) return DSGD_OK;
+  unsigned host[2] = {0, 0};
+  CU(cudaMemcpy(host, ctx->p_bar, sizeof host, cudaMemcpyDeviceToHost));
+  NEED(host[1] == 0, DSGD_ERR_TIMEOUT, "persistent sync kernel: a grid barrier hit its watchdog (arrivals %u)", host[0]);
+  return DSGD_OK;
+}
+
+// Debug: copies the last persistent run's clock64 timeline (256 steps x 16 stamps) out; needs DSGD_PERSIST_TIMELINE.
+extern "C" int dsgd_debug_timeline(dsgd_ctx *ctx, long long *out) {
+  if (!ctx || !out) return DSGD_ERR_INVALID;
+  NEED(ctx->p_tl, DSGD_ERR_STATE, "no timeline recorded (set DSGD_PERSIST_TIMELINE=1)");
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpy(out, ctx->p_tl, sizeof(long long) * 256 * 16, cudaMemcpyDeviceToHost));
+  return DSGD_OK;
+}
+
 extern "C" int dsgd_set_workers(dsgd_ctx *ctx, int32_t n_local, const int32_t *counts, int32_t k_total) {
   if (!ctx) return DSGD_ERR_INVALID;
   NEED(n_local >= 0 && k_total >= 0, DSGD_ERR_INVALID, "dsgd_set_workers: negative count");
@@ -612,6 +714,11 @@ extern "C" int dsgd_sync_steps_staged(dsgd_ctx *ctx, int64_t first, int64_t n_pe
   const int fin_blocks = cdiv(ctx->dim + 1, 256);
   const int32_t k_total = ctx->k_total > 0 ? ctx->k_total : ctx->world;
   const bool single = (ctx->world == 1 && ctx->n_local == 1 && k_total == 1);
+  static const bool no_persist = getenv("DSGD_NO_PERSIST") != nullptr;
+  if (single && !no_persist && n_steps > 0) {
+    // one worker on one GPU: the whole run of steps is one persistent cooperative kernel
+    return persist_run(ctx, ctx->samples + first, n_per_step, n_steps, lr, want_losses ? ctx->losses : nullptr);
+  }
   for (int64_t s = 0; s < n_steps; ++s) {
     const int32_t *smp = ctx->samples + first + s * n_per_step;
     double *loss_dev = want_losses ? ctx->losses + s : nullptr;
@@ -660,7 +767,7 @@ extern "C" int dsgd_read_losses(dsgd_ctx *ctx, double *losses_out, int64_t n_ste
   if (n_steps)
     CU(cudaMemcpyAsync(losses_out, ctx->losses, sizeof(double) * (size_t)n_steps, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  return DSGD_OK;
+  return persist_check(ctx);
 }
 
 extern "C" int dsgd_sync_steps(dsgd_ctx *ctx, const int32_t *samples, int64_t n_per_step, int64_t n_steps, double lr,
@@ -674,7 +781,7 @@ extern "C" int dsgd_sync_steps(dsgd_ctx *ctx, const int32_t *samples, int64_t n_
   if ((rc = dsgd_sync_steps_staged(ctx, 0, n_per_step, n_steps, lr, losses_out != nullptr))) return rc;
   if (losses_out) return dsgd_read_losses(ctx, losses_out, n_steps);
   CU(cudaStreamSynchronize(ctx->stream));
-  return DSGD_OK;
+  return persist_check(ctx);
 }
 
 extern "C" int dsgd_sync_step(dsgd_ctx *ctx, const int32_t *samples, int64_t n, double lr, double *loss_out) {

@@ -1,0 +1,130 @@
+// Dev microbenchmarks for the latency model of the persistent SGD kernel (sm_100a).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o microbench microbench.cu && ./microbench
+#include <cooperative_groups.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include <vector>
+namespace cg = cooperative_groups;
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1);} } while (0)
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned *p) { unsigned v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void red_release_gpu_add(unsigned *p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_relaxed_gpu_add(unsigned *p, unsigned v) { asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// 1. pointer chase: latency of dependent loads (.cg = L2, default = L1 allowed)
+template <int MODE>
+__global__ void k_chase(const unsigned *chain, int hops, long long *out, unsigned *sink) {
+  unsigned i = 0;
+  long long t0 = clock64();
+  for (int h = 0; h < hops; ++h) {
+    if (MODE == 0) i = __ldcg(&chain[i]);
+    else if (MODE == 1) i = chain[i];
+    else i = ld_relaxed_gpu(&chain[i]);
+  }
+  long long t1 = clock64();
+  *out = (t1 - t0) / hops;
+  *sink = i;
+}
+
+// 2. grid barrier cost: G CTAs, each interval does nothing but the barrier
+template <int MODE>
+__global__ void k_barrier(unsigned *bar, int iters, long long *out) {
+  __shared__ int dummy;
+  long long t0 = clock64();
+  for (int it = 1; it <= iters; ++it) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned target = (unsigned)it * gridDim.x;
+      if (MODE == 0) { red_release_gpu_add(bar, 1u); while (ld_acquire_gpu(bar) < target) {} }
+      else if (MODE == 1) { __threadfence(); atomicAdd(bar, 1u); while (*(volatile unsigned *)bar < target) {} __threadfence(); }
+      else { red_relaxed_gpu_add(bar, 1u); while (ld_relaxed_gpu(bar) < target) {} }
+      dummy = it;
+    }
+    __syncthreads();
+  }
+  long long t1 = clock64();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out = (t1 - t0) / iters;
+}
+__global__ void k_cg_barrier(int iters, long long *out) {
+  cg::grid_group g = cg::this_grid();
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) g.sync();
+  long long t1 = clock64();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out = (t1 - t0) / iters;
+}
+
+// 3. RED throughput: each of nthreads does `reps` REDs; addresses either all distinct-ish or a few hot ones
+template <typename T>
+__global__ void k_red(T *buf, int n_addr, int reps, long long *out) {
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  long long t0 = clock64();
+  unsigned a = tid * 2654435761u;
+  for (int r = 0; r < reps; ++r) { a = a * 1664525u + 1013904223u; atomicAdd(&buf[(a >> 8) % n_addr], (T)1); }
+  __threadfence();
+  long long t1 = clock64();
+  if (tid == 0) *out = (t1 - t0);
+}
+
+// 4. store -> release -> observe latency: CTA 0 writes a flag, CTA 1 polls it; round trip ping-pong
+__global__ void k_pingpong(unsigned *flags, int iters, long long *out) {
+  if (threadIdx.x != 0) return;
+  long long t0 = clock64();
+  if (blockIdx.x == 0) {
+    for (int it = 1; it <= iters; ++it) { red_release_gpu_add(&flags[0], 1u); while (ld_acquire_gpu(&flags[32]) < (unsigned)it) {} }
+    *out = (clock64() - t0) / iters;
+  } else {
+    for (int it = 1; it <= iters; ++it) { while (ld_acquire_gpu(&flags[0]) < (unsigned)it) {} red_release_gpu_add(&flags[32], 1u); }
+  }
+}
+
+int main() {
+  int dev = 0; CK(cudaSetDevice(dev));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, dev));
+  printf("%s, %d SMs, clock %d kHz\n", prop.name, prop.multiProcessorCount, prop.clockRate);
+  long long *out; CK(cudaMallocManaged(&out, 8)); unsigned *sink; CK(cudaMalloc(&sink, 4));
+  // chase over 64 KB (L2 resident after first pass) and over 1 GB (DRAM)
+  for (size_t bytes : {size_t(64) << 10, size_t(8) << 20, size_t(1) << 30}) {
+    size_t n = bytes / 4; std::vector<unsigned> h(n);
+    // random single cycle with stride >= 128 B granularity
+    size_t lines = n / 32; std::vector<unsigned> perm(lines); for (size_t i = 0; i < lines; ++i) perm[i] = i;
+    for (size_t i = lines - 1; i > 0; --i) { size_t j = rand() % (i + 1); std::swap(perm[i], perm[j]); }
+    for (size_t i = 0; i < lines; ++i) h[perm[i] * 32] = perm[(i + 1) % lines] * 32;
+    unsigned *d; CK(cudaMalloc(&d, bytes)); CK(cudaMemcpy(d, h.data(), bytes, cudaMemcpyHostToDevice));
+    int hops = 20000;
+    for (int rep = 0; rep < 2; ++rep) {
+      k_chase<0><<<1, 1>>>(d, hops, out, sink); CK(cudaDeviceSynchronize()); long long a = *out;
+      k_chase<1><<<1, 1>>>(d, hops, out, sink); CK(cudaDeviceSynchronize()); long long b = *out;
+      k_chase<2><<<1, 1>>>(d, hops, out, sink); CK(cudaDeviceSynchronize()); long long c = *out;
+      if (rep) printf("chase %8zu KB: ld.cg %lld cyc/hop, ld (L1) %lld, ld.relaxed.gpu %lld\n", bytes >> 10, a, b, c);
+    }
+    CK(cudaFree(d));
+  }
+  unsigned *bar; CK(cudaMalloc(&bar, 1024));
+  for (int G : {2, 8, 32, 64, 148}) {
+    long long r[4];
+    for (int mode = 0; mode < 3; ++mode) {
+      CK(cudaMemset(bar, 0, 1024));
+      int iters = 2000; void *args[] = {&bar, &iters, &out};
+      void *fn = mode == 0 ? (void *)k_barrier<0> : mode == 1 ? (void *)k_barrier<1> : (void *)k_barrier<2>;
+      CK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(512), args, 0, 0)); CK(cudaDeviceSynchronize()); r[mode] = *out;
+    }
+    { int iters = 2000; void *args[] = {&iters, &out};
+      CK(cudaLaunchCooperativeKernel((void *)k_cg_barrier, dim3(G), dim3(512), args, 0, 0)); CK(cudaDeviceSynchronize()); r[3] = *out; }
+    printf("grid barrier G=%3d x512thr: red.release/ld.acquire %lld cyc, fence+atomic+volatile %lld, relaxed %lld, cg::grid.sync %lld\n", G, r[0], r[1], r[2], r[3]);
+  }
+  { CK(cudaMemset(bar, 0, 1024)); int iters = 2000; k_pingpong<<<2, 32>>>(bar, iters, out); CK(cudaDeviceSynchronize());
+    printf("ping-pong round trip (release add -> acquire poll, two CTAs): %lld cyc\n", *out); }
+  double *bd; float *bf; CK(cudaMalloc(&bd, 8 << 20)); CK(cudaMalloc(&bf, 4 << 20)); CK(cudaMemset(bd, 0, 8 << 20)); CK(cudaMemset(bf, 0, 4 << 20));
+  for (int n_addr : {1, 16, 1024, 47236, 1 << 20}) {
+    for (int blocks : {32, 148}) {
+      int reps = 64;
+      k_red<double><<<blocks, 256>>>(bd, n_addr, reps, out); CK(cudaDeviceSynchronize()); long long a = *out;
+      k_red<float><<<blocks, 256>>>(bf, n_addr, reps, out); CK(cudaDeviceSynchronize()); long long b = *out;
+      double total = (double)blocks * 256 * reps;
+      printf("RED n_addr=%7d blocks=%3d: f64 %lld cyc (%.3f cyc/op chip-wide), f32 %lld cyc (%.3f)\n", n_addr, blocks, a, a / total, b, b / total);
+    }
+  }
+  return 0;
+}
