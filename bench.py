@@ -256,14 +256,17 @@ def main():
     # ---- leg 3: mean duration of the dominant kernel (gradient) over the same work -----------------------
     ctx.set_weights(np.zeros(data.dim))
     ctx.stage_samples(samples_np.reshape(-1))   # leg 2 re-staged one bench step at a time
-    ctx.profile_begin(sample_every=8)
+    ctx.profile_begin(sample_every=1)
     for i in range(args.warmup, total_steps):
         ctx.sync_steps_staged(i * S * B, B, S, LR, want_losses=False)
     k_ms, k_n = ctx.profile_end()
     barrier()
     hbm_peak, peak_src = peaks()
-    alg_per_launch = float(np.mean(alg_bytes_per_step[args.warmup:])) / S
+    # every launch of the dominant kernel was bracketed: algorithmic bytes of the region / launches
+    alg_per_launch = float(np.sum(alg_bytes_per_step[args.warmup:])) / max(k_n, 1)
     achieved = alg_per_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    kernel_name = ("k_sync_persistent (whole run of %d SGD steps per launch)" % S) if k_n == args.steps \
+        else "k_rows<scatter> (gradient, one launch per SGD step)"
     step_frac = (float(np.mean(alg_bytes_per_step[args.warmup:])) * args.steps / (ms * 1e-3) / 1e9) / hbm_peak
 
     # ---- leg 4: CPU baseline on this host (rank 0, N = 1 only) -------------------------------------------
@@ -287,7 +290,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(S * B * 4), "d2h_bytes_per_step": int(S * 8),
                     "api": "dsgd_sync_steps (C ABI, pinned host buffers)", "matches_device_leg": same},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_rows<scatter> (gradient)", "achieved": achieved, "peak": hbm_peak,
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_per_launch, "kernel_ms": k_ms, "launches_sampled": int(k_n),
                          "whole_step_frac": step_frac},

@@ -581,8 +581,9 @@ extern "C" int dsgd_comm_init(dsgd_ctx *ctx, const uint8_t id[DSGD_UNIQUE_ID_BYT
 }
 
 // ---- persistent single-worker loop ------------------------------------------------------------------------
-constexpr int kPRowWarps = 8, kPUpdWarps = 8, kPSlots = 8, kPCap = 256;
-using PSmem = PersistSmem<kPRowWarps, kPUpdWarps, kPSlots, kPCap>;
+constexpr int kPCons = 8, kPUpd = 6, kPStages = 8, kPStagePairs = 2560, kPMaxChunks = 128;
+using PSmem = PersistSmem<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks>;
+#define DSGD_PERSIST_KERNEL k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks>
 
 static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
   if (!ctx->p_ready) {
@@ -594,8 +595,7 @@ static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
     }
     CU(cudaMalloc(&ctx->p_partial, sizeof(double) * 2 * 2 * (size_t)ctx->sm_count));
     CU(cudaMalloc(&ctx->p_bar, sizeof(unsigned) * 4));
-    CU(cudaFuncSetAttribute(k_sync_persistent<kPRowWarps, kPUpdWarps, kPSlots, kPCap>,
-                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
+    CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
     ctx->p_ready = true;
   }
   if (ctx->p_hinge_cap < n_steps) {
@@ -608,12 +608,15 @@ static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
   return DSGD_OK;
 }
 
+// CTAs of the persistent kernel: every CTA owns at most kMaxRowsPerCta rows of a step.  0: batch too large.
 static int persist_grid(const dsgd_ctx *ctx, int64_t batch) {
+  const int g_min = cdiv(batch, kMaxRowsPerCta);
+  if (g_min > ctx->sm_count) return 0;
   if (const char *e = getenv("DSGD_PERSIST_CTAS")) {
     const int g = atoi(e);
-    if (g > 0) return std::min(g, ctx->sm_count);
+    if (g > 0) return std::max(g_min, std::min(g, ctx->sm_count));
   }
-  return (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(cdiv(batch, kPRowWarps), 32));
+  return ctx->sm_count;  // measured (tools/sweep_persist.py): one CTA per SM is fastest at batch 64, 256 and 1024
 }
 
 static int persist_run(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t n_per_step, int64_t n_steps, double lr,
@@ -645,8 +648,8 @@ static int persist_run(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t n_per_
   void *args[] = {&pp};
   auto *pe = prof_slot(ctx);
   if (pe) cudaEventRecord(pe->first, ctx->stream);
-  CU(cudaLaunchCooperativeKernel((void *)k_sync_persistent<kPRowWarps, kPUpdWarps, kPSlots, kPCap>, dim3(G),
-                                 dim3((kPRowWarps + kPUpdWarps) * 32), args, sizeof(PSmem), ctx->stream));
+  CU(cudaLaunchCooperativeKernel((void *)DSGD_PERSIST_KERNEL, dim3(G), dim3((kPCons + kPUpd + 1) * 32), args, sizeof(PSmem),
+                                 ctx->stream));
   if (pe) cudaEventRecord(pe->second, ctx->stream);
   LAUNCHED();
   return DSGD_OK;
@@ -715,7 +718,7 @@ extern "C" int dsgd_sync_steps_staged(dsgd_ctx *ctx, int64_t first, int64_t n_pe
   const int32_t k_total = ctx->k_total > 0 ? ctx->k_total : ctx->world;
   const bool single = (ctx->world == 1 && ctx->n_local == 1 && k_total == 1);
   static const bool no_persist = getenv("DSGD_NO_PERSIST") != nullptr;
-  if (single && !no_persist && n_steps > 0) {
+  if (single && !no_persist && n_steps > 0 && persist_grid(ctx, n_per_step) > 0) {
     // one worker on one GPU: the whole run of steps is one persistent cooperative kernel
     return persist_run(ctx, ctx->samples + first, n_per_step, n_steps, lr, want_losses ? ctx->losses : nullptr);
   }

@@ -1,25 +1,29 @@
-// dsgd_persistent.cuh -- the synchronous SGD loop as ONE persistent cooperative kernel (sm_100a).
+// dsgd_persistent.cuh -- the synchronous SGD loop as ONE persistent, warp-specialised cooperative kernel.
 //
 // Replaces, for a whole run of consecutive steps, the body of Master.fit's batch loop
 // (core/Master.scala:179-198) together with the slave's gradient request (core/Slave.scala:142-157):
 // no launch, no host round trip and exactly ONE grid-wide barrier per SGD step.
 //
-// Why it looks the way it does (measured in profiles/r1a: a two-kernel step costs 25 us while its 256
-// row windows are 197 KB -- the step is a chain of dependent latencies, not bandwidth):
-//   * Row windows do not depend on the weights, so they are fetched AHEAD of the step that needs them:
-//     each row warp owns a ring of shared-memory slots filled by TMA bulk copies (cp.async.bulk +
-//     mbarrier complete_tx), issued kSlots rows in advance; the sample id -> row pointer -> window
-//     address chain is software-pipelined two further rows ahead in registers.
-//   * Weights are double-buffered and gradients triple-buffered in L2 so that the update of step t and
-//     the gradient of step t+1 run in the SAME barrier interval: a row warp reads W_{t-1}[col] and
-//     g_{t-1}[col] and applies the update arithmetic itself ("on the fly") while the update warps write
-//     the same values to the W_t buffer for the interval after.  One barrier per step instead of two.
-//   * c = 2*lambda*(w . d) and ||w||^2 of every new weight vector are produced by the update warps as
-//     per-CTA partials and summed by every warp in a fixed order: deterministic, no extra barrier.
+// Measured facts this design answers (profiles/r1a, r1b; tools/microbench.cu on a B200):
+//   L2 hit 307 cycles; a gpu-scope release/acquire grid barrier ~2300 cycles; a two-kernel step 25 us for
+//   197 KB of row windows.  The step is a chain of dependent latencies, so the kernel removes links:
+//   * PRODUCER warp (one per CTA): row windows do not depend on the weights, so it walks the sample ids
+//     kStages steps ahead -- ids -> row pointers -> one TMA bulk copy (cp.async.bulk, mbarrier
+//     complete_tx) per row into the stage's shared-memory partition, plus a chunk list.  Full/empty
+//     mbarriers per stage, the classic TMA pipeline.
+//   * CONSUMER warps: the CTA's rows of a step are cut into 128-pair chunks dealt round-robin to the
+//     warps, so one 2000-nnz row does not serialise a warp (the step time is the MAX over rows).  Pass 1:
+//     partial dots per chunk (fixed order -> deterministic); pass 2: gate per row, RED y*x into g.
+//   * UPDATE warps: weights are double-buffered and gradients triple-buffered in L2 so the update of step
+//     t-1 and the gradient of step t share one barrier interval: consumers read W_{t-1}[col], g_{t-1}[col]
+//     and apply the update arithmetic themselves ("on the fly") while the update warps write the same
+//     values into the W_t buffer for the interval after, zero the buffer g_{t+1} will use and reduce
+//     c_t = 2*lambda*(W_t . d) and ||W_t||^2 to per-CTA partials (summed in a fixed order by one warp per
+//     CTA and handed to the others through shared memory).
 //
-// Interval I_t (between barrier t-1 and barrier t), with W_t the weights step t differentiates at:
-//   row warps   : x.W_t with W_t[col] computed on the fly from (W_{t-1}, g_{t-1}, c_{t-1}); gate; RED y*x into g_t
-//   update warps: W_t buffer <- update(W_{t-1}, g_{t-1}, c_{t-1}); zero g_{t+1}'s buffer; partials of c_t, ||W_t||^2
+// Interval I_t (between grid barrier t-1 and t), with W_t the weights step t differentiates at:
+//   consumers: x.W_t with W_t[col] = update(W_{t-1}[col], g_{t-1}[col], c_{t-1}); gate; RED into g_t
+//   updaters : W_t buffer <- update(W_{t-1}, g_{t-1}, c_{t-1}); zero g_{t+1}'s buffer; partials of c_t, ||W_t||^2
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -39,17 +43,17 @@ struct PersistParams {
   double *wbuf[2];  // on entry wbuf[1] holds the initial weights ("W_{-1}" == W_0)
   double *gbuf[3];  // all zero on entry and on exit
   const double *d;
-  double *partial;         // [2][gridDim.x][2]
-  unsigned *hinge;         // [n_steps], zero on entry
-  double *losses;          // [n_steps] or nullptr
-  double *w_out;           // resident weights after the last step
+  double *partial;  // [2][gridDim.x][2]
+  unsigned *hinge;  // [n_steps], zero on entry
+  double *losses;   // [n_steps] or nullptr
+  double *w_out;    // resident weights after the last step
   float *w32_out;
-  double *scal;            // kScalC / kScalNrm2 of the resident weights
-  unsigned *bar;           // grid barrier counter, zero on entry
-  int *abort_flag;         // set to 1 if a wait hit the watchdog
+  double *scal;     // kScalC / kScalNrm2 of the resident weights
+  unsigned *bar;    // grid barrier counter, zero on entry
+  int *abort_flag;  // set to 1 if a wait hit the watchdog
   double lambda, lr, k_den;
   long long timeout_cycles;
-  long long *tl;           // debug timeline: [256 steps][16 stamps] of clock64 (CTA 0), or nullptr
+  long long *tl;    // debug timeline: [256 steps][16 stamps] of clock64 (CTA 0), or nullptr
 };
 
 // ---- PTX helpers: mbarrier + TMA bulk copy -------------------------------------------------------------
@@ -59,6 +63,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *b, unsigned count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *b, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *b) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -75,13 +82,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *b, unsigned parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+// Bounded wait: if the phase does not complete within `timeout` cycles (or somebody already raised the abort
+// flag) the flag is raised and the caller carries on -- results are then garbage, but nothing deadlocks and the
+// host turns the flag into DSGD_ERR_TIMEOUT.
+__device__ __forceinline__ void mbar_wait(uint64_t *b, unsigned parity, int *abort_flag, long long timeout) {
+  if (mbar_try_wait(b, parity)) return;
+  const long long t0 = clock64();
+  unsigned spins = 0;
+  while (!mbar_try_wait(b, parity)) {
+    if ((++spins & 255u) == 0u && (clock64() - t0 > timeout || *(volatile int *)abort_flag)) {
+      *(volatile int *)abort_flag = 1;
+      return;
+    }
+  }
+}
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned *p) {
   unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void red_release_gpu_add(unsigned *p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
 
 // w_j after one SGD update given the raw gradient-sum entry (same arithmetic as k_update<true>):
@@ -92,7 +117,7 @@ __device__ __forceinline__ double apply_update(double wv, double graw, double c,
   if (v != 0.0) {
     if (add_c) v = filt(v + c);
     if (v != 0.0) {
-      const double mean = filt(v / k_den);
+      const double mean = (k_den == 1.0) ? v : filt(v / k_den);  // x / 1.0 == x exactly
       const double step = filt(mean * lr);
       wv = filt(wv - step);
     }
@@ -100,25 +125,42 @@ __device__ __forceinline__ double apply_update(double wv, double graw, double c,
   return wv;
 }
 
-// Fixed-order sum of the per-CTA partials (stride 2 doubles per CTA); identical in every warp.
-__device__ __forceinline__ double sum_partials(const double *p, int n_cta, int lane) {
-  double s = 0.0;
-  for (int b = lane; b < n_cta; b += 32) s += __ldcg(&p[2 * b]);
-  return warp_sum(s);
+// Fixed-order sums of the per-CTA partials {c-dot, ||w||^2} (2 doubles per CTA); the same in every CTA.
+// All loads are issued before the first add (up to kPartLoads per lane: covers 160 CTAs), so the cost is one
+// L2 round trip plus the shuffle tree rather than one round trip per 32 CTAs.
+constexpr int kPartLoads = 5;
+__device__ __forceinline__ void sum_partials2(const double *p, int n_cta, int lane, double &s0, double &s1) {
+  double2 v[kPartLoads];
+#pragma unroll
+  for (int i = 0; i < kPartLoads; ++i) {
+    const int b = lane + 32 * i;
+    v[i] = make_double2(0.0, 0.0);
+    if (b < n_cta) v[i] = __ldcg(reinterpret_cast<const double2 *>(p) + b);
+  }
+  double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+  for (int i = 0; i < kPartLoads; ++i) { a0 += v[i].x; a1 += v[i].y; }
+  for (int b = lane + 32 * kPartLoads; b < n_cta; b += 32) {  // more than 160 CTAs: not on a B200
+    const double2 w2 = __ldcg(reinterpret_cast<const double2 *>(p) + b);
+    a0 += w2.x; a1 += w2.y;
+  }
+  s0 = warp_sum(a0);
+  s1 = warp_sum(a1);
 }
 
-// One grid-wide barrier: every CTA arrives once; `target` = number of arrivals that completes this phase.
-// Returns false if the watchdog fired (or another CTA raised the abort flag).
+// One grid-wide barrier among the barrier-synchronised warps of every CTA (the producer warp stays out):
+// CTA-level named barrier, one release arrival, relaxed polling, one acquire fence.
+// `target` = number of arrivals that completes this phase.  Returns false if the watchdog fired.
 __device__ __forceinline__ bool grid_barrier(unsigned *bar, unsigned target, int *abort_flag, long long timeout,
-                                             int *smem_ok, long long *tl = nullptr) {
-  __syncthreads();
+                                             int *smem_ok, int n_sync_threads, long long *tl = nullptr) {
+  named_bar_sync(3, n_sync_threads);
   if (threadIdx.x == 0) {
     if (tl) tl[0] = clock64();
     red_release_gpu_add(bar, 1u);
     int ok = 1;
     const long long t0 = clock64();
     unsigned spins = 0;
-    while (ld_acquire_gpu(bar) < target) {
+    while (ld_relaxed_gpu(bar) < target) {
       if ((++spins & 1023u) == 0u) {
         if (clock64() - t0 > timeout || *(volatile int *)abort_flag) {
           *(volatile int *)abort_flag = 1;
@@ -127,112 +169,164 @@ __device__ __forceinline__ bool grid_barrier(unsigned *bar, unsigned target, int
         }
       }
     }
+    fence_acq_rel_gpu();
     *smem_ok = ok;
     if (tl) tl[1] = clock64();
   }
-  __syncthreads();
-  return *smem_ok != 0;
+  named_bar_sync(3, n_sync_threads);
+  return *(volatile int *)smem_ok != 0;
 }
+
+constexpr int kChunkPairs = 128;             // 4 pairs per lane per chunk
+constexpr uint32_t kChunkGlobal = 1u << 31;  // chunk offset flag: read from global, the row did not fit the stage
+constexpr int kMaxRowsPerCta = 32;           // rows of one step per CTA (one producer lane each)
+
+template <int kMaxChunks>
+struct StageMeta {
+  int n_rows;
+  int n_chunks;
+  int row_y[kMaxRowsPerCta];
+  uint32_t row_b[kMaxRowsPerCta];    // window start (16-byte units) -- for rows that missed the chunk list
+  int row_len[kMaxRowsPerCta];       // pairs, padding included
+  short row_first[kMaxRowsPerCta];   // first chunk of the row
+  short row_nch[kMaxRowsPerCta];     // chunks of the row; -1: not in the chunk list (whole-row slow path)
+  uint32_t ch_off[kMaxChunks];       // pair offset inside the stage partition, or kChunkGlobal | global pair index
+  short ch_n[kMaxChunks];            // pairs in the chunk (<= kChunkPairs)
+  short ch_row[kMaxChunks];          // local row
+  double part[kMaxChunks];           // pass-1 partial dot of the chunk
+};
+
+template <int kCons, int kUpd, int kStages, int kStagePairs, int kMaxChunks>
+struct PersistSmem {
+  uint2 ring[kStages][kStagePairs];
+  StageMeta<kMaxChunks> meta[kStages];
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t c_bar[2];
+  double c_val[2];
+  double red[kUpd][2];
+  unsigned hinge_acc;
+  int ok;
+};
 
 #define DSGD_TL(slot_)                                                                        \
   do {                                                                                        \
     if (p.tl && blockIdx.x == 0 && lane == 0 && t < 256) p.tl[t * 16 + (slot_)] = clock64(); \
   } while (0)
 
-template <int kRowWarps, int kUpdWarps, int kSlots, int kCapPairs>
-struct PersistSmem {
-  uint2 ring[kRowWarps][kSlots][kCapPairs];
-  uint64_t mbar[kRowWarps][kSlots];
-  double red[kUpdWarps][2];
-  int ok;
-};
-
-template <int kRowWarps, int kUpdWarps, int kSlots, int kCapPairs>
-__global__ void __launch_bounds__((kRowWarps + kUpdWarps) * 32, 1) k_sync_persistent(const PersistParams p) {
-  using Smem = PersistSmem<kRowWarps, kUpdWarps, kSlots, kCapPairs>;
+template <int kCons, int kUpd, int kStages, int kStagePairs, int kMaxChunks>
+__global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(const PersistParams p) {
+  using Smem = PersistSmem<kCons, kUpd, kStages, kStagePairs, kMaxChunks>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const bool is_row = warp < kRowWarps;
+  const bool is_cons = warp < kCons;
+  const bool is_upd = warp >= kCons && warp < kCons + kUpd;
   const int G = gridDim.x;
   const int B = p.batch;
   const int64_t S = p.n_steps;
+  constexpr int kSyncThreads = (kCons + kUpd) * 32;
+  // rows of a step owned by this CTA: i = blockIdx.x + m * G  (a small batch is spread over all CTAs); <= 32
+  const int n_r = (B > (int)blockIdx.x) ? (B - 1 - (int)blockIdx.x) / G + 1 : 0;
 
-  if (is_row && lane == 0) {
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s) mbar_init(&sm.mbar[warp][s], 1u);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&sm.full[s], 1u);
+      mbar_init(&sm.empty[s], (unsigned)kCons);
+    }
+    mbar_init(&sm.c_bar[0], 1u);
+    mbar_init(&sm.c_bar[1], 1u);
+    sm.hinge_acc = 0u;
+    sm.ok = 1;
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
 
-  // ---- row-warp prefetch pipeline state (all lanes hold the same values) -------------------------------
-  const int NW = G * kRowWarps;
-  const int wg = warp * G + blockIdx.x;  // row i of a step goes to CTA i % G: spreads a small batch over all CTAs
-  const int RPW = (B + NW - 1) / NW;     // rows per warp per step
-  const int64_t Q = S * RPW;             // length of this warp's row sequence (some entries may be holes)
-  // per-slot metadata of the rows currently in the ring
-  uint32_t m_start[kSlots];  // window start, 16-byte units
-  int m_len[kSlots];         // pairs, padding included; -1: hole (no row)
-  int m_y[kSlots];
-  unsigned m_par[kSlots];    // mbarrier phase parity the copy into this slot completes
-  unsigned par_mask = 0u;    // bit s: parity of the NEXT copy into slot s
-  // two-deep register pipeline ahead of the copy: ids, then row pointers
-  int64_t q_next = 0;           // next sequence number to enter stage A
-  int32_t stA_row = -1;         // stage A result: row id of q_next-1 (or -1 hole)
-  int32_t stB_len = -1;         // stage B result: window of q_next-2
-  uint32_t stB_start = 0;
-  int stB_y = 0;
-
-  auto seq_row = [&](int64_t q) -> int32_t {  // row id of sequence entry q, or -1
-    if (q >= Q) return -1;
-    const int64_t t = q / RPW;
-    const int i = wg + (int)(q % RPW) * NW;
-    return i < B ? __ldg(&p.samples[t * B + i]) : -1;
-  };
-  auto stage_a = [&]() { stA_row = seq_row(q_next); ++q_next; };
-  auto stage_b = [&]() {  // consumes stA_row
-    if (stA_row >= 0) {
-      const uint32_t b = __ldg(&p.rp16[stA_row]), e = __ldg(&p.rp16[stA_row + 1]);
-      stB_start = b;
-      stB_len = (int)(e - b) * 2;
-      stB_y = (int)__ldg(&p.label[stA_row]);
-    } else {
-      stB_len = -1;
-    }
-  };
-  auto stage_c = [&](int slot) {  // consumes stB_*: TMA the window (its first kCapPairs pairs) into `slot`
-    m_start[slot] = stB_start;
-    m_len[slot] = stB_len;
-    m_y[slot] = stB_y;
-    m_par[slot] = (par_mask >> slot) & 1u;
-    if (stB_len > 0) par_mask ^= (1u << slot);
-    if (stB_len > 0 && lane == 0) {
-      const unsigned bytes = (unsigned)(stB_len < kCapPairs ? stB_len : kCapPairs) * 8u;
-      mbar_expect_tx(&sm.mbar[warp][slot], bytes);
-      bulk_g2s(&sm.ring[warp][slot][0], p.pairs + (size_t)stB_start * 2, bytes, &sm.mbar[warp][slot]);
-    }
-  };
-
-  if (is_row) {
-    // prologue: fill the ring (blocking loads, once)
-    stage_a();
-    stage_b();
-    stage_a();
+  // =========================================================================================================
+  // PRODUCER warp: runs ahead of everybody else, bounded only by the empty[] barriers.  Lane m owns row m.
+  // =========================================================================================================
+  if (!is_cons && !is_upd) {
+    auto load_id = [&](int64_t t) -> int32_t {
+      return (t < S && lane < n_r) ? __ldg(&p.samples[t * B + blockIdx.x + lane * G]) : -1;
+    };
+    uint32_t b0 = 0, e0 = 0, b1 = 0, e1 = 0;
+    int y0 = 0, y1 = 0;
+    auto load_win = [&](int32_t id, uint32_t &b, uint32_t &e, int &y) {
+      b = 0u; e = 0u; y = 0;
+      if (id >= 0) {
+        b = __ldg(&p.rp16[id]);
+        e = __ldg(&p.rp16[id + 1]);
+        y = (int)__ldg(&p.label[id]);
+      }
+    };
+    load_win(load_id(0), b0, e0, y0);   // window of step t      (stage C input)
+    load_win(load_id(1), b1, e1, y1);   // window of step t + 1  (stage B)
+    int32_t id_next = load_id(2);       // sample id of step t + 2 (stage A)
+    for (int64_t t = 0; t < S; ++t) {
+      const int st = (int)(t % kStages);
+      if (t >= kStages) {
+        mbar_wait(&sm.empty[st], (unsigned)(((t / kStages) - 1) & 1), p.abort_flag, p.timeout_cycles);
+        if (*(volatile int *)p.abort_flag) return;  // the barrier-synchronised warps gave up (watchdog)
+      }
+      auto &mt = sm.meta[st];
+      // lay the rows out: exclusive scans over the CTA's rows of pairs and chunks
+      const int len = (lane < n_r) ? (int)(e0 - b0) * 2 : 0;
+      const int nch = (len + kChunkPairs - 1) / kChunkPairs;
+      int ps = len, cs = nch;  // inclusive warp scans
 #pragma unroll
-    for (int s = 0; s < kSlots; ++s) {
-      stage_c(s);
-      stage_b();
-      stage_a();
+      for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, ps, o), c2 = __shfl_up_sync(0xffffffffu, cs, o);
+        if (lane >= o) { ps += a; cs += c2; }
+      }
+      const int my_pair = ps - len, my_chunk = cs - nch;
+      const int tot_chunks = __shfl_sync(0xffffffffu, cs, 31);
+      const bool listed = (my_chunk + nch) <= kMaxChunks;           // prefix property: later rows miss too
+      const bool in_ring = listed && (my_pair + len) <= kStagePairs;
+      if (lane < n_r) {
+        mt.row_y[lane] = y0;
+        mt.row_b[lane] = b0;
+        mt.row_len[lane] = len;
+        mt.row_first[lane] = (short)my_chunk;
+        mt.row_nch[lane] = (short)(listed ? nch : -1);
+        if (listed) {
+          for (int c = 0; c < nch; ++c) {
+            const int n = min(kChunkPairs, len - c * kChunkPairs);
+            mt.ch_off[my_chunk + c] = in_ring ? (uint32_t)(my_pair + c * kChunkPairs)
+                                              : (kChunkGlobal | (b0 * 2u + (uint32_t)(c * kChunkPairs)));
+            mt.ch_n[my_chunk + c] = (short)n;
+            mt.ch_row[my_chunk + c] = (short)lane;
+          }
+        }
+      }
+      const unsigned my_bytes = (lane < n_r && in_ring) ? (unsigned)len * 8u : 0u;
+      unsigned ring_bytes = my_bytes;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ring_bytes += __shfl_xor_sync(0xffffffffu, ring_bytes, o);
+      if (lane == 0) {
+        mt.n_rows = n_r;
+        mt.n_chunks = tot_chunks < kMaxChunks ? tot_chunks : kMaxChunks;
+      }
+      __syncwarp();  // every lane's metadata is written before lane 0 arrives on the full barrier
+      if (lane == 0) {
+        if (ring_bytes) mbar_expect_tx(&sm.full[st], ring_bytes);
+        else mbar_arrive(&sm.full[st]);  // metadata only: complete the phase
+      }
+      __syncwarp();
+      if (my_bytes) bulk_g2s(&sm.ring[st][my_pair], p.pairs + (size_t)b0 * 2, my_bytes, &sm.full[st]);
+      // advance the register pipeline
+      b0 = b1; e0 = e1; y0 = y1;
+      load_win(id_next, b1, e1, y1);
+      id_next = load_id(t + 3);
     }
+    return;
   }
 
-  const int n_upd = G * kUpdWarps * 32;
-  const int u0 = blockIdx.x * kUpdWarps * 32 + (threadIdx.x - kRowWarps * 32);
+  const int n_upd = G * kUpd * 32;
+  const int u0 = blockIdx.x * kUpd * 32 + (threadIdx.x - kCons * 32);
   const double k_den = p.k_den, lr = p.lr;
   unsigned phase = 0;
-  int64_t q = 0;  // row warps: next sequence entry to consume
 
   for (int64_t t = 0; t <= S; ++t) {
     const double *Wprev = p.wbuf[(t + 1) & 1];
@@ -242,91 +336,147 @@ __global__ void __launch_bounds__((kRowWarps + kUpdWarps) * 32, 1) k_sync_persis
     double *Gzero = p.gbuf[(t + 1) % 3];
     const double *part_prev = p.partial + (size_t)((t + 1) & 1) * G * 2;
     double *part_cur = p.partial + (size_t)(t & 1) * G * 2;
+    const unsigned c_par = (unsigned)((t >> 1) & 1);
 
-    // c_{t-1} = 2*lambda*(W_{t-1} . d): at t == 0 g_{-1} is all zero, so its value is irrelevant
-    if (warp == 0) DSGD_TL(0);
-    if (warp == kRowWarps) DSGD_TL(8);
-    double c_prev = 0.0;
-    if (t > 0) c_prev = p.lambda * 2.0 * sum_partials(part_prev, G, lane);
-    if (warp == 0) DSGD_TL(1);
-    const bool add_c = (c_prev != 0.0) && (fabs(c_prev) > kEps);
-
-    if (is_row) {
+    if (is_cons) {
+      if (warp == 0) DSGD_TL(0);
       if (t < S) {
+        const int st = (int)(t % kStages);
+        auto &mt = sm.meta[st];
+        mbar_wait(&sm.full[st], (unsigned)((t / kStages) & 1), p.abort_flag, p.timeout_cycles);
+        if (warp == 0) DSGD_TL(1);
+        const int n_ch = mt.n_chunks;
+        const uint2 *ring = &sm.ring[st][0];
+        double c_prev = 0.0;
+        bool add_c = false, have_c = false;
+        auto get_c = [&]() {  // c_{t-1}: summed by update warp 0 of this CTA, handed over through shared memory
+          if (!have_c) {
+            mbar_wait(&sm.c_bar[t & 1], c_par, p.abort_flag, p.timeout_cycles);
+            c_prev = sm.c_val[t & 1];
+            add_c = (c_prev != 0.0) && (fabs(c_prev) > kEps);
+            have_c = true;
+          }
+        };
+        // ---- pass 1: partial dots of this warp's chunks ----
+        for (int c = warp; c < n_ch; c += kCons) {
+          const uint32_t off = mt.ch_off[c];
+          const int n = mt.ch_n[c];
+          const uint2 *src = (off & kChunkGlobal) ? (p.pairs + (off & ~kChunkGlobal)) : (ring + off);
+          uint2 pr[4];
+          double wv[4], gv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int k = u * 32 + lane;
+            pr[u] = (k < n) ? src[k] : make_uint2(0u, 0u);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int k = u * 32 + lane;
+            wv[u] = 0.0;
+            gv[u] = 0.0;
+            if (k < n) {
+              wv[u] = __ldcg(&Wprev[pr[u].x]);
+              gv[u] = __ldcg(&Gprev[pr[u].x]);
+            }
+          }
+          get_c();
+          double acc = 0.0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const double xv = filt((double)__uint_as_float(pr[u].y));
+            const double wt = apply_update(wv[u], gv[u], c_prev, add_c, k_den, lr);
+            acc += filt(xv * wt);  // (x * w).sum  (math/Vec.scala:58)
+          }
+          acc = warp_sum(acc);
+          if (lane == 0) mt.part[c] = acc;
+        }
+        if (warp == 0) DSGD_TL(2);
+        named_bar_sync(2, kCons * 32);
+        // ---- pass 2: row dot (chunk partials in order), prediction, gate, scatter ----
         unsigned hinge = 0;
-        for (int m = 0; m < RPW; ++m, ++q) {
-          const int slot = (int)(q % kSlots);
-          // static indexing of the register arrays
-          uint32_t start = 0;
-          unsigned parity = 0u;
-          int len = -1, yi = 0;
-#pragma unroll
-          for (int s = 0; s < kSlots; ++s)
-            if (s == slot) { start = m_start[s]; len = m_len[s]; yi = m_y[s]; parity = m_par[s]; }
-          if (len >= 0) {
-            const int n_smem = len < kCapPairs ? len : kCapPairs;
-            const uint2 *srow = &sm.ring[warp][slot][0];
-            const uint2 *grow = p.pairs + (size_t)start * 2;
-            if (len > 0) {
-              while (!mbar_try_wait(&sm.mbar[warp][slot], parity)) {}
-            }
-            if (warp == 0) DSGD_TL(2);
-            double acc = 0.0;
-            for (int k0 = 0; k0 < len; k0 += 128) {
-              uint2 pr[4];
-              double wv[4], gv[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int k = k0 + u * 32 + lane;
-                pr[u] = make_uint2(0u, 0u);
-                if (k < len) pr[u] = (k < n_smem) ? srow[k] : __ldg(&grow[k]);
-              }
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int k = k0 + u * 32 + lane;
-                wv[u] = 0.0;
-                gv[u] = 0.0;
-                if (k < len) {
-                  wv[u] = __ldcg(&Wprev[pr[u].x]);
-                  gv[u] = __ldcg(&Gprev[pr[u].x]);
-                }
-              }
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const double xv = filt((double)__uint_as_float(pr[u].y));
-                const double wt = apply_update(wv[u], gv[u], c_prev, add_c, k_den, lr);
-                acc += filt(xv * wt);  // (x * w).sum  (math/Vec.scala:58)
-              }
-            }
-            const double dot = warp_sum(acc);
-            if (warp == 0) DSGD_TL(3);
-            const double y = (double)yi;
+        for (int c = warp; c < n_ch; c += kCons) {
+          const int row = mt.ch_row[c];
+          const int first = mt.row_first[row], nch = mt.row_nch[row];
+          double dot = 0.0;
+          for (int i = 0; i < nch; ++i) dot += mt.part[first + i];
+          const int yi = mt.row_y[row];
+          const double y = (double)yi;
+          if (c == first && lane == 0) {
             const int pred = (dot > 0.0) ? -1 : ((dot < 0.0) ? 1 : 0);
             hinge += (unsigned)(1 - yi * pred);
-            if (!(y * dot < 0.0)) {  // SparseSVM.scala:28
+          }
+          if (!(y * dot < 0.0)) {  // SparseSVM.scala:28
+            const uint32_t off = mt.ch_off[c];
+            const int n = mt.ch_n[c];
+            const uint2 *src = (off & kChunkGlobal) ? (p.pairs + (off & ~kChunkGlobal)) : (ring + off);
+            for (int k = lane; k < n; k += 32) {
+              const uint2 pr = src[k];
+              const double gvv = filt(filt((double)__uint_as_float(pr.y)) * y);
+              if (gvv != 0.0) atomicAdd(&Gcur[pr.x], gvv);
+            }
+          }
+        }
+        // rows outside the chunk list: empty rows (dot 0 -> prediction 0, hinge 1, nothing to scatter) and, if a
+        // step ever overflows the chunk list, whole rows straight from global memory, one warp per row
+        for (int m = warp; m < mt.n_rows; m += kCons) {
+          const int nch = mt.row_nch[m];
+          if (nch == 0) {
+            if (lane == 0) hinge += 1u;
+          } else if (nch < 0) {
+            const uint2 *grow = p.pairs + (size_t)mt.row_b[m] * 2;
+            const int len = mt.row_len[m];
+            get_c();
+            double acc = 0.0;
+            for (int k = lane; k < len; k += 32) {
+              const uint2 pr = __ldg(&grow[k]);
+              const double wt = apply_update(__ldcg(&Wprev[pr.x]), __ldcg(&Gprev[pr.x]), c_prev, add_c, k_den, lr);
+              acc += filt(filt((double)__uint_as_float(pr.y)) * wt);
+            }
+            const double dot = warp_sum(acc);
+            const int yi = mt.row_y[m];
+            const double y = (double)yi;
+            if (lane == 0) {
+              const int pred = (dot > 0.0) ? -1 : ((dot < 0.0) ? 1 : 0);
+              hinge += (unsigned)(1 - yi * pred);
+            }
+            if (!(y * dot < 0.0)) {
               for (int k = lane; k < len; k += 32) {
-                const uint2 pr = (k < n_smem) ? srow[k] : __ldg(&grow[k]);
+                const uint2 pr = __ldg(&grow[k]);
                 const double gvv = filt(filt((double)__uint_as_float(pr.y)) * y);
                 if (gvv != 0.0) atomicAdd(&Gcur[pr.x], gvv);
               }
             }
           }
-          if (warp == 0) DSGD_TL(4);
-          __syncwarp();
-          // the slot is free: refill it kSlots rows ahead, advance the register pipeline
-          {
-#pragma unroll
-            for (int s = 0; s < kSlots; ++s)
-              if (s == slot) stage_c(s);
-            stage_b();
-            stage_a();
-          }
         }
-        if (lane == 0 && hinge) atomicAdd(&p.hinge[t], hinge);
-        if (warp == 0) DSGD_TL(5);
+        if (lane == 0 && hinge) atomicAdd(&sm.hinge_acc, hinge);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[st]);
+        if (warp == 0) DSGD_TL(3);
       }
     } else {
-      // ---- update warps: W_t buffer, zero the buffer g_{t+1} will use, partials of c_t and ||W_t||^2 ----
+      const int uw = warp - kCons;
+      if (uw == 0) DSGD_TL(8);
+      // c_{t-1} = 2*lambda*(W_{t-1} . d): at t == 0 g_{-1} is all zero, so its value is irrelevant
+      double c_prev = 0.0;
+      if (uw == 0) {
+        if (t > 0) {
+          double sd, sn;
+          sum_partials2(part_prev, G, lane, sd, sn);
+          c_prev = p.lambda * 2.0 * sd;
+          // loss of step t-1 = lambda*||W_{t-1}||^2 + hinge_{t-1}/batch  (SparseSVM.scala:20-23)
+          if (p.losses && blockIdx.x == 0 && lane == 0)
+            p.losses[t - 1] = p.lambda * sn + (double)__ldcg(&p.hinge[t - 1]) / (double)B;
+        }
+        if (lane == 0) {
+          sm.c_val[t & 1] = c_prev;
+          mbar_arrive(&sm.c_bar[t & 1]);
+        }
+        DSGD_TL(9);
+      } else {
+        mbar_wait(&sm.c_bar[t & 1], c_par, p.abort_flag, p.timeout_cycles);
+        c_prev = sm.c_val[t & 1];
+      }
+      const bool add_c = (c_prev != 0.0) && (fabs(c_prev) > kEps);
       double pd = 0.0, pn = 0.0;
       for (int j = u0; j < p.dim; j += n_upd) {
         const double wn = apply_update(__ldcg(&Wprev[j]), __ldcg(&Gprev[j]), c_prev, add_c, k_den, lr);
@@ -337,30 +487,34 @@ __global__ void __launch_bounds__((kRowWarps + kUpdWarps) * 32, 1) k_sync_persis
       }
       pd = warp_sum(pd);
       pn = warp_sum(pn);
-      if (warp == kRowWarps) DSGD_TL(9);
-      const int uw = warp - kRowWarps;
       if (lane == 0) { sm.red[uw][0] = pd; sm.red[uw][1] = pn; }
-      asm volatile("bar.sync 1, %0;" ::"r"(kUpdWarps * 32) : "memory");
+      named_bar_sync(1, kUpd * 32);
       if (uw == 0 && lane == 0) {
         double sd = 0.0, sn = 0.0;
 #pragma unroll
-        for (int i = 0; i < kUpdWarps; ++i) { sd += sm.red[i][0]; sn += sm.red[i][1]; }
+        for (int i = 0; i < kUpd; ++i) { sd += sm.red[i][0]; sn += sm.red[i][1]; }
         part_cur[2 * blockIdx.x] = sd;
         part_cur[2 * blockIdx.x + 1] = sn;
       }
-      // loss of step t-1 = lambda*||W_{t-1}||^2 + hinge_{t-1}/batch  (SparseSVM.scala:20-23)
-      if (t > 0 && p.losses && blockIdx.x == 0 && uw == 1) {
-        const double nrm = sum_partials(part_prev + 1, G, lane);
-        if (lane == 0) p.losses[t - 1] = p.lambda * nrm + (double)__ldcg(&p.hinge[t - 1]) / (double)B;
+      if (uw == 0) DSGD_TL(10);
+    }
+    // ---- grid barrier t (the CTA's hinge total rides in front of the arrival) ----
+    named_bar_sync(3, kSyncThreads);
+    if (threadIdx.x == 0) {
+      const unsigned h = sm.hinge_acc;
+      if (h) {
+        atomicAdd(&p.hinge[t < S ? t : 0], h);
+        sm.hinge_acc = 0u;
       }
     }
-    if (warp == kRowWarps) DSGD_TL(10);
     ++phase;
-    if (!grid_barrier(p.bar, phase * (unsigned)G, p.abort_flag, p.timeout_cycles, &sm.ok, (p.tl && blockIdx.x == 0 && t < 256) ? p.tl + t * 16 + 6 : nullptr)) return;
+    if (!grid_barrier(p.bar, phase * (unsigned)G, p.abort_flag, p.timeout_cycles, &sm.ok, kSyncThreads,
+                      (p.tl && blockIdx.x == 0 && t < 256) ? p.tl + t * 16 + 6 : nullptr))
+      return;
   }
 
   // ---- epilogue: W_S is complete in wbuf[S & 1]; publish it as the resident weights, clear g_{S-1} ----------
-  if (!is_row) {
+  if (is_upd) {
     const double *Wfin = p.wbuf[S & 1];
     double *Glast = p.gbuf[(S + 2) % 3];
     for (int j = u0; j < p.dim; j += n_upd) {
@@ -369,10 +523,10 @@ __global__ void __launch_bounds__((kRowWarps + kUpdWarps) * 32, 1) k_sync_persis
       p.w32_out[j] = (float)wv;
       Glast[j] = 0.0;
     }
-    if (blockIdx.x == 0 && warp == kRowWarps) {
+    if (blockIdx.x == 0 && warp == kCons) {
       const double *part = p.partial + (size_t)(S & 1) * G * 2;
-      const double sd = sum_partials(part, G, lane);
-      const double sn = sum_partials(part + 1, G, lane);
+      double sd, sn;
+      sum_partials2(part, G, lane, sd, sn);
       if (lane == 0) {
         p.scal[kScalC] = p.lambda * 2.0 * sd;
         p.scal[kScalNrm2] = sn;

@@ -21,9 +21,9 @@ ctx.synchronize()
 tl = np.zeros((256, 16), dtype=np.int64)
 l = lib(); l.dsgd_debug_timeline.argtypes = [C.c_void_p, C.c_void_p]
 assert l.dsgd_debug_timeline(ctx._h, tl.ctypes.data_as(C.c_void_p)) == 0
-names = {0: "interval start (row warp 0)", 1: "c_prev summed", 2: "row window landed (mbarrier)", 3: "dot reduced",
-         4: "scatter issued", 5: "hinge atomic issued", 6: "CTA synced, arriving at grid barrier", 7: "grid barrier passed",
-         8: "interval start (update warp 0)", 9: "update slice done", 10: "update partials published"}
+names = {0: "interval start (consumer warp 0)", 1: "stage full (TMA landed)", 2: "pass 1 done (partial dots)",
+         3: "pass 2 done (scatter issued)", 6: "CTA synced, arriving at grid barrier", 7: "grid barrier passed",
+         8: "interval start (update warp 0)", 9: "c summed + handed over", 10: "update slice + partials published"}
 t = tl[50:250]
 base = t[:, 0:1]
 print("batch", B, "CTAs", os.environ.get("DSGD_PERSIST_CTAS", "default"))
