@@ -3,7 +3,8 @@
 #include "../../include/dsgd.h"
 
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library itself is bound at run time (see nccl_api)
 
 #include <algorithm>
 #include <cstdarg>
@@ -14,6 +15,8 @@
 
 #include "dsgd_kernels.cuh"
 #include "dsgd_persistent.cuh"
+#include "dsgd_stream.cuh"
+#include "dsgd_async.cuh"
 #include <cstdlib>
 
 using namespace dsgd;
@@ -40,7 +43,9 @@ struct dsgd_ctx {
 
   // state (fp64, L2 resident) -- g has dim + 2 slots (hinge sum and batch size ride in the allreduce)
   double *w = nullptr, *g = nullptr, *d = nullptr, *w_req = nullptr;
-  float *w32 = nullptr;
+  float *w32 = nullptr, *w32_req = nullptr;
+  unsigned long long *n_exact = nullptr;  // rows that took the exact fallback in streaming passes (diagnostic)
+  bool stream_ready = false;
   double *scal = nullptr;
   unsigned long long *cnt = nullptr;
   double *partial = nullptr;  // 2 doubles per k_update block
@@ -70,6 +75,21 @@ struct dsgd_ctx {
   bool p_ready = false;
   long long *p_tl = nullptr;   // debug timeline (DSGD_PERSIST_TIMELINE)
 
+  // async (Hogwild) mode
+  cudaStream_t astream = nullptr;   // the worker loop
+  cudaStream_t stream2 = nullptr;   // service calls that must not queue behind anything
+  double *m_w = nullptr;            // master replica hosted by this ctx (dsgd_async_host_master)
+  double *peer_w[kMaxReplicas] = {};  // [r] = replica of rank r, [world] = master replica; nullptr: not attached
+  bool peer_ipc[kMaxReplicas] = {};
+  int *a_stop = nullptr;
+  unsigned long long *a_cnt = nullptr;   // [0] claimed, [1] done
+  double *a_scratch = nullptr;
+  int64_t a_scratch_lanes = 0;
+  int32_t *a_rows = nullptr, *a_assigned = nullptr, *a_replay = nullptr;
+  int64_t a_rows_cap = 0, a_assigned_cap = 0, a_replay_cap = 0;
+  int32_t *u_idx = nullptr; double *u_val = nullptr; int64_t u_cap = 0;  // update_grad staging
+  bool a_running = false;
+
   // sampled per-launch timing of the gradient kernel
   int32_t prof_every = 0;
   int64_t prof_seen = 0;
@@ -81,6 +101,38 @@ struct dsgd_ctx {
 };
 
 static thread_local std::string g_create_err;
+
+// NCCL is bound lazily with dlopen instead of at link time: a host process may already carry its own libnccl.so.2
+// (PyTorch bundles a newer one than the system's), and two different libraries under one SONAME cannot coexist.
+// Order: a copy already loaded in the process, then $DSGD_NCCL_PATH, then the default search path.
+struct nccl_api {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+  std::string why;
+};
+static nccl_api &nccl() {
+  static nccl_api api = [] {
+    nccl_api a;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h)
+      if (const char *p = getenv("DSGD_NCCL_PATH")) h = dlopen(p, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { a.why = std::string("cannot load libnccl.so.2: ") + dlerror(); return a; }
+    a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
+    a.AllReduce = (decltype(a.AllReduce))dlsym(h, "ncclAllReduce");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
+    a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy && a.GetErrorString;
+    if (!a.ok) a.why = "libnccl.so.2 lacks a required symbol";
+    return a;
+  }();
+  return api;
+}
 
 static int fail(const dsgd_ctx *ctx, int code, const char *fmt, ...) {
   char buf[512];
@@ -103,7 +155,7 @@ static int fail(const dsgd_ctx *ctx, int code, const char *fmt, ...) {
   do {                                                                                                   \
     ncclResult_t r_ = (call);                                                                            \
     if (r_ != ncclSuccess)                                                                               \
-      return fail(ctx, DSGD_ERR_NCCL, "%s failed: %s (%s:%d)", #call, ncclGetErrorString(r_), __FILE__, \
+      return fail(ctx, DSGD_ERR_NCCL, "%s failed: %s (%s:%d)", #call, nccl().GetErrorString(r_), __FILE__, \
                   __LINE__);                                                                             \
   } while (0)
 #define NEED(cond, code, ...) \
@@ -159,16 +211,25 @@ extern "C" int dsgd_create(dsgd_ctx **out, int device, int32_t dim, double lambd
     { int rc = fail(nullptr, DSGD_ERR_CUDA, "dsgd_create: device %d is sm_%d%d; this library is built for sm_100a only",
                     device, prop.major, prop.minor); delete ctx; return rc; }
   if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->astream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if ((e = cudaMalloc(&ctx->a_stop, sizeof(int))) != cudaSuccess) return bail("cudaMalloc a_stop", e);
+  if ((e = cudaMalloc(&ctx->a_cnt, sizeof(unsigned long long) * 2)) != cudaSuccess) return bail("cudaMalloc a_cnt", e);
+  cudaMemsetAsync(ctx->a_stop, 0, sizeof(int), ctx->own_stream);
+  cudaMemsetAsync(ctx->a_cnt, 0, sizeof(unsigned long long) * 2, ctx->own_stream);
   ctx->stream = ctx->own_stream;
   if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("event", e);
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("event", e);
-  const size_t vd = sizeof(double) * (size_t)(dim + 2);
+  const size_t vd = sizeof(double) * (size_t)(dim + kReplicaPad);
   const int upd_blocks = cdiv(dim, 256);
   if ((e = cudaMalloc(&ctx->w, vd)) != cudaSuccess) return bail("cudaMalloc w", e);
   if ((e = cudaMalloc(&ctx->g, vd)) != cudaSuccess) return bail("cudaMalloc g", e);
   if ((e = cudaMalloc(&ctx->d, vd)) != cudaSuccess) return bail("cudaMalloc d", e);
   if ((e = cudaMalloc(&ctx->w_req, vd)) != cudaSuccess) return bail("cudaMalloc w_req", e);
-  if ((e = cudaMalloc(&ctx->w32, sizeof(float) * (size_t)(dim + 2))) != cudaSuccess) return bail("cudaMalloc w32", e);
+  if ((e = cudaMalloc(&ctx->w32, sizeof(float) * (size_t)(dim + 4))) != cudaSuccess) return bail("cudaMalloc w32", e);
+  if ((e = cudaMalloc(&ctx->w32_req, sizeof(float) * (size_t)(dim + 4))) != cudaSuccess) return bail("cudaMalloc w32_req", e);
+  if ((e = cudaMalloc(&ctx->n_exact, sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc n_exact", e);
+  cudaMemsetAsync(ctx->n_exact, 0, sizeof(unsigned long long), ctx->stream);
   if ((e = cudaMalloc(&ctx->scal, sizeof(double) * kNumScal)) != cudaSuccess) return bail("cudaMalloc scal", e);
   if ((e = cudaMalloc(&ctx->cnt, sizeof(unsigned long long) * kNumCnt)) != cudaSuccess) return bail("cudaMalloc cnt", e);
   if ((e = cudaMalloc(&ctx->partial, sizeof(double) * 2 * (size_t)upd_blocks)) != cudaSuccess) return bail("cudaMalloc partial", e);
@@ -191,8 +252,14 @@ extern "C" int dsgd_destroy(dsgd_ctx *ctx) {
   if (!ctx) return DSGD_OK;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  if (ctx->comm) ncclCommDestroy(ctx->comm);
-  void *ptrs[] = {ctx->rp16, ctx->pairs, ctx->label, ctx->w, ctx->g, ctx->d, ctx->w_req, ctx->w32, ctx->scal,
+  if (ctx->comm) nccl().CommDestroy(ctx->comm);
+  for (int r = 0; r < kMaxReplicas; ++r)
+    if (ctx->peer_w[r] && ctx->peer_ipc[r]) cudaIpcCloseMemHandle(ctx->peer_w[r]);
+  void *aptrs[] = {ctx->m_w, ctx->a_stop, ctx->a_cnt, ctx->a_scratch, ctx->a_rows, ctx->a_assigned, ctx->a_replay, ctx->u_idx, ctx->u_val};
+  for (void *q : aptrs) if (q) cudaFree(q);
+  if (ctx->astream) cudaStreamDestroy(ctx->astream);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  void *ptrs[] = {ctx->rp16, ctx->pairs, ctx->label, ctx->w, ctx->g, ctx->d, ctx->w_req, ctx->w32, ctx->w32_req, ctx->n_exact, ctx->scal,
                   ctx->cnt, ctx->partial, ctx->out2, ctx->gsum, ctx->p_wbuf[0], ctx->p_wbuf[1], ctx->p_gbuf[0],
                   ctx->p_gbuf[1], ctx->p_gbuf[2], ctx->p_partial, ctx->p_hinge, ctx->p_bar, ctx->samples, ctx->losses, ctx->preds};
   for (void *p : ptrs) if (p) cudaFree(p);
@@ -341,6 +408,10 @@ static int refresh_resident(dsgd_ctx *ctx) {
   LAUNCHED();
   k_to_f32<<<cdiv(ctx->dim, 256), 256, 0, ctx->stream>>>(ctx->w, ctx->w32, ctx->dim);
   LAUNCHED();
+  if (ctx->flags & DSGD_FLAG_ASYNC) {
+    k_async_init_ctl<1024><<<1, 1024, 0, ctx->stream>>>(ctx->w, ctx->d, ctx->dim);
+    LAUNCHED();
+  }
   CU(cudaGetLastError());
   return DSGD_OK;
 }
@@ -445,14 +516,18 @@ extern "C" int dsgd_stage_samples(dsgd_ctx *ctx, const int32_t *samples, int64_t
 
 // weights to use for a request: NULL -> resident; else copy into w_req and compute its scalars
 static int request_weights(dsgd_ctx *ctx, const double *w, const double **w_dev, const double **c_dev,
-                           const double **nrm_dev) {
+                           const double **nrm_dev, const float **w32_dev = nullptr) {
   if (!w) {
     *w_dev = ctx->w; *c_dev = ctx->scal + kScalC; *nrm_dev = ctx->scal + kScalNrm2;
+    if (w32_dev) *w32_dev = ctx->w32;
     return DSGD_OK;
   }
+  if (w32_dev) *w32_dev = ctx->w32_req;
   CU(cudaMemcpyAsync(ctx->w_req, w, sizeof(double) * (size_t)ctx->dim, cudaMemcpyHostToDevice, ctx->stream));
   k_prepare<1024><<<1, 1024, 0, ctx->stream>>>(ctx->w_req, ctx->d, ctx->dim, ctx->lambda, ctx->scal + kScalReqC,
                                                 ctx->scal + kScalReqNrm2);
+  LAUNCHED();
+  k_to_f32<<<cdiv(ctx->dim, 256), 256, 0, ctx->stream>>>(ctx->w_req, ctx->w32_req, ctx->dim);
   LAUNCHED();
   CU(cudaGetLastError());
   *w_dev = ctx->w_req; *c_dev = ctx->scal + kScalReqC; *nrm_dev = ctx->scal + kScalReqNrm2;
@@ -461,6 +536,39 @@ static int request_weights(dsgd_ctx *ctx, const double *w, const double **w_dev,
 
 static inline int rows_grid(const dsgd_ctx *ctx, int64_t n) {
   return (int)std::min<int64_t>(std::max<int64_t>(cdiv(n, 8), 1), (int64_t)ctx->sm_count * 8);
+}
+
+// ---- streaming pass (large n): fp32 weights staged in shared memory, one persistent CTA per SM -----------------
+constexpr int64_t kStreamMinRows = 2048;
+
+static bool stream_eligible(const dsgd_ctx *ctx, int64_t n) {
+  static const bool off = getenv("DSGD_NO_STREAM") != nullptr;
+  return !off && n >= kStreamMinRows && (size_t)ctx->dim * sizeof(float) + 1024 <= 227u * 1024u;
+}
+
+template <bool kScatter, bool kPreds>
+static int stream_launch(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t row_begin, int64_t n, const double *w_dev,
+                         const float *w32_dev, double *g, double *preds) {
+  const size_t smem = (size_t)ctx->dim * sizeof(float);
+  if (!ctx->stream_ready) {
+    CU(cudaFuncSetAttribute(k_stream_rows<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k_stream_rows<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k_stream_rows<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctx->stream_ready = true;
+  }
+  StreamParams sp;
+  sp.rp16 = ctx->rp16; sp.units = reinterpret_cast<const uint4 *>(ctx->pairs); sp.label = ctx->label;
+  sp.samples = samples_dev; sp.row_begin = row_begin; sp.n = n; sp.w = w_dev; sp.w32 = w32_dev; sp.dim = ctx->dim;
+  sp.g = g; sp.preds = preds; sp.cnt = ctx->cnt; sp.n_exact = ctx->n_exact;
+  const int64_t blocks32 = (n + 31) / 32;
+  const int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, cdiv(blocks32, kStreamThreads / 32)));
+  auto *pe = prof_slot(ctx);
+  if (pe) cudaEventRecord(pe->first, ctx->stream);
+  k_stream_rows<kScatter, kPreds><<<grid, kStreamThreads, smem, ctx->stream>>>(sp);
+  if (pe) cudaEventRecord(pe->second, ctx->stream);
+  LAUNCHED();
+  CU(cudaGetLastError());
+  return DSGD_OK;
 }
 
 // ---- forward / gradient / eval -------------------------------------------------------------------------
@@ -474,10 +582,15 @@ extern "C" int dsgd_forward(dsgd_ctx *ctx, const double *w, const int32_t *sampl
   rc = ensure_f64(ctx, &ctx->preds, &ctx->preds_cap, n);
   if (rc) return rc;
   const double *wd, *cd, *nd;
-  if ((rc = request_weights(ctx, w, &wd, &cd, &nd))) return rc;
-  k_rows<false, true><<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(ctx->rp16, ctx->pairs, ctx->label, ctx->samples, 0, n,
-                                                                  wd, nullptr, ctx->preds, ctx->cnt);
-  LAUNCHED();
+  const float *w32d;
+  if ((rc = request_weights(ctx, w, &wd, &cd, &nd, &w32d))) return rc;
+  if (stream_eligible(ctx, n)) {
+    if ((rc = stream_launch<false, true>(ctx, ctx->samples, 0, n, wd, w32d, nullptr, ctx->preds))) return rc;
+  } else {
+    k_rows<false, true><<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(ctx->rp16, ctx->pairs, ctx->label, ctx->samples, 0, n,
+                                                                    wd, nullptr, ctx->preds, ctx->cnt);
+    LAUNCHED();
+  }
   CU(cudaGetLastError());
   CU(cudaMemsetAsync(ctx->cnt, 0, sizeof(unsigned long long) * 2, ctx->stream));
   CU(cudaMemcpyAsync(preds_out, ctx->preds, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -495,10 +608,15 @@ extern "C" int dsgd_gradient(dsgd_ctx *ctx, const double *w, const int32_t *samp
   int rc = dsgd_stage_samples(ctx, samples, n);
   if (rc) return rc;
   const double *wd, *cd, *nd;
-  if ((rc = request_weights(ctx, w, &wd, &cd, &nd))) return rc;
-  k_rows<true, false><<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(ctx->rp16, ctx->pairs, ctx->label, ctx->samples, 0, n,
-                                                                  wd, ctx->g, nullptr, ctx->cnt);
-  LAUNCHED();
+  const float *w32d;
+  if ((rc = request_weights(ctx, w, &wd, &cd, &nd, &w32d))) return rc;
+  if (stream_eligible(ctx, n)) {
+    if ((rc = stream_launch<true, false>(ctx, ctx->samples, 0, n, wd, w32d, ctx->g, nullptr))) return rc;
+  } else {
+    k_rows<true, false><<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(ctx->rp16, ctx->pairs, ctx->label, ctx->samples, 0, n,
+                                                                    wd, ctx->g, nullptr, ctx->cnt);
+    LAUNCHED();
+  }
   k_finish<<<cdiv(ctx->dim + 1, 256), 256, 0, ctx->stream>>>(ctx->g, ctx->dim, cd, ctx->cnt, (double)n);
   LAUNCHED();
   k_loss_scalar<<<1, 1, 0, ctx->stream>>>(nd, ctx->cnt, ctx->lambda, (double)n, ctx->out2);
@@ -521,11 +639,16 @@ static int eval_impl(dsgd_ctx *ctx, const double *w, int64_t row_begin, int64_t 
   CU(cudaSetDevice(ctx->device));
   const int64_t n = row_end - row_begin;
   const double *wd, *cd, *nd;
+  const float *w32d;
   int rc;
-  if ((rc = request_weights(ctx, w, &wd, &cd, &nd))) return rc;
-  k_rows<false, false><<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(ctx->rp16, ctx->pairs, ctx->label, nullptr, row_begin, n,
-                                                                   wd, nullptr, nullptr, ctx->cnt);
-  LAUNCHED();
+  if ((rc = request_weights(ctx, w, &wd, &cd, &nd, &w32d))) return rc;
+  if (stream_eligible(ctx, n)) {
+    if ((rc = stream_launch<false, false>(ctx, nullptr, row_begin, n, wd, w32d, nullptr, nullptr))) return rc;
+  } else {
+    k_rows<false, false><<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(ctx->rp16, ctx->pairs, ctx->label, nullptr, row_begin, n,
+                                                                     wd, nullptr, nullptr, ctx->cnt);
+    LAUNCHED();
+  }
   k_loss_scalar<<<1, 1, 0, ctx->stream>>>(nd, ctx->cnt, ctx->lambda, (double)n, ctx->out2);
   LAUNCHED();
   CU(cudaGetLastError());
@@ -562,9 +685,10 @@ extern "C" int dsgd_eval_counts(dsgd_ctx *ctx, const double *w, int64_t row_begi
 extern "C" int dsgd_comm_unique_id(uint8_t id[DSGD_UNIQUE_ID_BYTES]) {
   static_assert(sizeof(ncclUniqueId) == DSGD_UNIQUE_ID_BYTES, "ncclUniqueId size");
   if (!id) return DSGD_ERR_INVALID;
+  if (!nccl().ok) return fail(nullptr, DSGD_ERR_NCCL, "%s", nccl().why.c_str());
   ncclUniqueId u;
-  ncclResult_t r = ncclGetUniqueId(&u);
-  if (r != ncclSuccess) return fail(nullptr, DSGD_ERR_NCCL, "ncclGetUniqueId: %s", ncclGetErrorString(r));
+  ncclResult_t r = nccl().GetUniqueId(&u);
+  if (r != ncclSuccess) return fail(nullptr, DSGD_ERR_NCCL, "ncclGetUniqueId: %s", nccl().GetErrorString(r));
   memcpy(id, &u, sizeof u);
   return DSGD_OK;
 }
@@ -576,7 +700,8 @@ extern "C" int dsgd_comm_init(dsgd_ctx *ctx, const uint8_t id[DSGD_UNIQUE_ID_BYT
   CU(cudaSetDevice(ctx->device));
   ncclUniqueId u;
   memcpy(&u, id, sizeof u);
-  NC(ncclCommInitRank(&ctx->comm, ctx->world, u, ctx->rank));
+  NEED(nccl().ok, DSGD_ERR_NCCL, "%s", nccl().why.c_str());
+  NC(nccl().CommInitRank(&ctx->comm, ctx->world, u, ctx->rank));
   return DSGD_OK;
 }
 
@@ -640,8 +765,8 @@ static int persist_run(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t n_per_
   pp.lambda = ctx->lambda; pp.lr = lr; pp.k_den = 1.0;
   pp.tl = nullptr;
   if (getenv("DSGD_PERSIST_TIMELINE")) {
-    if (!ctx->p_tl) CU(cudaMalloc(&ctx->p_tl, sizeof(long long) * 256 * 16));
-    CU(cudaMemsetAsync(ctx->p_tl, 0, sizeof(long long) * 256 * 16, ctx->stream));
+    if (!ctx->p_tl) CU(cudaMalloc(&ctx->p_tl, sizeof(long long) * (256 * 16 + 4 * 160 * 2)));
+    CU(cudaMemsetAsync(ctx->p_tl, 0, sizeof(long long) * (256 * 16 + 4 * 160 * 2), ctx->stream));
     pp.tl = ctx->p_tl;
   }
   pp.timeout_cycles = 4000000000ll;  // ~2 s at 1.9 GHz: a healthy barrier takes well under a microsecond
@@ -668,7 +793,7 @@ extern "C" int dsgd_debug_timeline(dsgd_ctx *ctx, long long *out) {
   if (!ctx || !out) return DSGD_ERR_INVALID;
   NEED(ctx->p_tl, DSGD_ERR_STATE, "no timeline recorded (set DSGD_PERSIST_TIMELINE=1)");
   CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaMemcpy(out, ctx->p_tl, sizeof(long long) * 256 * 16, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(out, ctx->p_tl, sizeof(long long) * (256 * 16 + 4 * 160 * 2), cudaMemcpyDeviceToHost));
   return DSGD_OK;
 }
 
@@ -754,7 +879,7 @@ extern "C" int dsgd_sync_steps_staged(dsgd_ctx *ctx, int64_t first, int64_t n_pe
     }
     if (ctx->n_local == 0) CU(cudaMemsetAsync(ctx->gsum, 0, sizeof(double) * (size_t)(ctx->dim + 2), ctx->stream));
     if (ctx->world > 1)
-      NC(ncclAllReduce(ctx->gsum, ctx->gsum, (size_t)ctx->dim + 2, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+      NC(nccl().AllReduce(ctx->gsum, ctx->gsum, (size_t)ctx->dim + 2, ncclDouble, ncclSum, ctx->comm, ctx->stream));
     k_update<false><<<upd_blocks, 256, 0, ctx->stream>>>(ctx->w, ctx->w32, ctx->gsum, ctx->d, ctx->dim, ctx->lambda, lr,
                                                          (double)k_total, ctx->scal, ctx->cnt, ctx->partial, 0.0, loss_dev);
     LAUNCHED();
@@ -791,47 +916,248 @@ extern "C" int dsgd_sync_step(dsgd_ctx *ctx, const int32_t *samples, int64_t n, 
   return dsgd_sync_steps(ctx, samples, n, 1, lr, loss_out);
 }
 
-// ---- async mode (filled in by dsgd_async.cuh in a later milestone) -----------------------------------------
+// ---- async (Hogwild) mode -------------------------------------------------------------------------------------
 
-extern "C" int dsgd_ipc_export(dsgd_ctx *ctx, uint8_t handle[DSGD_IPC_HANDLE_BYTES]) {
+static int ensure_dev(dsgd_ctx *ctx, void **buf, int64_t *cap, int64_t n, size_t elt) {
+  if (*cap >= n) return DSGD_OK;
+  if (*buf) CU(cudaFree(*buf));
+  *buf = nullptr; *cap = 0;
+  const int64_t want = std::max<int64_t>(n, 1024);
+  CU(cudaMalloc(buf, elt * (size_t)want));
+  *cap = want;
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_async_host_master(dsgd_ctx *ctx, const double *w0) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(ctx->flags & DSGD_FLAG_ASYNC, DSGD_ERR_STATE, "Cannot host the async master replica: ctx is in synchronous mode.");
+  NEED(w0, DSGD_ERR_INVALID, "dsgd_async_host_master: w0 is NULL");
+  NEED(ctx->have_d, DSGD_ERR_STATE, "dsgd_async_host_master: dimSparsity not set");
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->m_w) CU(cudaMalloc(&ctx->m_w, sizeof(double) * (size_t)(ctx->dim + kReplicaPad)));
+  CU(cudaMemsetAsync(ctx->m_w, 0, sizeof(double) * (size_t)(ctx->dim + kReplicaPad), ctx->stream));
+  CU(cudaMemcpyAsync(ctx->m_w, w0, sizeof(double) * (size_t)ctx->dim, cudaMemcpyHostToDevice, ctx->stream));
+  k_async_init_ctl<1024><<<1, 1024, 0, ctx->stream>>>(ctx->m_w, ctx->d, ctx->dim);
+  LAUNCHED();
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_ipc_export(dsgd_ctx *ctx, int which, uint8_t handle[DSGD_IPC_HANDLE_BYTES]) {
   if (!ctx || !handle) return DSGD_ERR_INVALID;
   static_assert(sizeof(cudaIpcMemHandle_t) == DSGD_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+  NEED(which == DSGD_REPLICA_SELF || which == DSGD_REPLICA_MASTER, DSGD_ERR_INVALID, "dsgd_ipc_export: bad `which`");
+  NEED(which == DSGD_REPLICA_SELF || ctx->m_w, DSGD_ERR_STATE, "dsgd_ipc_export: this ctx does not host the master replica");
   CU(cudaSetDevice(ctx->device));
   cudaIpcMemHandle_t h;
-  CU(cudaIpcGetMemHandle(&h, ctx->w));
+  CU(cudaIpcGetMemHandle(&h, which == DSGD_REPLICA_SELF ? ctx->w : ctx->m_w));
   memcpy(handle, &h, sizeof h);
   return DSGD_OK;
 }
 
 extern "C" int dsgd_ipc_import(dsgd_ctx *ctx, int peer_rank, const uint8_t handle[DSGD_IPC_HANDLE_BYTES]) {
   if (!ctx || !handle) return DSGD_ERR_INVALID;
-  (void)peer_rank;
-  return fail(ctx, DSGD_ERR_STATE, "dsgd_ipc_import: async mode is not built yet");
+  NEED(peer_rank >= 0 && peer_rank <= ctx->world && peer_rank < kMaxReplicas, DSGD_ERR_INVALID,
+       "dsgd_ipc_import: peer_rank %d outside [0,%d]", peer_rank, ctx->world);
+  NEED(peer_rank != ctx->rank, DSGD_ERR_INVALID, "dsgd_ipc_import: a worker does not import its own replica");
+  NEED(!ctx->a_running, DSGD_ERR_STATE, "dsgd_ipc_import: async computation is running");
+  CU(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  void *ptr = nullptr;
+  CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  if (ctx->peer_w[peer_rank] && ctx->peer_ipc[peer_rank]) cudaIpcCloseMemHandle(ctx->peer_w[peer_rank]);
+  ctx->peer_w[peer_rank] = static_cast<double *>(ptr);
+  ctx->peer_ipc[peer_rank] = true;
+  return DSGD_OK;
 }
 
-extern "C" int dsgd_start_async(dsgd_ctx *ctx, const double *, const int32_t *, int64_t, int32_t, double, int32_t, int64_t,
-                                uint64_t) {
+extern "C" int dsgd_peer_attach(dsgd_ctx *ctx, int peer_rank, dsgd_ctx *peer, int which) {
+  if (!ctx || !peer) return DSGD_ERR_INVALID;
+  NEED(peer_rank >= 0 && peer_rank <= ctx->world && peer_rank < kMaxReplicas, DSGD_ERR_INVALID,
+       "dsgd_peer_attach: peer_rank %d outside [0,%d]", peer_rank, ctx->world);
+  NEED(which == DSGD_REPLICA_SELF || peer->m_w, DSGD_ERR_STATE, "dsgd_peer_attach: peer does not host the master replica");
+  NEED(peer->dim == ctx->dim, DSGD_ERR_INVALID, "dsgd_peer_attach: dimension mismatch");
+  CU(cudaSetDevice(ctx->device));
+  if (peer->device != ctx->device) {
+    int can = 0;
+    CU(cudaDeviceCanAccessPeer(&can, ctx->device, peer->device));
+    NEED(can, DSGD_ERR_CUDA, "dsgd_peer_attach: device %d cannot access device %d", ctx->device, peer->device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+    (void)cudaGetLastError();
+  }
+  ctx->peer_w[peer_rank] = which == DSGD_REPLICA_SELF ? peer->w : peer->m_w;
+  ctx->peer_ipc[peer_rank] = false;
+  return DSGD_OK;
+}
+
+static int async_launch(dsgd_ctx *ctx, const double *w0, const int32_t *assigned, int64_t n_assigned, const int32_t *replay,
+                        int32_t batch, double lr, int32_t lanes, int64_t max_updates, uint64_t seed, cudaStream_t st) {
+  NEED(ctx->flags & DSGD_FLAG_ASYNC, DSGD_ERR_STATE, "Cannot initialize async computation: slave is in synchronous mode.");
+  NEED(!ctx->a_running, DSGD_ERR_STATE,
+       "Async computation already running, can't be initialized unless stopped first");
+  NEED(ctx->pairs && ctx->have_d, DSGD_ERR_STATE, "dsgd_start_async: rows or dimSparsity missing");
+  NEED(w0 && batch >= 1 && lanes >= 1 && lanes <= 4096, DSGD_ERR_INVALID, "dsgd_start_async: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  // weights() = request.weights
+  CU(cudaMemcpyAsync(ctx->w, w0, sizeof(double) * (size_t)ctx->dim, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = refresh_resident(ctx);  // also S = w . d and the control slots of the replica
+  if (rc) return rc;
+  if (ctx->a_scratch_lanes < lanes) {
+    if (ctx->a_scratch) CU(cudaFree(ctx->a_scratch));
+    ctx->a_scratch = nullptr; ctx->a_scratch_lanes = 0;
+    CU(cudaMalloc(&ctx->a_scratch, sizeof(double) * (size_t)lanes * (size_t)ctx->dim));
+    CU(cudaMemsetAsync(ctx->a_scratch, 0, sizeof(double) * (size_t)lanes * (size_t)ctx->dim, ctx->stream));
+    ctx->a_scratch_lanes = lanes;
+  }
+  if ((rc = ensure_dev(ctx, (void **)&ctx->a_rows, &ctx->a_rows_cap, (int64_t)lanes * batch, sizeof(int32_t)))) return rc;
+  CU(cudaMemsetAsync(ctx->a_stop, 0, sizeof(int), ctx->stream));
+  CU(cudaMemsetAsync(ctx->a_cnt, 0, sizeof(unsigned long long) * 2, ctx->stream));
+  AsyncParams ap;
+  ap.rp16 = ctx->rp16; ap.pairs = ctx->pairs; ap.label = ctx->label; ap.d = ctx->d; ap.dim = ctx->dim;
+  ap.assigned = assigned; ap.n_assigned = n_assigned; ap.replay = replay; ap.batch = batch; ap.lr = lr; ap.lambda = ctx->lambda;
+  int nr = 0;
+  ap.replica[nr++] = ctx->w;
+  for (int r = 0; r < ctx->world && r < kMaxReplicas - 1; ++r)
+    if (r != ctx->rank && ctx->peer_w[r]) ap.replica[nr++] = ctx->peer_w[r];
+  ap.master_slot = -1;
+  double *master = ctx->m_w ? ctx->m_w : (ctx->world < kMaxReplicas ? ctx->peer_w[ctx->world] : nullptr);
+  if (master) { ap.master_slot = nr; ap.replica[nr++] = master; }
+  for (int q = nr; q < kMaxReplicas; ++q) ap.replica[q] = nullptr;
+  ap.n_replicas = nr;
+  ap.scratch = ctx->a_scratch; ap.batch_rows = ctx->a_rows; ap.n_lanes = lanes; ap.max_updates = max_updates; ap.seed = seed;
+  ap.stop = ctx->a_stop; ap.claimed = ctx->a_cnt; ap.done = ctx->a_cnt + 1;
+  CU(cudaStreamSynchronize(ctx->stream));  // inputs in place before the loop's own stream starts
+  k_async_worker<<<cdiv(lanes, 4), 128, 0, st>>>(ap);
+  LAUNCHED();
+  CU(cudaGetLastError());
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_start_async(dsgd_ctx *ctx, const double *w0, const int32_t *assigned, int64_t n_assigned, int32_t batch,
+                                double lr, int32_t concurrency, int64_t max_updates, uint64_t seed) {
   if (!ctx) return DSGD_ERR_INVALID;
-  NEED(ctx->flags & DSGD_FLAG_ASYNC, DSGD_ERR_STATE,
-       "Cannot initialize async computation: slave is in synchronous mode.");
-  return fail(ctx, DSGD_ERR_STATE, "dsgd_start_async: async mode is not built yet");
+  NEED(ctx->flags & DSGD_FLAG_ASYNC, DSGD_ERR_STATE, "Cannot initialize async computation: slave is in synchronous mode.");
+  NEED(assigned && n_assigned >= 1, DSGD_ERR_EMPTY, "dsgd_start_async: no samples assigned (Random.nextInt(0) throws)");
+  NEED(n_assigned <= ctx->n_rows, DSGD_ERR_RANGE, "dsgd_start_async: more assigned samples than rows");
+  for (int64_t i = 0; i < n_assigned; ++i)
+    NEED(assigned[i] >= 0 && assigned[i] < ctx->n_rows, DSGD_ERR_RANGE, "assigned sample %d at position %lld outside [0,%lld)",
+         assigned[i], (long long)i, (long long)ctx->n_rows);
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_dev(ctx, (void **)&ctx->a_assigned, &ctx->a_assigned_cap, n_assigned, sizeof(int32_t));
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->a_assigned, assigned, sizeof(int32_t) * (size_t)n_assigned, cudaMemcpyHostToDevice, ctx->stream));
+  if (batch > n_assigned) batch = (int32_t)n_assigned;  // `take batchSize` of a shorter shuffle
+  rc = async_launch(ctx, w0, ctx->a_assigned, n_assigned, nullptr, batch, lr, concurrency, max_updates, seed, ctx->astream);
+  if (rc) return rc;
+  ctx->a_running = true;
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_async_replay(dsgd_ctx *ctx, const double *w0, const int32_t *samples, int32_t batch, int64_t n_updates,
+                                 double lr) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(ctx->flags & DSGD_FLAG_ASYNC, DSGD_ERR_STATE, "Cannot initialize async computation: slave is in synchronous mode.");
+  NEED(samples && batch >= 1 && n_updates >= 1, DSGD_ERR_EMPTY, "dsgd_async_replay: empty sequence");
+  const int64_t n = (int64_t)batch * n_updates;
+  for (int64_t i = 0; i < n; ++i)
+    NEED(samples[i] >= 0 && samples[i] < ctx->n_rows, DSGD_ERR_RANGE, "sample index %d at position %lld outside [0,%lld)",
+         samples[i], (long long)i, (long long)ctx->n_rows);
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_dev(ctx, (void **)&ctx->a_replay, &ctx->a_replay_cap, n, sizeof(int32_t));
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->a_replay, samples, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  rc = async_launch(ctx, w0, nullptr, 1, ctx->a_replay, batch, lr, 1, n_updates, 0, ctx->stream);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  rc = refresh_resident(ctx);
+  // refresh_resident re-derives S from the weights; the loop's running S is what the NEXT replay would start from anyway
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_async_running(dsgd_ctx *ctx, int *running) {
+  if (!ctx || !running) return DSGD_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  *running = 0;
+  if (ctx->a_running) {
+    cudaError_t e = cudaStreamQuery(ctx->astream);
+    if (e == cudaErrorNotReady) *running = 1;
+    else if (e != cudaSuccess) CU(e);
+  }
+  return DSGD_OK;
 }
 
 extern "C" int dsgd_stop_async(dsgd_ctx *ctx) {
   if (!ctx) return DSGD_ERR_INVALID;
   NEED(ctx->flags & DSGD_FLAG_ASYNC, DSGD_ERR_STATE, "Cannot stop async computation: slave is in synchronous mode.");
-  return fail(ctx, DSGD_ERR_STATE, "dsgd_stop_async: async mode is not built yet");
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->a_running) return DSGD_OK;  // runningAsync() = false on an idle slave is a no-op in the reference too
+  static const int one = 1;
+  CU(cudaMemcpyAsync(ctx->a_stop, &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream2));
+  CU(cudaStreamSynchronize(ctx->stream2));
+  CU(cudaStreamSynchronize(ctx->astream));
+  ctx->a_running = false;
+  k_prepare<1024><<<1, 1024, 0, ctx->stream>>>(ctx->w, ctx->d, ctx->dim, ctx->lambda, ctx->scal + kScalC, ctx->scal + kScalNrm2);
+  LAUNCHED();
+  k_to_f32<<<cdiv(ctx->dim, 256), 256, 0, ctx->stream>>>(ctx->w, ctx->w32, ctx->dim);
+  LAUNCHED();
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));
+  return DSGD_OK;
 }
 
 extern "C" int dsgd_update_grad(dsgd_ctx *ctx, const int32_t *idx, const double *val, int64_t nnz) {
   if (!ctx) return DSGD_ERR_INVALID;
   NEED(ctx->flags & DSGD_FLAG_ASYNC, DSGD_ERR_STATE, "Cannot update gradient: slave is in synchronous mode.");
   NEED(nnz >= 0 && (nnz == 0 || (idx && val)), DSGD_ERR_INVALID, "dsgd_update_grad: bad arguments");
-  return fail(ctx, DSGD_ERR_STATE, "dsgd_update_grad: async mode is not built yet");
+  for (int64_t k = 0; k < nnz; ++k)
+    NEED(idx[k] >= 0 && idx[k] < ctx->dim, DSGD_ERR_RANGE, "dsgd_update_grad: key %d outside [0,%d)", idx[k], ctx->dim);
+  if (nnz == 0) return DSGD_OK;
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->u_cap < nnz) {
+    if (ctx->u_idx) CU(cudaFree(ctx->u_idx));
+    if (ctx->u_val) CU(cudaFree(ctx->u_val));
+    ctx->u_idx = nullptr; ctx->u_val = nullptr; ctx->u_cap = 0;
+    const int64_t want = std::max<int64_t>(nnz, 4096);
+    CU(cudaMalloc(&ctx->u_idx, sizeof(int32_t) * (size_t)want));
+    CU(cudaMalloc(&ctx->u_val, sizeof(double) * (size_t)want));
+    ctx->u_cap = want;
+  }
+  CU(cudaMemcpyAsync(ctx->u_idx, idx, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream2));
+  CU(cudaMemcpyAsync(ctx->u_val, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream2));
+  k_async_apply_delta<<<std::min(cdiv(nnz, 256), 64), 256, 0, ctx->stream2>>>(ctx->w, ctx->dim, ctx->d, ctx->u_idx, ctx->u_val, nnz, 0);
+  LAUNCHED();
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream2));
+  return DSGD_OK;
+}
+
+static double *master_replica(dsgd_ctx *ctx) {
+  return ctx->m_w ? ctx->m_w : (ctx->world < kMaxReplicas ? ctx->peer_w[ctx->world] : nullptr);
 }
 
 extern "C" int dsgd_async_updates(dsgd_ctx *ctx, int64_t *count) {
   if (!ctx || !count) return DSGD_ERR_INVALID;
-  *count = 0;
+  CU(cudaSetDevice(ctx->device));
+  unsigned long long v = 0;
+  double *m = master_replica(ctx);
+  const void *src = m ? (const void *)(reinterpret_cast<unsigned long long *>(m) + ctx->dim + kCtlUpdates) : (const void *)(ctx->a_cnt + 1);
+  CU(cudaMemcpyAsync(&v, src, sizeof v, cudaMemcpyDeviceToHost, ctx->stream2));
+  CU(cudaStreamSynchronize(ctx->stream2));
+  *count = (int64_t)v;
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_async_master_weights(dsgd_ctx *ctx, double *w_out) {
+  if (!ctx || !w_out) return DSGD_ERR_INVALID;
+  double *m = master_replica(ctx);
+  NEED(m, DSGD_ERR_STATE, "dsgd_async_master_weights: no master replica hosted or imported");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(w_out, m, sizeof(double) * (size_t)ctx->dim, cudaMemcpyDeviceToHost, ctx->stream2));
+  CU(cudaStreamSynchronize(ctx->stream2));
   return DSGD_OK;
 }

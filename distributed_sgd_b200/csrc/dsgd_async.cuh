@@ -1,0 +1,199 @@
+// dsgd_async.cuh -- asynchronous (Hogwild) worker loop as a persistent kernel with lock-free peer writes.
+//
+// Reference: Slave.asyncTask (core/Slave.scala:79-111) + SlaveImpl.updateGrad (177-185) +
+// AsyncMasterGrpcImpl.updateGrad (core/MasterAsync.scala:164-177).  Per iteration the reference worker
+//   samples a batch, snapshots its weights, computes  delta = lr * regularize(mean_i backward(w, x_i, y_i), w),
+//   applies  w_self -= delta, and sends the SAME sparse delta to every peer slave and to the master, which each
+//   apply  w -= delta  (the master also counts updates).
+// Here every replica (peers' and the master's) is mapped into this GPU's address space over NVLink and the
+// "send" is a system-scope fp64 reduction (red.add of -delta_j) straight into peer memory: no message, no
+// lock, uniform cost to every peer through the NVSwitch.
+//
+// One Hogwild LANE is one warp running the loop body; `concurrency` lanes share this GPU's replica (1 lane ==
+// the reference's strictly sequential loop).  c = 2*lambda*(w . d) needs the whole weight vector every iteration
+// in the reference; each replica instead carries S = w . d in a control slot, and whoever applies a delta to a
+// replica also applies  S -= sum_j delta_j d_j  to it -- O(nnz) instead of O(dim), same value up to fp64 rounding.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dsgd_kernels.cuh"
+
+namespace dsgd {
+
+constexpr int kMaxReplicas = 17;  // 16 workers + the master replica
+// control slots that follow the dim weights (and two spare doubles) of every replica block
+constexpr int kCtlS = 2;        // double: S = w . d of this replica
+constexpr int kCtlUpdates = 3;  // unsigned long long: updates applied to this replica's owner (the master's counter)
+constexpr int kReplicaPad = 8;  // doubles after the weights
+
+struct AsyncParams {
+  const uint32_t *rp16;
+  const uint2 *pairs;
+  const int8_t *label;
+  const double *d;
+  int dim;
+  const int32_t *assigned;  // row ids this worker may sample (StartAsyncRequest.samples)
+  int64_t n_assigned;
+  const int32_t *replay;    // explicit sequence of max_updates * batch row ids, or nullptr (sample on the device)
+  int batch;
+  double lr, lambda;
+  double *replica[kMaxReplicas];  // [0] = own replica; then peers; the master last if present
+  int n_replicas;
+  int master_slot;          // index into replica[] of the master replica, or -1
+  double *scratch;          // [n_lanes][dim] zero on entry and exit: per-lane batch accumulator
+  int32_t *batch_rows;      // [n_lanes][batch]
+  int n_lanes;
+  long long max_updates;    // total over lanes; <= 0: until stopped
+  unsigned long long seed;
+  volatile int *stop;       // raised by dsgd_stop_async
+  unsigned long long *claimed;  // next iteration number to claim (lanes race for iterations)
+  unsigned long long *done;     // iterations finished by this worker
+};
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long &s) {
+  unsigned long long z = (s += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(128) k_async_worker(const AsyncParams p) {
+  const int lane = threadIdx.x & 31;
+  const int lane_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // Hogwild lane
+  if (lane_id >= p.n_lanes) return;
+  double *w = p.replica[0];
+  double *scratch = p.scratch + (size_t)lane_id * p.dim;
+  int32_t *rows = p.batch_rows + (size_t)lane_id * p.batch;
+  const int B = p.batch;
+  unsigned long long rng = p.seed * 0xD1342543DE82EF95ull + 0x632BE59BD9B4E019ull * (unsigned long long)(lane_id + 1);
+
+  for (;;) {
+    if (*p.stop) break;
+    // claim the next iteration (keeps the total bounded and, with a replay sequence, deals the recorded batches)
+    unsigned long long it = 0;
+    if (lane == 0) it = atomicAdd(p.claimed, 1ull);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    if (p.max_updates > 0 && it >= (unsigned long long)p.max_updates) break;
+
+    // ---- 1. the batch (core/Slave.scala:83-88) ----
+    if (p.replay) {
+      for (int b = lane; b < B; b += 32) rows[b] = p.replay[it * (unsigned long long)B + b];
+    } else if (B == 1) {
+      // data(assignedSamples(Random.nextInt(size)))
+      if (lane == 0) rows[0] = p.assigned[mix64(rng) % (unsigned long long)p.n_assigned];
+    } else {
+      // Random.shuffle(assignedSamples.indices) take batchSize map data: POSITIONS 0..n-1 index `data` directly
+      // (quirk Q6), drawn without replacement
+      if (lane == 0) {
+        for (int b = 0; b < B; ++b) {
+          int32_t pos;
+          bool dup;
+          do {
+            pos = (int32_t)(mix64(rng) % (unsigned long long)p.n_assigned);
+            dup = false;
+            for (int k = 0; k < b; ++k) dup |= (rows[k] == pos);
+          } while (dup);
+          rows[b] = pos;
+        }
+      }
+    }
+    __syncwarp();
+
+    // ---- 2. c from the replica's running S = w . d (SparseSVM.scala:31) ----
+    const double S = *(volatile double *)&w[p.dim + kCtlS];
+    const double c = p.lambda * 2.0 * S;
+    const bool add_c = (c != 0.0) && (fabs(c) > kEps);
+
+    // ---- 3. backward per sample against the current replica, summed into the lane's scratch ----
+    for (int b = 0; b < B; ++b) {
+      const int32_t r = rows[b];
+      const int64_t s0 = (int64_t)p.rp16[r] * 2, s1 = (int64_t)p.rp16[r + 1] * 2;
+      const double y = (double)p.label[r];
+      double dot = 0.0;
+      for (int64_t k = s0 + lane; k < s1; k += 32) {
+        const uint2 pr = p.pairs[k];
+        dot += filt(filt((double)__uint_as_float(pr.y)) * __ldcg(&w[pr.x]));
+      }
+      dot = warp_sum(dot);
+      if (!(y * dot < 0.0)) {  // SparseSVM.scala:28
+        for (int64_t k = s0 + lane; k < s1; k += 32) {
+          const uint2 pr = p.pairs[k];
+          const double gv = filt(filt((double)__uint_as_float(pr.y)) * y);
+          if (gv != 0.0) scratch[pr.x] = filt(scratch[pr.x] + gv);  // Vec.sum: left fold, filter after each +
+        }
+      }
+      __syncwarp();
+    }
+
+    // ---- 4. delta = lr * regularize(sum / B, w) on the summed support; apply to every replica ----
+    double sd = 0.0;  // sum_j delta_j * d_j
+    for (int b = 0; b < B; ++b) {
+      const int32_t r = rows[b];
+      const int64_t s0 = (int64_t)p.rp16[r] * 2, s1 = (int64_t)p.rp16[r + 1] * 2;
+      for (int64_t k = s0 + lane; k < s1; k += 32) {
+        const uint2 pr = p.pairs[k];
+        // a padding pair repeats the row's last column with val == 0: only the real pair may claim the key
+        if (filt((double)__uint_as_float(pr.y)) == 0.0) continue;
+        const double v = scratch[pr.x];
+        if (v != 0.0) {
+          scratch[pr.x] = 0.0;                        // claim the key: later duplicates of the column see 0
+          double m = filt(v / (double)B);             // Vec.mean = sum / size (math/Vec.scala:139)
+          if (m != 0.0 && add_c) m = filt(m + c);     // regularize on the surviving keys
+          const double delta = filt(m * p.lr);        // learningRate * (...)
+          if (delta != 0.0) {
+            for (int q = 0; q < p.n_replicas; ++q) atomicAdd_system(&p.replica[q][pr.x], -delta);
+            sd += delta * p.d[pr.x];
+          }
+        }
+      }
+      __syncwarp();
+    }
+    sd = warp_sum(sd);
+    if (lane == 0) {
+      if (sd != 0.0)
+        for (int q = 0; q < p.n_replicas; ++q) atomicAdd_system(&p.replica[q][p.dim + kCtlS], -sd);
+      if (p.master_slot >= 0)
+        atomicAdd_system(reinterpret_cast<unsigned long long *>(&p.replica[p.master_slot][p.dim + kCtlUpdates]), 1ull);
+      __threadfence_system();
+      atomicAdd(p.done, 1ull);
+    }
+    __syncwarp();
+  }
+}
+
+// weights -= delta for a sparse delta, keeping S in step (core/Slave.scala:177-185; core/ml/GradState.scala:8)
+__global__ void __launch_bounds__(256) k_async_apply_delta(double *__restrict__ w, int dim, const double *__restrict__ d,
+                                                           const int32_t *__restrict__ idx,
+                                                           const double *__restrict__ val, int64_t nnz, int count_update) {
+  __shared__ double red[8];
+  double sd = 0.0;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) {
+    const double v = filt(val[k]);
+    if (v != 0.0) {
+      atomicAdd_system(&w[idx[k]], -v);
+      sd += v * d[idx[k]];
+    }
+  }
+  sd = block_sum<256>(sd, red);
+  if (threadIdx.x == 0) {
+    if (sd != 0.0) atomicAdd_system(&w[dim + kCtlS], -sd);
+    if (count_update && blockIdx.x == 0)
+      atomicAdd_system(reinterpret_cast<unsigned long long *>(&w[dim + kCtlUpdates]), 1ull);
+  }
+}
+
+// S = w . d into the replica's control slot (fixed order), used when weights are installed
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) k_async_init_ctl(double *__restrict__ w, const double *__restrict__ d, int dim) {
+  __shared__ double red[kThreads / 32];
+  double s = 0.0;
+  for (int j = threadIdx.x; j < dim; j += kThreads) s += filt(w[j] * d[j]);
+  s = block_sum<kThreads>(s, red);
+  if (threadIdx.x == 0) {
+    w[dim + kCtlS] = s;
+    reinterpret_cast<unsigned long long *>(w)[dim + kCtlUpdates] = 0ull;
+  }
+}
+
+}  // namespace dsgd

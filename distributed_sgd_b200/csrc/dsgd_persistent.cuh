@@ -151,11 +151,17 @@ __device__ __forceinline__ void sum_partials2(const double *p, int n_cta, int la
 // One grid-wide barrier among the barrier-synchronised warps of every CTA (the producer warp stays out):
 // CTA-level named barrier, one release arrival, relaxed polling, one acquire fence.
 // `target` = number of arrivals that completes this phase.  Returns false if the watchdog fired.
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ bool grid_barrier(unsigned *bar, unsigned target, int *abort_flag, long long timeout,
-                                             int *smem_ok, int n_sync_threads, long long *tl = nullptr) {
+                                             int *smem_ok, int n_sync_threads, long long *tl = nullptr,
+                                             bool tl_ns = false) {
   named_bar_sync(3, n_sync_threads);
   if (threadIdx.x == 0) {
-    if (tl) tl[0] = clock64();
+    if (tl) tl[0] = tl_ns ? global_ns() : clock64();
     red_release_gpu_add(bar, 1u);
     int ok = 1;
     const long long t0 = clock64();
@@ -171,7 +177,7 @@ __device__ __forceinline__ bool grid_barrier(unsigned *bar, unsigned target, int
     }
     fence_acq_rel_gpu();
     *smem_ok = ok;
-    if (tl) tl[1] = clock64();
+    if (tl) tl[1] = tl_ns ? global_ns() : clock64();
   }
   named_bar_sync(3, n_sync_threads);
   return *(volatile int *)smem_ok != 0;
@@ -508,9 +514,13 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
       }
     }
     ++phase;
-    if (!grid_barrier(p.bar, phase * (unsigned)G, p.abort_flag, p.timeout_cycles, &sm.ok, kSyncThreads,
-                      (p.tl && blockIdx.x == 0 && t < 256) ? p.tl + t * 16 + 6 : nullptr))
-      return;
+    long long *tl_slot = nullptr;
+    bool tl_ns = false;
+    if (p.tl) {
+      if (t >= 100 && t < 104) { tl_slot = p.tl + 4096 + ((t - 100) * 160 + blockIdx.x) * 2; tl_ns = true; }
+      else if (blockIdx.x == 0 && t < 256) tl_slot = p.tl + t * 16 + 6;
+    }
+    if (!grid_barrier(p.bar, phase * (unsigned)G, p.abort_flag, p.timeout_cycles, &sm.ok, kSyncThreads, tl_slot, tl_ns)) return;
   }
 
   // ---- epilogue: W_S is complete in wbuf[S & 1]; publish it as the resident weights, clear g_{S-1} ----------

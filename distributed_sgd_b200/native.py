@@ -22,6 +22,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "dsgd.h")
 UNIQUE_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
 FLAG_ASYNC = 1
+REPLICA_SELF, REPLICA_MASTER = 0, 1
 
 OK, ERR_INVALID, ERR_STATE, ERR_EMPTY, ERR_RANGE, ERR_CUDA, ERR_NCCL, ERR_NOMEM, ERR_TIMEOUT = 0, -1, -2, -3, -4, -5, -6, -7, -8
 
@@ -102,8 +103,13 @@ ABI = {
     "dsgd_stage_samples": [_vp, _vp, _i64],
     "dsgd_sync_steps_staged": [_vp, _i64, _i64, _i64, _f64, C.c_int],
     "dsgd_read_losses": [_vp, _vp, _i64],
-    "dsgd_ipc_export": [_vp, _vp],
+    "dsgd_async_host_master": [_vp, _vp],
+    "dsgd_ipc_export": [_vp, C.c_int, _vp],
     "dsgd_ipc_import": [_vp, C.c_int, _vp],
+    "dsgd_peer_attach": [_vp, C.c_int, _vp, C.c_int],
+    "dsgd_async_replay": [_vp, _vp, _vp, _i32, _i64, _f64],
+    "dsgd_async_running": [_vp, C.POINTER(C.c_int)],
+    "dsgd_async_master_weights": [_vp, _vp],
     "dsgd_start_async": [_vp, _vp, _vp, _i64, _i32, _f64, _i32, _i64, _u64],
     "dsgd_stop_async": [_vp],
     "dsgd_update_grad": [_vp, _vp, _vp, _i64],
@@ -336,10 +342,36 @@ class NativeCtx:
         return out
 
     # -- async --
-    def ipc_export(self) -> bytes:
+    def async_host_master(self, w0):
+        """Host the master's replica (GradState.grad + update counter) on this GPU."""
+        w0 = _arr(w0, np.float64, self.dim, "weights")
+        self._ck(self._l.dsgd_async_host_master(self._h, _ptr(w0)))
+
+    def ipc_export(self, which: int = REPLICA_SELF) -> bytes:
         buf = (C.c_uint8 * IPC_HANDLE_BYTES)()
-        self._ck(self._l.dsgd_ipc_export(self._h, C.cast(buf, C.c_void_p)))
+        self._ck(self._l.dsgd_ipc_export(self._h, which, C.cast(buf, C.c_void_p)))
         return bytes(buf)
+
+    def peer_attach(self, peer_rank: int, peer: "NativeCtx", which: int = REPLICA_SELF):
+        """Same-process peer (several ctxs driven by one host process)."""
+        self._ck(self._l.dsgd_peer_attach(self._h, peer_rank, peer._h, which))
+
+    def async_replay(self, w0, samples, batch: int, lr: float):
+        w0 = _arr(w0, np.float64, self.dim, "weights")
+        samples = _arr(samples, np.int32)
+        if samples.size % batch:
+            raise DsgdInvalid(ERR_INVALID, "async_replay: len(samples) is not a multiple of batch")
+        self._ck(self._l.dsgd_async_replay(self._h, _ptr(w0), _ptr(samples), batch, samples.size // batch, lr))
+
+    def async_running(self) -> bool:
+        r = C.c_int()
+        self._ck(self._l.dsgd_async_running(self._h, C.byref(r)))
+        return bool(r.value)
+
+    def async_master_weights(self) -> np.ndarray:
+        out = np.zeros(self.dim, dtype=np.float64)
+        self._ck(self._l.dsgd_async_master_weights(self._h, _ptr(out)))
+        return out
 
     def ipc_import(self, peer_rank: int, handle: bytes):
         buf = (C.c_uint8 * IPC_HANDLE_BYTES).from_buffer_copy(handle)

@@ -144,24 +144,45 @@ int dsgd_sync_steps_staged(dsgd_ctx *ctx, int64_t first, int64_t n_per_step, int
                            int want_losses);
 int dsgd_read_losses(dsgd_ctx *ctx, double *losses_out, int64_t n_steps);
 
-/* ---- async (Hogwild) mode.  Peer replicas are reached by address over NVLink: each rank exports its
- *      weight replica, the host transports the handles, each rank imports its peers'.  Replaces the
- *      slave<->slave channels (core/Slave.scala:23; core/Master.scala:229-233). ---------------------------- */
-int dsgd_ipc_export(dsgd_ctx *ctx, uint8_t handle[DSGD_IPC_HANDLE_BYTES]);
+/* ---- async (Hogwild) mode.  Every worker keeps its own weight replica (core/Slave.scala:30) and pushes each
+ *      delta to every peer replica and to the master's replica (core/Slave.scala:101-105).  Here replicas are
+ *      reached by ADDRESS over NVLink: a rank exports its replica, the host transports the handle, peers import
+ *      it and the device loop issues system-scope fp64 reductions (red.add) straight into peer memory.
+ *      Replaces the slave<->slave and slave->master channels (core/Slave.scala:23,26; core/Master.scala:
+ *      229-233).  `which`: DSGD_REPLICA_SELF = this worker's replica; DSGD_REPLICA_MASTER = the master's replica
+ *      (GradState.grad + the update counter, core/MasterAsync.scala:66,164-177), hosted by the ctx that calls
+ *      dsgd_async_host_master.  peer_rank in dsgd_ipc_import: 0..world-1, or `world` for the master replica. */
+#define DSGD_REPLICA_SELF 0
+#define DSGD_REPLICA_MASTER 1
+int dsgd_async_host_master(dsgd_ctx *ctx, const double *w0);
+int dsgd_ipc_export(dsgd_ctx *ctx, int which, uint8_t handle[DSGD_IPC_HANDLE_BYTES]);
 int dsgd_ipc_import(dsgd_ctx *ctx, int peer_rank, const uint8_t handle[DSGD_IPC_HANDLE_BYTES]);
+/* Same-process peers (several ctxs in one host process, e.g. a JVM driving all GPUs of a box): attach by ctx. */
+int dsgd_peer_attach(dsgd_ctx *ctx, int peer_rank, dsgd_ctx *peer, int which);
 /* SlaveImpl.startAsync (core/Slave.scala:159-175): weights := w0, then the worker loop (asyncTask,
- * core/Slave.scala:79-111) runs on the device until dsgd_stop_async or max_updates local updates.
- * concurrency = number of Hogwild lanes on this GPU (1 = the reference's strictly sequential loop).
- * seed drives the device-side sampling of `assigned` (core/Slave.scala:84,87). */
+ * core/Slave.scala:79-111) runs on the device until dsgd_stop_async or until this worker has made max_updates
+ * updates (0: unbounded).  concurrency = Hogwild lanes on this GPU (warps running the loop body concurrently on
+ * the shared replica; 1 = the reference's strictly sequential loop).  seed drives the device-side sampling of
+ * `assigned` (core/Slave.scala:84,87; batch > 1 indexes rows by POSITION like the reference, quirk Q6).
+ * Returns immediately; the loop runs on its own stream. */
 int dsgd_start_async(dsgd_ctx *ctx, const double *w0, const int32_t *assigned, int64_t n_assigned, int32_t batch,
                      double lr, int32_t concurrency, int64_t max_updates, uint64_t seed);
-/* SlaveImpl.stopAsync (core/Slave.scala:187-195). */
+/* The same loop body over a RECORDED sampling sequence (n_updates * batch row ids), one lane, blocking: the
+ * deterministic K = 1 case of core/Slave.scala:79-111, used to replay a reference run and by the parity tests. */
+int dsgd_async_replay(dsgd_ctx *ctx, const double *w0, const int32_t *samples, int32_t batch, int64_t n_updates,
+                      double lr);
+/* SlaveImpl.stopAsync (core/Slave.scala:187-195): raises the stop flag and waits for the loop to drain. */
 int dsgd_stop_async(dsgd_ctx *ctx);
+/* 1 while the device loop is running (it also ends by itself after max_updates). */
+int dsgd_async_running(dsgd_ctx *ctx, int *running);
 /* SlaveImpl.updateGrad / AsyncMasterGrpcImpl.updateGrad (core/Slave.scala:177-185; core/MasterAsync.scala:
- * 164-177): weights -= delta for a sparse delta given as (idx, val) pairs. */
+ * 164-177): weights -= delta for a sparse delta given as (idx, val) pairs.  which selects the replica. */
 int dsgd_update_grad(dsgd_ctx *ctx, const int32_t *idx, const double *val, int64_t nnz);
-/* GradState.updates as seen by this replica (core/ml/GradState.scala:8; core/MasterAsync.scala:165). */
+/* GradState.updates (core/ml/GradState.scala:8; core/MasterAsync.scala:165): updates the master replica has
+ * received if this ctx hosts or has imported it, else the updates this worker has made. */
 int dsgd_async_updates(dsgd_ctx *ctx, int64_t *count);
+/* Snapshot of the master replica (gradState.single().grad, core/MasterAsync.scala:109). */
+int dsgd_async_master_weights(dsgd_ctx *ctx, double *w_out);
 
 #ifdef __cplusplus
 }

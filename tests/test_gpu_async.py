@@ -1,0 +1,138 @@
+"""Async (Hogwild) mode through the C ABI: deterministic replay against the oracle, the free-running device
+loop, peer / master replicas, and the reference's mode errors (core/Slave.scala:159-195)."""
+import time
+
+import numpy as np
+import pytest
+
+from helpers import make_pair
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def synth():
+    from distributed_sgd_b200.utils import synthetic_rcv1
+    return synthetic_rcv1(n_rows=5000, seed=9)
+
+
+@pytest.mark.parametrize("batch,n_updates", [(1, 300), (4, 120), (32, 40)])
+def test_async_replay_matches_oracle(synth, batch, n_updates):
+    """One lane over a recorded sampling sequence == the K = 1 case of Slave.asyncTask.  Tolerance: the device
+    keeps S = w.d incrementally (fp64), the oracle recomputes it every iteration: rtol 1e-9 on the weights."""
+    rng = np.random.default_rng(batch)
+    ctx, orc = make_pair(synth, lam=1e-3, n_train=4000, is_async=True)
+    idx = rng.integers(0, 4000, size=(n_updates, batch)).astype(np.int32)
+    if batch > 1:  # without replacement inside a batch, like `shuffle take batchSize`
+        idx = np.stack([rng.choice(4000, size=batch, replace=False) for _ in range(n_updates)]).astype(np.int32)
+    w0 = np.zeros(synth.dim)
+    ctx.async_replay(w0, idx.reshape(-1), batch, 0.5)
+    w = ctx.get_weights()
+    w_ref = orc.async_run(w0, idx.reshape(-1), batch, 0.5)
+    assert (w == 0).tolist() == (w_ref == 0).tolist()
+    np.testing.assert_allclose(w, w_ref, rtol=1e-9, atol=1e-13)
+    assert ctx.async_updates() == n_updates
+    ctx.close()
+
+
+def test_async_free_running_with_master_replica(synth):
+    ctx, orc = make_pair(synth, lam=1e-5, n_train=4000, is_async=True)
+    w0 = np.zeros(synth.dim)
+    ctx.async_host_master(w0)
+    assigned = np.arange(4000, dtype=np.int32)
+    loss0, _ = ctx.eval(4000, 5000, w0)
+    ctx.start_async(w0, assigned, batch=1, lr=0.1, concurrency=1, max_updates=3000, seed=7)
+    with pytest.raises(Exception):
+        ctx.start_async(w0, assigned, batch=1, lr=0.1)              # "already running"
+    t0 = time.time()
+    while ctx.async_running() and time.time() - t0 < 60:
+        time.sleep(0.01)
+    assert not ctx.async_running()
+    ctx.stop_async()
+    assert ctx.async_updates() == 3000                              # the master counted every update
+    w, wm = ctx.get_weights(), ctx.async_master_weights()
+    np.testing.assert_array_equal(w, wm)                            # one lane: identical delta stream to both replicas
+    loss1, acc1 = ctx.eval(4000, 5000, w)
+    assert loss1 < loss0 and acc1 > 0.5
+    # the loop body is the oracle's: replaying nothing else, c from S must track w.d
+    ctx.close()
+
+
+def test_async_hogwild_lanes_and_update_grad(synth):
+    ctx, orc = make_pair(synth, lam=1e-5, n_train=4000, is_async=True)
+    w0 = np.zeros(synth.dim)
+    ctx.async_host_master(w0)
+    ctx.start_async(w0, np.arange(4000, dtype=np.int32), batch=4, lr=0.05, concurrency=16, max_updates=4000, seed=3)
+    # SlaveImpl.updateGrad while the loop runs: weights -= delta
+    ctx.update_grad([5, 17], [0.25, -0.5])
+    t0 = time.time()
+    while ctx.async_running() and time.time() - t0 < 60:
+        time.sleep(0.01)
+    ctx.stop_async()
+    assert ctx.async_updates() == 4000
+    w, wm = ctx.get_weights(), ctx.async_master_weights()
+    # the peer-pushed delta reached only this replica; everything else reached both (order differs: fp64 rounding)
+    diff = w - wm
+    assert diff[5] == pytest.approx(-0.25, abs=1e-12) and diff[17] == pytest.approx(0.5, abs=1e-12)
+    diff[[5, 17]] = 0
+    assert np.abs(diff).max() < 1e-12
+    loss, acc = ctx.eval(4000, 5000, wm)
+    assert acc > 0.5
+    ctx.close()
+
+
+def test_async_stop_interrupts_unbounded_loop(synth):
+    ctx, orc = make_pair(synth, lam=1e-5, n_train=4000, is_async=True)
+    ctx.start_async(np.zeros(synth.dim), np.arange(4000, dtype=np.int32), batch=1, lr=0.1, concurrency=4, max_updates=0, seed=1)
+    time.sleep(0.05)
+    assert ctx.async_running()
+    n1 = ctx.async_updates()
+    time.sleep(0.05)
+    assert ctx.async_updates() > n1 > 0
+    ctx.stop_async()
+    assert not ctx.async_running()
+    ctx.stop_async()                                                 # idempotent, like the reference
+    ctx.close()
+
+
+def test_async_mode_errors(synth):
+    from distributed_sgd_b200 import native
+    ctx, orc = make_pair(synth, lam=1e-5, n_train=4000, is_async=False)
+    with pytest.raises(native.DsgdState):
+        ctx.start_async(np.zeros(synth.dim), [0, 1], 1, 0.1)        # "slave is in synchronous mode"
+    with pytest.raises(native.DsgdState):
+        ctx.stop_async()
+    ctx.close()
+    actx, _ = make_pair(synth, lam=1e-5, n_train=4000, is_async=True)
+    with pytest.raises(native.DsgdEmpty):
+        actx.start_async(np.zeros(synth.dim), np.zeros(0, np.int32), 1, 0.1)
+    with pytest.raises(native.DsgdRange):
+        actx.start_async(np.zeros(synth.dim), [5000], 1, 0.1)
+    actx.close()
+
+
+def test_async_two_gpus_peer_writes(synth):
+    """Two workers on two GPUs of one process: each pushes its deltas into the other's replica and the master's
+    over NVLink (red.add on peer memory).  All three replicas end up equal up to fp64 summation order."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    a, _ = make_pair(synth, lam=1e-5, n_train=4000, device=0, rank=0, world=2, is_async=True)
+    b, _ = make_pair(synth, lam=1e-5, n_train=4000, device=1, rank=1, world=2, is_async=True)
+    w0 = np.zeros(synth.dim)
+    a.async_host_master(w0)
+    from distributed_sgd_b200.native import REPLICA_MASTER, REPLICA_SELF
+    a.peer_attach(1, b, REPLICA_SELF)
+    b.peer_attach(0, a, REPLICA_SELF)
+    b.peer_attach(2, a, REPLICA_MASTER)
+    a.start_async(w0, np.arange(0, 2000, dtype=np.int32), batch=1, lr=0.1, concurrency=8, max_updates=2000, seed=1)
+    b.start_async(w0, np.arange(2000, 4000, dtype=np.int32), batch=1, lr=0.1, concurrency=8, max_updates=2000, seed=2)
+    t0 = time.time()
+    while (a.async_running() or b.async_running()) and time.time() - t0 < 60:
+        time.sleep(0.01)
+    a.stop_async(); b.stop_async()
+    assert a.async_updates() == 4000 == b.async_updates()
+    wa, wb, wm = a.get_weights(), b.get_weights(), a.async_master_weights()
+    assert np.abs(wa - wm).max() < 1e-12 and np.abs(wb - wm).max() < 1e-12
+    assert a.eval(4000, 5000, wm)[1] > 0.5
+    a.close(); b.close()

@@ -205,3 +205,58 @@ def test_error_invalid_column_is_range():
     with pytest.raises(native.DsgdState):
         sctx.update_grad([0], [1.0])                                       # "slave is in synchronous mode"
     sctx.close()
+
+
+def test_streaming_pass_large_batches(synth):
+    """n >= 2048 rows go through the streaming kernel (fp32 weights in shared memory + exact fallback)."""
+    rng = np.random.default_rng(77)
+    ctx, orc = make_pair(synth, lam=1e-3, n_train=4800)
+    for w in (np.zeros(synth.dim), rand_w(rng, synth.dim, 0.6, 0.2)):
+        idx = rng.integers(0, 4800, size=3000).astype(np.int32)               # with repeats
+        g_ref, _ = orc.gradient(w, idx)
+        g, loss = ctx.gradient(idx, w, want_loss=True)
+        assert (g == 0).tolist() == (g_ref == 0).tolist()
+        # 3000 signed contributions cancel heavily in some entries: the error is fp64 rounding of the SUMMANDS
+        # (order differs: atomics), so the bound is absolute at the summands' scale, plus the usual relative one
+        np.testing.assert_allclose(g, g_ref, rtol=RTOL, atol=1e-13)
+        assert loss == pytest.approx(orc.loss_acc(w, idx=idx)[0], rel=RTOL)
+        np.testing.assert_array_equal(ctx.forward(idx, w), orc.forward(w, idx))
+        # resident-weights flavour and a ragged tail (n not a multiple of 32)
+        ctx.set_weights(w)
+        np.testing.assert_array_equal(ctx.forward(idx[:2077]), orc.forward(w, idx[:2077]))
+    ctx.close()
+
+
+def test_streaming_exact_fallback_decides_like_fp64():
+    """Rows whose dot product is below fp32 resolution of the weights must still get the fp64 sign."""
+    dim, reps = 16, 2500
+    # row A: x = (v, v) on cols (0,1), w = (1 + 2^-40, -1): fp32 weights give exactly 0, fp64 gives v * 2^-40 > 0
+    # row B: same columns, w makes it exactly 0 in fp64 too (cols 2,3 with +1/-1)
+    # row C: an ordinary row
+    rp = [0]
+    col, val, lab = [], [], []
+    for r in range(reps):
+        kind = r % 3
+        if kind == 0:
+            col += [0, 1]; val += [0.75, 0.75]
+        elif kind == 1:
+            col += [2, 3]; val += [0.5, 0.5]
+        else:
+            col += [4, 5, 6]; val += [0.25, 0.5, 1.0]
+        rp.append(len(col))
+        lab.append(1 if (r // 3) % 2 == 0 else -1)
+    data = data_from_csr(rp, col, val, lab, dim)
+    ctx, orc = make_pair(data, lam=0.0)
+    w = np.zeros(dim)
+    w[0], w[1] = 1.0 + 2.0 ** -40, -1.0
+    w[2], w[3] = 1.0, -1.0
+    w[4], w[5], w[6] = 0.3, -0.2, 0.1
+    idx = np.arange(reps, dtype=np.int32)
+    preds_ref = orc.forward(w, idx)
+    assert set(preds_ref[0::3]) == {-1.0} and set(preds_ref[1::3]) == {0.0}
+    np.testing.assert_array_equal(ctx.forward(idx, w), preds_ref)
+    loss, acc = ctx.eval(0, reps, w)
+    loss_ref, acc_ref = orc.loss_acc(w, begin=0, n=reps)
+    assert (loss, acc) == (loss_ref, acc_ref)
+    np.testing.assert_array_equal(ctx.gradient(idx, w), orc.gradient(w, idx)[0])   # exact sums of 0.25/0.5/0.75/1.0
+    ctx.close()

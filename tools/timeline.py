@@ -18,9 +18,11 @@ ctx.set_weights(np.zeros(data.dim))
 for _ in range(2):
     ctx.sync_steps_staged(0, B, S, 0.5, want_losses=True)
 ctx.synchronize()
-tl = np.zeros((256, 16), dtype=np.int64)
+tl_all = np.zeros(256 * 16 + 4 * 160 * 2, dtype=np.int64)
 l = lib(); l.dsgd_debug_timeline.argtypes = [C.c_void_p, C.c_void_p]
-assert l.dsgd_debug_timeline(ctx._h, tl.ctypes.data_as(C.c_void_p)) == 0
+assert l.dsgd_debug_timeline(ctx._h, tl_all.ctypes.data_as(C.c_void_p)) == 0
+tl = tl_all[:4096].reshape(256, 16)
+per_cta = tl_all[4096:].reshape(4, 160, 2)
 names = {0: "interval start (consumer warp 0)", 1: "stage full (TMA landed)", 2: "pass 1 done (partial dots)",
          3: "pass 2 done (scatter issued)", 6: "CTA synced, arriving at grid barrier", 7: "grid barrier passed",
          8: "interval start (update warp 0)", 9: "c summed + handed over", 10: "update slice + partials published"}
@@ -33,3 +35,10 @@ for k in sorted(names):
     v = v[t[:, k] > 0]
     if len(v):
         print(f"  {names[k]:45s} +{np.mean(v):8.0f} cycles (min {v.min()}, max {v.max()})")
+
+G = int(os.environ.get("DSGD_PERSIST_CTAS", "148"))
+for k in range(4):
+    a = per_cta[k, :G, 0]; b = per_cta[k, :G, 1]
+    a0 = a.min()
+    print(f"step {100+k} (ns, globaltimer): arrivals spread {a.max()-a0} (p50 {int(np.median(a-a0))}, p90 {int(np.percentile(a-a0,90))}); "
+          f"last arrival -> first pass {b.min()-a.max()} ; last arrival -> last pass {b.max()-a.max()}")
