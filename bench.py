@@ -198,6 +198,8 @@ def main():
     if world > 1:
         uid = NativeCtx.comm_unique_id() if rank == 0 else b""
         ctx.comm_init(group.broadcast_bytes(uid, 0))
+        if not os.environ.get("DSGD_NO_P2P"):
+            ctx.setup_peer_exchange(group)   # fused step: gradients summed out of peer memory over NVLink
 
     B = args.batch
     S = args.sgd_steps or -(-n_train // B)            # one epoch of the 1-worker fit loop: ceil(560000 / 256) = 2188
@@ -269,6 +271,32 @@ def main():
         else "k_rows<scatter> (gradient, one launch per SGD step)"
     step_frac = (float(np.mean(alg_bytes_per_step[args.warmup:])) * args.steps / (ms * 1e-3) / 1e9) / hbm_peak
 
+    # ---- leg 3b: the same row kernels where they are bandwidth- rather than latency-bound -----------------------
+    # (batch 256 moves 197 KB per step; the HBM roofline of the path shows on the full-shard evaluation pass,
+    #  Master.localLoss/localAccuracy, and on the gradient of a very large batch -- SURVEY.md 8d "Expected regime")
+    streaming = None
+    if rank == 0:
+        def best_ms(fn, reps=5):
+            fn(); ctx.synchronize()
+            ts = []
+            for _ in range(reps):
+                ctx.profile_begin(1); fn(); t_ms, _n = ctx.profile_end(); ts.append(t_ms)
+            return min(ts)
+        ev_bytes = data.algorithmic_bytes(np.arange(n_train))
+        ev_ms = best_ms(lambda: ctx.eval(0, n_train))
+        big = np.random.default_rng(1).choice(n_train, size=min(262144, n_train), replace=False).astype(np.int32)
+        gr_bytes = data.algorithmic_bytes(big)
+        gr_ms = best_ms(lambda: ctx.gradient(big))
+        streaming = {
+            "eval_full_train_pass": {"kernel": "k_stream_rows<eval>", "rows": int(n_train), "ms": ev_ms,
+                                     "achieved": ev_bytes / ev_ms / 1e6, "unit": "GB/s", "frac": ev_bytes / ev_ms / 1e6 / hbm_peak},
+            "gradient_batch_%d" % len(big): {"kernel": "k_stream_rows<scatter>", "rows": int(len(big)), "ms": gr_ms,
+                                             "achieved": gr_bytes / gr_ms / 1e6, "unit": "GB/s",
+                                             "frac": gr_bytes / gr_ms / 1e6 / hbm_peak,
+                                             "note": "bounded by fp64 RED issue rate at L2 (0.48 per SM-cycle measured), not HBM"},
+        }
+    barrier()
+
     # ---- leg 4: CPU baseline on this host (rank 0, N = 1 only) -------------------------------------------
     cpu = None
     if rank == 0 and world == 1:
@@ -294,6 +322,7 @@ def main():
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_per_launch, "kernel_ms": k_ms, "launches_sampled": int(k_n),
                          "whole_step_frac": step_frac},
+            "roofline_streaming": streaming,
             "cpu_baseline": cpu,
             "clocks": clock_info,
             "final_batch_loss": float(last_losses[-1]),

@@ -44,8 +44,12 @@ class Master:
         self.rng = np.random.default_rng(seed)
         self.log = log or (lambda s: None)
         if self.group.world > 1 and not slave.is_async:
+            # NCCL communicator (general path: several logical workers per GPU) ...
             uid = NativeCtx.comm_unique_id() if self.group.rank == 0 else b""
             self.ctx.comm_init(self.group.broadcast_bytes(uid, 0))
+            # ... and the peer-memory exchange of the fused persistent kernel (one worker per GPU)
+            if hasattr(self.ctx, "setup_peer_exchange"):
+                self.ctx.setup_peer_exchange(self.group)
 
     @staticmethod
     def create(node, data, test_data, model, is_async, node_count, **kw) -> "Master":

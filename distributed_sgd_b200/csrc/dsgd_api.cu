@@ -90,6 +90,12 @@ struct dsgd_ctx {
   int32_t *u_idx = nullptr; double *u_val = nullptr; int64_t u_cap = 0;  // update_grad staging
   bool a_running = false;
 
+  // sync-mode exchange block shared with peers over NVLink: 3 gradient buffers (dim + 8 doubles each) + flag words
+  double *xblk = nullptr;
+  double *peer_x[kMaxWorld] = {};
+  bool peer_x_ipc[kMaxWorld] = {};
+  int64_t x_step = 0;   // global step counter of the fused multi-GPU kernel (identical on every rank)
+
   // sampled per-launch timing of the gradient kernel
   int32_t prof_every = 0;
   int64_t prof_seen = 0;
@@ -255,6 +261,9 @@ extern "C" int dsgd_destroy(dsgd_ctx *ctx) {
   if (ctx->comm) nccl().CommDestroy(ctx->comm);
   for (int r = 0; r < kMaxReplicas; ++r)
     if (ctx->peer_w[r] && ctx->peer_ipc[r]) cudaIpcCloseMemHandle(ctx->peer_w[r]);
+  for (int r = 0; r < kMaxWorld; ++r)
+    if (ctx->peer_x[r] && ctx->peer_x_ipc[r]) cudaIpcCloseMemHandle(ctx->peer_x[r]);
+  if (ctx->xblk) cudaFree(ctx->xblk);
   void *aptrs[] = {ctx->m_w, ctx->a_stop, ctx->a_cnt, ctx->a_scratch, ctx->a_rows, ctx->a_assigned, ctx->a_replay, ctx->u_idx, ctx->u_val};
   for (void *q : aptrs) if (q) cudaFree(q);
   if (ctx->astream) cudaStreamDestroy(ctx->astream);
@@ -708,7 +717,8 @@ extern "C" int dsgd_comm_init(dsgd_ctx *ctx, const uint8_t id[DSGD_UNIQUE_ID_BYT
 // ---- persistent single-worker loop ------------------------------------------------------------------------
 constexpr int kPCons = 8, kPUpd = 6, kPStages = 8, kPStagePairs = 2560, kPMaxChunks = 128;
 using PSmem = PersistSmem<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks>;
-#define DSGD_PERSIST_KERNEL k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks>
+#define DSGD_PERSIST_KERNEL k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, false>
+#define DSGD_PERSIST_KERNEL_MULTI k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, true>
 
 static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
   if (!ctx->p_ready) {
@@ -721,6 +731,7 @@ static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
     CU(cudaMalloc(&ctx->p_partial, sizeof(double) * 2 * 2 * (size_t)ctx->sm_count));
     CU(cudaMalloc(&ctx->p_bar, sizeof(unsigned) * 4));
     CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
+    CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL_MULTI, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
     ctx->p_ready = true;
   }
   if (ctx->p_hinge_cap < n_steps) {
@@ -755,6 +766,8 @@ static int persist_run(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t n_per_
   CU(cudaMemsetAsync(ctx->p_hinge, 0, sizeof(unsigned) * (size_t)n_steps, ctx->stream));
   CU(cudaMemsetAsync(ctx->p_bar, 0, sizeof(unsigned) * 4, ctx->stream));
   PersistParams pp;
+  memset(&pp, 0, sizeof pp);
+  pp.world = 1;
   pp.rp16 = ctx->rp16; pp.pairs = ctx->pairs; pp.label = ctx->label; pp.samples = samples_dev;
   pp.n_steps = n_steps; pp.batch = (int32_t)n_per_step; pp.dim = ctx->dim;
   pp.wbuf[0] = ctx->p_wbuf[0]; pp.wbuf[1] = ctx->p_wbuf[1];
@@ -777,6 +790,124 @@ static int persist_run(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t n_per_
                                  ctx->stream));
   if (pe) cudaEventRecord(pe->second, ctx->stream);
   LAUNCHED();
+  return DSGD_OK;
+}
+
+// ---- fused multi-GPU loop: all ranks run the persistent kernel and exchange gradients through peer memory ----
+// exported block of a rank: receive area [sender][parity][dim + 8] doubles, then flag words [sender][cta] (u64)
+constexpr int kXFlagCtas = 192;
+static size_t xblk_doubles(const dsgd_ctx *ctx) {  // an LL element is 16 bytes = 2 doubles' worth
+  return 2 * (size_t)kMaxWorld * 2 * (size_t)(ctx->dim + kReplicaPad) + (size_t)kMaxWorld * kXFlagCtas;
+}
+
+static int xblk_ensure(dsgd_ctx *ctx) {
+  if (ctx->xblk) return DSGD_OK;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMalloc(&ctx->xblk, sizeof(double) * xblk_doubles(ctx)));
+  CU(cudaMemset(ctx->xblk, 0, sizeof(double) * xblk_doubles(ctx)));
+  return DSGD_OK;
+}
+
+static bool xchg_complete(const dsgd_ctx *ctx) {
+  if (ctx->world <= 1 || ctx->world > kMaxWorld || !ctx->xblk) return false;
+  for (int r = 0; r < ctx->world; ++r)
+    if (r != ctx->rank && !ctx->peer_x[r]) return false;
+  return true;
+}
+
+static int persist_run_multi(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t n_per_step, int64_t n_steps, double lr,
+                             double *losses_dev) {
+  int rc = persist_prepare(ctx, n_steps);
+  if (rc) return rc;
+  const int G = ctx->sm_count;  // the same on every rank
+  NEED((uint64_t)G * (uint64_t)(2 * n_steps + 2) < (1ull << 32), DSGD_ERR_INVALID, "dsgd_sync_steps: too many steps for one launch");
+  const size_t vd = sizeof(double) * (size_t)ctx->dim;
+  CU(cudaMemcpyAsync(ctx->p_wbuf[ctx->x_step & 1], ctx->w, vd, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemsetAsync(ctx->p_bar, 0, sizeof(unsigned) * 4, ctx->stream));
+  PersistParams pp;
+  memset(&pp, 0, sizeof pp);
+  pp.rp16 = ctx->rp16; pp.pairs = ctx->pairs; pp.label = ctx->label; pp.samples = samples_dev;
+  pp.n_steps = n_steps; pp.batch = (int32_t)n_per_step; pp.dim = ctx->dim;
+  pp.wbuf[0] = ctx->p_wbuf[0]; pp.wbuf[1] = ctx->p_wbuf[1];
+  for (int i = 0; i < 3; ++i) pp.gbuf[i] = ctx->p_gbuf[i];
+  pp.d = ctx->d; pp.partial = ctx->p_partial; pp.hinge = ctx->p_hinge; pp.losses = losses_dev;
+  pp.w_out = ctx->w; pp.w32_out = ctx->w32; pp.scal = ctx->scal;
+  pp.bar = ctx->p_bar; pp.abort_flag = reinterpret_cast<int *>(ctx->p_bar + 1);
+  pp.lambda = ctx->lambda; pp.lr = lr; pp.k_den = (double)ctx->world;
+  pp.timeout_cycles = 20000000000ll;  // ~10 s: covers a peer that launches late
+  pp.tl = nullptr;
+  if (getenv("DSGD_PERSIST_TIMELINE")) {
+    if (!ctx->p_tl) CU(cudaMalloc(&ctx->p_tl, sizeof(long long) * (256 * 16 + 4 * 160 * 2)));
+    CU(cudaMemsetAsync(ctx->p_tl, 0, sizeof(long long) * (256 * 16 + 4 * 160 * 2), ctx->stream));
+    pp.tl = ctx->p_tl;
+  }
+  pp.world = ctx->world; pp.rank = ctx->rank; pp.step_base = ctx->x_step;
+  const size_t stride = (size_t)(ctx->dim + kReplicaPad);
+  NEED(G <= kXFlagCtas, DSGD_ERR_INVALID, "more SMs than flag words");
+  pp.xstride = (int)stride;
+  for (int b = 0; b < 3; ++b) pp.xg[b] = ctx->p_gbuf[b];   // local: peers never read them, they receive pushed copies
+  for (int r = 0; r < ctx->world; ++r) {
+    double *base = (r == ctx->rank) ? ctx->xblk : ctx->peer_x[r];
+    pp.xrecv[r] = base;
+    pp.xflag[r] = reinterpret_cast<unsigned long long *>(base + 2 * (size_t)kMaxWorld * 2 * stride);
+  }
+  void *args[] = {&pp};
+  auto *pe = prof_slot(ctx);
+  if (pe) cudaEventRecord(pe->first, ctx->stream);
+  CU(cudaLaunchCooperativeKernel((void *)DSGD_PERSIST_KERNEL_MULTI, dim3(G), dim3((kPCons + kPUpd + 1) * 32), args, sizeof(PSmem),
+                                 ctx->stream));
+  if (pe) cudaEventRecord(pe->second, ctx->stream);
+  LAUNCHED();
+  ctx->x_step += n_steps;
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_xchg_export(dsgd_ctx *ctx, uint8_t handle[DSGD_IPC_HANDLE_BYTES]) {
+  if (!ctx || !handle) return DSGD_ERR_INVALID;
+  NEED(!(ctx->flags & DSGD_FLAG_ASYNC), DSGD_ERR_STATE, "dsgd_xchg_export: ctx is in async mode");
+  int rc = xblk_ensure(ctx);
+  if (rc) return rc;
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, ctx->xblk));
+  memcpy(handle, &h, sizeof h);
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_xchg_import(dsgd_ctx *ctx, int peer_rank, const uint8_t handle[DSGD_IPC_HANDLE_BYTES]) {
+  if (!ctx || !handle) return DSGD_ERR_INVALID;
+  NEED(peer_rank >= 0 && peer_rank < ctx->world && peer_rank < kMaxWorld && peer_rank != ctx->rank, DSGD_ERR_INVALID,
+       "dsgd_xchg_import: bad peer rank %d", peer_rank);
+  int rc = xblk_ensure(ctx);
+  if (rc) return rc;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  void *ptr = nullptr;
+  CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  if (ctx->peer_x[peer_rank] && ctx->peer_x_ipc[peer_rank]) cudaIpcCloseMemHandle(ctx->peer_x[peer_rank]);
+  ctx->peer_x[peer_rank] = static_cast<double *>(ptr);
+  ctx->peer_x_ipc[peer_rank] = true;
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_xchg_attach(dsgd_ctx *ctx, int peer_rank, dsgd_ctx *peer) {
+  if (!ctx || !peer) return DSGD_ERR_INVALID;
+  NEED(peer_rank >= 0 && peer_rank < ctx->world && peer_rank < kMaxWorld && peer_rank != ctx->rank, DSGD_ERR_INVALID,
+       "dsgd_xchg_attach: bad peer rank %d", peer_rank);
+  NEED(peer->dim == ctx->dim, DSGD_ERR_INVALID, "dsgd_xchg_attach: dimension mismatch");
+  int rc = xblk_ensure(ctx);
+  if (rc) return rc;
+  if ((rc = xblk_ensure(peer))) { ctx->err = peer->err; return rc; }
+  CU(cudaSetDevice(ctx->device));
+  if (peer->device != ctx->device) {
+    int can = 0;
+    CU(cudaDeviceCanAccessPeer(&can, ctx->device, peer->device));
+    NEED(can, DSGD_ERR_CUDA, "dsgd_xchg_attach: device %d cannot access device %d", ctx->device, peer->device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+    (void)cudaGetLastError();
+  }
+  ctx->peer_x[peer_rank] = peer->xblk;
+  ctx->peer_x_ipc[peer_rank] = false;
   return DSGD_OK;
 }
 
@@ -821,7 +952,8 @@ extern "C" int dsgd_sync_steps_staged(dsgd_ctx *ctx, int64_t first, int64_t n_pe
   NEED(n_steps >= 0 && first >= 0, DSGD_ERR_INVALID, "dsgd_sync_steps: bad arguments");
   NEED(n_per_step >= 0, DSGD_ERR_INVALID, "dsgd_sync_steps: bad arguments");
   NEED(first + n_per_step * n_steps <= ctx->samples_n, DSGD_ERR_RANGE, "dsgd_sync_steps: staged samples exhausted");
-  NEED(ctx->world == 1 || ctx->comm, DSGD_ERR_STATE, "dsgd_sync_steps: world > 1 but dsgd_comm_init was not called");
+  NEED(ctx->world == 1 || ctx->comm || xchg_complete(ctx), DSGD_ERR_STATE,
+       "dsgd_sync_steps: world > 1 but neither dsgd_comm_init nor the peer exchange (dsgd_xchg_*) was set up");
   if (ctx->n_local == 0) {
     NEED(n_per_step == 0, DSGD_ERR_INVALID, "dsgd_sync_steps: a bystander rank (n_local == 0) takes no samples");
   } else {
@@ -846,6 +978,12 @@ extern "C" int dsgd_sync_steps_staged(dsgd_ctx *ctx, int64_t first, int64_t n_pe
   if (single && !no_persist && n_steps > 0 && persist_grid(ctx, n_per_step) > 0) {
     // one worker on one GPU: the whole run of steps is one persistent cooperative kernel
     return persist_run(ctx, ctx->samples + first, n_per_step, n_steps, lr, want_losses ? ctx->losses : nullptr);
+  }
+  static const bool no_p2p = getenv("DSGD_NO_P2P") != nullptr;
+  if (!no_p2p && !no_persist && ctx->world > 1 && ctx->n_local == 1 && k_total == ctx->world && n_steps > 0 &&
+      xchg_complete(ctx) && persist_grid(ctx, n_per_step) > 0) {
+    // one worker per GPU, every peer's exchange block mapped: aggregate inside the persistent kernel over NVLink
+    return persist_run_multi(ctx, ctx->samples + first, n_per_step, n_steps, lr, want_losses ? ctx->losses : nullptr);
   }
   for (int64_t s = 0; s < n_steps; ++s) {
     const int32_t *smp = ctx->samples + first + s * n_per_step;
@@ -999,12 +1137,14 @@ static int async_launch(dsgd_ctx *ctx, const double *w0, const int32_t *assigned
   NEED(!ctx->a_running, DSGD_ERR_STATE,
        "Async computation already running, can't be initialized unless stopped first");
   NEED(ctx->pairs && ctx->have_d, DSGD_ERR_STATE, "dsgd_start_async: rows or dimSparsity missing");
-  NEED(w0 && batch >= 1 && lanes >= 1 && lanes <= 4096, DSGD_ERR_INVALID, "dsgd_start_async: bad arguments");
+  NEED(batch >= 1 && lanes >= 1 && lanes <= 4096, DSGD_ERR_INVALID, "dsgd_start_async: bad arguments");
   CU(cudaSetDevice(ctx->device));
-  // weights() = request.weights
-  CU(cudaMemcpyAsync(ctx->w, w0, sizeof(double) * (size_t)ctx->dim, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = refresh_resident(ctx);  // also S = w . d and the control slots of the replica
-  if (rc) return rc;
+  int rc = DSGD_OK;
+  if (w0) {  // weights() = request.weights
+    CU(cudaMemcpyAsync(ctx->w, w0, sizeof(double) * (size_t)ctx->dim, cudaMemcpyHostToDevice, ctx->stream));
+    rc = refresh_resident(ctx);  // also S = w . d and the control slots of the replica
+    if (rc) return rc;
+  }  // else: keep the resident replica (already initialised; deltas peers pushed since then must survive)
   if (ctx->a_scratch_lanes < lanes) {
     if (ctx->a_scratch) CU(cudaFree(ctx->a_scratch));
     ctx->a_scratch = nullptr; ctx->a_scratch_lanes = 0;

@@ -32,6 +32,8 @@
 
 namespace dsgd {
 
+constexpr int kMaxWorld = 16;
+
 struct PersistParams {
   const uint32_t *rp16;
   const uint2 *pairs;
@@ -54,6 +56,14 @@ struct PersistParams {
   double lambda, lr, k_den;
   long long timeout_cycles;
   long long *tl;    // debug timeline: [256 steps][16 stamps] of clock64 (CTA 0), or nullptr
+  // ---- multi-GPU exchange over peer memory (world > 1): every rank's gradient buffers and flag words are mapped
+  //      into every other rank's address space (cudaIpc / peer access over NVLink) ----
+  int world, rank;
+  int64_t step_base;                           // global step number of this launch's first step (same on all ranks)
+  double *xg[3];                               // this rank's gradient buffers (local, dim + 8 doubles each)
+  double *xrecv[kMaxWorld];                    // xrecv[k]: receive area of rank k: [sender][parity][dim + 8]; [rank] is local
+  unsigned long long *xflag[kMaxWorld];        // xflag[k]: flag words of rank k: [sender][cta]; [rank] is local
+  int xstride;                                 // dim + 8
 };
 
 // ---- PTX helpers: mbarrier + TMA bulk copy -------------------------------------------------------------
@@ -105,6 +115,41 @@ __device__ __forceinline__ void red_release_gpu_add(unsigned *p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double *p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// "LL" element of the cross-GPU exchange: a double travels as two 8-byte words {low 32 bits, tag} and
+// {high 32 bits, tag}.  An aligned 8-byte store is single-copy atomic, so a word whose tag matches carries valid
+// data: no fence, no separate flag, one one-way NVLink store per word (the scheme of NCCL's LL protocol).
+__device__ __forceinline__ void ll_store(unsigned long long *dst, double v, unsigned tag) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long w0 = (bits & 0xffffffffull) | ((unsigned long long)tag << 32);
+  const unsigned long long w1 = (bits >> 32) | ((unsigned long long)tag << 32);
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ bool ll_try_load(const unsigned long long *src, unsigned tag, double &v) {
+  unsigned long long w0, w1;
+  asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+  if ((unsigned)(w0 >> 32) != tag || (unsigned)(w1 >> 32) != tag) return false;
+  v = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+  return true;
+}
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
@@ -183,6 +228,7 @@ __device__ __forceinline__ bool grid_barrier(unsigned *bar, unsigned target, int
   return *(volatile int *)smem_ok != 0;
 }
 
+constexpr int kChunkPairs_unused_guard = 0;
 constexpr int kChunkPairs = 128;             // 4 pairs per lane per chunk
 constexpr uint32_t kChunkGlobal = 1u << 31;  // chunk offset flag: read from global, the row did not fit the stage
 constexpr int kMaxRowsPerCta = 32;           // rows of one step per CTA (one producer lane each)
@@ -220,7 +266,7 @@ struct PersistSmem {
     if (p.tl && blockIdx.x == 0 && lane == 0 && t < 256) p.tl[t * 16 + (slot_)] = clock64(); \
   } while (0)
 
-template <int kCons, int kUpd, int kStages, int kStagePairs, int kMaxChunks>
+template <int kCons, int kUpd, int kStages, int kStagePairs, int kMaxChunks, bool kMulti>
 __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(const PersistParams p) {
   using Smem = PersistSmem<kCons, kUpd, kStages, kStagePairs, kMaxChunks>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -326,6 +372,225 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
       load_win(id_next, b1, e1, y1);
       id_next = load_id(t + 3);
     }
+    return;
+  }
+
+  if constexpr (kMulti) {
+    // =======================================================================================================
+    // world > 1: aggregate over GPUs inside the kernel, through peer memory.  Step T (global number):
+    //   [A] consumers: x.W_T from the materialised W_T buffer; gate; RED y*x into this rank's g_T
+    //       -- grid barrier 1 --
+    //   [push] CTA b owns a contiguous slice of the columns on EVERY rank: it copies its slice of g_T into each
+    //       peer's receive area with plain remote stores (one-way NVLink traffic, no round trip), fences at
+    //       system scope and raises ITS flag word on each peer.
+    //   [B] CTA b waits for the K-1 flags of the peers' CTA b only, then reduces its slice from LOCAL memory in
+    //       rank order (the master's left fold over replies, core/Master.scala:194), regularizing each reply on
+    //       its own support: W_{T+1} = W_T - lr * sum / K; partials of c_{T+1}, ||W_{T+1}||^2;
+    //       zeroes the buffer g_{T+1} will use.
+    //       -- grid barrier 2 --
+    // Every rank computes the full W_{T+1} itself with the same operations in the same order: replicas stay
+    // bit-identical, no broadcast exists.  The cross-GPU critical path is one store + fence + one flag store.
+    // =======================================================================================================
+    const int K = p.world, me = p.rank;
+    // columns per CTA, plus ONE counter slot [dim] = hinge total + 2^32 * sample count (exact in fp64)
+    const int slice = (p.dim + 1 + G - 1) / G;
+    const int j_lo = min(blockIdx.x * slice, p.dim + 1), j_hi = min(j_lo + slice, p.dim + 1);
+    const int cnt_owner = p.dim / slice;                          // the CTA whose slice holds slot [dim]
+    const int n_all = G * kSyncThreads;
+    const int a0 = blockIdx.x * kSyncThreads + threadIdx.x;
+    const int par_stride = p.xstride, snd_stride = 2 * p.xstride;
+    const double lr = p.lr, kd = (double)K;
+    unsigned phase = 0;
+    double c_cur = p.scal[kScalC], nrm_cur = p.scal[kScalNrm2];  // of W_base, left by the previous launch / k_prepare
+    for (int64_t t = 0; t < S; ++t) {
+      const int64_t T = p.step_base + t;
+      const double *Wt = p.wbuf[T & 1];
+      double *Wn = p.wbuf[(T + 1) & 1];
+      double *Gme = p.xg[T % 3];
+      double *Gzero = p.xg[(T + 1) % 3];
+      const int par = (int)(T & 1);
+      double *part_cur = p.partial + (size_t)((T + 1) & 1) * G * 2;
+      if (warp == 0) DSGD_TL(0);
+      if (is_cons) {
+        const int st = (int)(t % kStages);
+        auto &mt = sm.meta[st];
+        mbar_wait(&sm.full[st], (unsigned)((t / kStages) & 1), p.abort_flag, p.timeout_cycles);
+        if (warp == 0) DSGD_TL(1);
+        const int n_ch = mt.n_chunks;
+        const uint2 *ring = &sm.ring[st][0];
+        for (int c = warp; c < n_ch; c += kCons) {
+          const uint32_t off = mt.ch_off[c];
+          const int n = mt.ch_n[c];
+          const uint2 *src = (off & kChunkGlobal) ? (p.pairs + (off & ~kChunkGlobal)) : (ring + off);
+          double acc = 0.0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int k = u * 32 + lane;
+            if (k < n) {
+              const uint2 pr = src[k];
+              acc += filt(filt((double)__uint_as_float(pr.y)) * __ldcg(&Wt[pr.x]));
+            }
+          }
+          acc = warp_sum(acc);
+          if (lane == 0) mt.part[c] = acc;
+        }
+        named_bar_sync(2, kCons * 32);
+        unsigned hinge = 0;
+        for (int c = warp; c < n_ch; c += kCons) {
+          const int row = mt.ch_row[c];
+          const int first = mt.row_first[row], nch = mt.row_nch[row];
+          double dot = 0.0;
+          for (int i = 0; i < nch; ++i) dot += mt.part[first + i];
+          const int yi = mt.row_y[row];
+          const double y = (double)yi;
+          if (c == first && lane == 0) hinge += (unsigned)(1 - yi * ((dot > 0.0) ? -1 : ((dot < 0.0) ? 1 : 0)));
+          if (!(y * dot < 0.0)) {
+            const uint32_t off = mt.ch_off[c];
+            const int n = mt.ch_n[c];
+            const uint2 *src = (off & kChunkGlobal) ? (p.pairs + (off & ~kChunkGlobal)) : (ring + off);
+            for (int k = lane; k < n; k += 32) {
+              const uint2 pr = src[k];
+              const double gvv = filt(filt((double)__uint_as_float(pr.y)) * y);
+              if (gvv != 0.0) atomicAdd(&Gme[pr.x], gvv);
+            }
+          }
+        }
+        for (int m = warp; m < mt.n_rows; m += kCons) {
+          const int nch = mt.row_nch[m];
+          if (nch == 0) {
+            if (lane == 0) hinge += 1u;
+          } else if (nch < 0) {  // row outside the chunk list: whole row from global memory
+            const uint2 *grow = p.pairs + (size_t)mt.row_b[m] * 2;
+            const int len = mt.row_len[m];
+            double acc = 0.0;
+            for (int k = lane; k < len; k += 32) {
+              const uint2 pr = __ldg(&grow[k]);
+              acc += filt(filt((double)__uint_as_float(pr.y)) * __ldcg(&Wt[pr.x]));
+            }
+            const double dot = warp_sum(acc);
+            const int yi = mt.row_y[m];
+            const double y = (double)yi;
+            if (lane == 0) hinge += (unsigned)(1 - yi * ((dot > 0.0) ? -1 : ((dot < 0.0) ? 1 : 0)));
+            if (!(y * dot < 0.0))
+              for (int k = lane; k < len; k += 32) {
+                const uint2 pr = __ldg(&grow[k]);
+                const double gvv = filt(filt((double)__uint_as_float(pr.y)) * y);
+                if (gvv != 0.0) atomicAdd(&Gme[pr.x], gvv);
+              }
+          }
+        }
+        if (lane == 0 && hinge) atomicAdd(&sm.hinge_acc, hinge);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[st]);
+        if (warp == 0) DSGD_TL(2);
+      }
+      // ---- grid barrier 1: this rank's g_T is complete (the CTA's hinge total and batch ride in slots dim, dim+1) ----
+      named_bar_sync(3, kSyncThreads);
+      if (threadIdx.x == 0) {
+        const unsigned h = sm.hinge_acc;
+        if (h) { atomicAdd(&Gme[p.dim], (double)h); sm.hinge_acc = 0u; }
+        if (blockIdx.x == 0) atomicAdd(&Gme[p.dim], (double)B * 4294967296.0);
+      }
+      ++phase;
+      if (!grid_barrier(p.bar, phase * (unsigned)G, p.abort_flag, p.timeout_cycles, &sm.ok, kSyncThreads)) return;
+      if (warp == 0) DSGD_TL(3);
+      // ---- push: my slice of g_T (and the packed counter slot) into every peer's receive area as LL words ----
+      const unsigned tag = (unsigned)(T + 1);
+      for (int j = j_lo + threadIdx.x; j < j_hi; j += kSyncThreads) {
+        const double v = __ldcg(&Gme[j]);
+        for (int k = 0; k < K; ++k)
+          if (k != me)
+            ll_store(reinterpret_cast<unsigned long long *>(p.xrecv[k]) + 2 * ((size_t)me * snd_stride + (size_t)par * par_stride + j), v, tag);
+      }
+      if (warp == 0) DSGD_TL(4);
+      // ---- [B]: every thread waits for ITS elements from every peer (tag == step), reduces in rank order, updates ----
+      const bool add_c = (c_cur != 0.0) && (fabs(c_cur) > kEps);
+      const unsigned long long *rcv = reinterpret_cast<const unsigned long long *>(p.xrecv[me]) + 2 * (size_t)par * par_stride;
+      double pd = 0.0, pn = 0.0;
+      bool ok = true;
+      const long long t0 = clock64();
+      for (int j = j_lo + threadIdx.x; j < j_hi; j += kSyncThreads) {
+        double s = 0.0;
+        for (int k = 0; k < K; ++k) {
+          double raw;
+          if (k == me) {
+            raw = __ldcg(&Gme[j]);
+          } else {
+            unsigned spins = 0;
+            while (!ll_try_load(rcv + 2 * ((size_t)k * snd_stride + j), tag, raw)) {
+              if ((++spins & 255u) == 0u && (clock64() - t0 > p.timeout_cycles || *(volatile int *)p.abort_flag)) {
+                *(volatile int *)p.abort_flag = 1;
+                ok = false;
+                raw = 0.0;
+                break;
+              }
+            }
+          }
+          if (j == p.dim) {                                   // packed counters: plain sum
+            s += raw;
+          } else {
+            double v = filt(raw);
+            if (v != 0.0 && add_c) v = filt(v + c_cur);       // regularize on this worker's own support
+            s = (k == 0) ? v : filt(s + v);                     // Vec.sum: left fold over the replies
+          }
+        }
+        if (j == p.dim) {
+          if (p.losses) {  // loss of step T on W_T: lambda*||W_T||^2 + (all ranks' hinge) / (all ranks' samples)
+            const double ns = floor(s / 4294967296.0);
+            p.losses[t] = p.lambda * nrm_cur + (s - ns * 4294967296.0) / ns;
+          }
+        } else {
+          double wn = __ldcg(&Wt[j]);
+          if (s != 0.0) {
+            const double mean = filt(s / kd);
+            const double step = filt(mean * lr);
+            wn = filt(wn - step);
+          }
+          Wn[j] = wn;
+          pd += filt(wn * __ldg(&p.d[j]));
+          pn += wn * wn;
+        }
+        Gzero[j] = 0.0;
+      }
+      if (warp == 0) DSGD_TL(5);
+      if (!ok) *(volatile int *)&sm.ok = 0;
+      if (warp == 0) DSGD_TL(8);
+      // per-CTA partials of c_{T+1} and ||W_{T+1}||^2 in a fixed order: warp -> shared -> thread 0
+      pd = warp_sum(pd);
+      pn = warp_sum(pn);
+      __shared__ double red_all[kCons + kUpd][2];
+      if (lane == 0) { red_all[warp][0] = pd; red_all[warp][1] = pn; }
+      named_bar_sync(3, kSyncThreads);
+      if (*(volatile int *)&sm.ok == 0) return;
+      if (threadIdx.x == 0) {
+        double sd = 0.0, sn = 0.0;
+#pragma unroll
+        for (int i = 0; i < kCons + kUpd; ++i) { sd += red_all[i][0]; sn += red_all[i][1]; }
+        part_cur[2 * blockIdx.x] = sd;
+        part_cur[2 * blockIdx.x + 1] = sn;
+      }
+      // ---- grid barrier 2: W_{T+1} and its partials are complete ----
+      if (warp == 0) DSGD_TL(9);
+      ++phase;
+      if (!grid_barrier(p.bar, phase * (unsigned)G, p.abort_flag, p.timeout_cycles, &sm.ok, kSyncThreads)) return;
+      if (warp == 0) DSGD_TL(10);
+      if (warp == 0) {
+        double sd, sn;
+        sum_partials2(part_cur, G, lane, sd, sn);
+        if (lane == 0) { sm.c_val[0] = p.lambda * 2.0 * sd; sm.c_val[1] = sn; }
+      }
+      named_bar_sync(3, kSyncThreads);
+      c_cur = sm.c_val[0];
+      nrm_cur = sm.c_val[1];
+    }
+    // epilogue: publish W_{base+S} as the resident weights
+    const double *Wfin = p.wbuf[(p.step_base + S) & 1];
+    for (int j = a0; j < p.dim; j += n_all) {
+      const double wv = __ldcg(&Wfin[j]);
+      p.w_out[j] = wv;
+      p.w32_out[j] = (float)wv;
+    }
+    if (a0 == 0) { p.scal[kScalC] = c_cur; p.scal[kScalNrm2] = nrm_cur; }
     return;
   }
 

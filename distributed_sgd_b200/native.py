@@ -97,6 +97,9 @@ ABI = {
     "dsgd_eval_counts": [_vp, _vp, _i64, _i64, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_f64)],
     "dsgd_comm_unique_id": [_vp],
     "dsgd_comm_init": [_vp, _vp],
+    "dsgd_xchg_export": [_vp, _vp],
+    "dsgd_xchg_import": [_vp, C.c_int, _vp],
+    "dsgd_xchg_attach": [_vp, C.c_int, _vp],
     "dsgd_set_workers": [_vp, _i32, _vp, _i32],
     "dsgd_sync_step": [_vp, _vp, _i64, _f64, C.POINTER(_f64)],
     "dsgd_sync_steps": [_vp, _vp, _i64, _i64, _f64, _vp],
@@ -317,6 +320,27 @@ class NativeCtx:
         buf = (C.c_uint8 * UNIQUE_ID_BYTES).from_buffer_copy(uid)
         self._ck(self._l.dsgd_comm_init(self._h, C.cast(buf, C.c_void_p)))
 
+    def xchg_export(self) -> bytes:
+        buf = (C.c_uint8 * IPC_HANDLE_BYTES)()
+        self._ck(self._l.dsgd_xchg_export(self._h, C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def xchg_import(self, peer_rank: int, handle: bytes):
+        buf = (C.c_uint8 * IPC_HANDLE_BYTES).from_buffer_copy(handle)
+        self._ck(self._l.dsgd_xchg_import(self._h, peer_rank, C.cast(buf, C.c_void_p)))
+
+    def xchg_attach(self, peer_rank: int, peer: "NativeCtx"):
+        self._ck(self._l.dsgd_xchg_attach(self._h, peer_rank, peer._h))
+
+    def setup_peer_exchange(self, group) -> None:
+        """One process per GPU: swap exchange-block handles through the process group and map every peer's block
+        (the fused multi-GPU sync step then needs no NCCL)."""
+        handles = group.all_gather_bytes(self.xchg_export())
+        for r, h in enumerate(handles):
+            if r != self.rank:
+                self.xchg_import(r, h)
+        group.barrier()
+
     def sync_step(self, samples, lr: float, want_loss: bool = True):
         samples = _arr(samples, np.int32)
         loss = C.c_double()
@@ -378,7 +402,7 @@ class NativeCtx:
         self._ck(self._l.dsgd_ipc_import(self._h, peer_rank, C.cast(buf, C.c_void_p)))
 
     def start_async(self, w0, assigned, batch: int, lr: float, concurrency: int = 1, max_updates: int = 0, seed: int = 0):
-        w0 = _arr(w0, np.float64, self.dim, "weights")
+        w0 = None if w0 is None else _arr(w0, np.float64, self.dim, "weights")
         assigned = _arr(assigned, np.int32)
         self._ck(self._l.dsgd_start_async(self._h, _ptr(w0), _ptr(assigned), assigned.size, batch, lr, concurrency,
                                           max_updates, seed))

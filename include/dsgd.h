@@ -119,6 +119,15 @@ int dsgd_eval_counts(dsgd_ctx *ctx, const double *w, int64_t row_begin, int64_t 
 int dsgd_comm_unique_id(uint8_t id[DSGD_UNIQUE_ID_BYTES]);
 int dsgd_comm_init(dsgd_ctx *ctx, const uint8_t id[DSGD_UNIQUE_ID_BYTES]);
 
+/* Peer exchange for the FUSED multi-GPU step: each rank exports its exchange block (three gradient buffers and
+ * flag words), the host transports the handles, every rank imports every other rank's.  Once all world-1 peers
+ * are attached, sync steps with one worker per GPU run as one persistent kernel per call that sums the workers'
+ * replies directly out of peer memory over NVLink (no NCCL call, no launch per step); otherwise the NCCL
+ * allreduce path is used.  dsgd_xchg_attach is the same-process form. */
+int dsgd_xchg_export(dsgd_ctx *ctx, uint8_t handle[DSGD_IPC_HANDLE_BYTES]);
+int dsgd_xchg_import(dsgd_ctx *ctx, int peer_rank, const uint8_t handle[DSGD_IPC_HANDLE_BYTES]);
+int dsgd_xchg_attach(dsgd_ctx *ctx, int peer_rank, dsgd_ctx *peer);
+
 /* ---- logical workers of a sync step.  Default: this ctx is ONE worker (its whole slice is one
  *      GradientRequest) and the master averages over `world` results.  With n_local > 1 the slice of every
  *      following step is cut into n_local consecutive requests of counts[v] samples, each with its own batch
@@ -164,6 +173,8 @@ int dsgd_peer_attach(dsgd_ctx *ctx, int peer_rank, dsgd_ctx *peer, int which);
  * updates (0: unbounded).  concurrency = Hogwild lanes on this GPU (warps running the loop body concurrently on
  * the shared replica; 1 = the reference's strictly sequential loop).  seed drives the device-side sampling of
  * `assigned` (core/Slave.scala:84,87; batch > 1 indexes rows by POSITION like the reference, quirk Q6).
+ * w0 == NULL keeps the resident replica: initialise every replica with dsgd_set_weights first, then start the
+ * loops, and no delta a faster peer pushes early is overwritten (the reference has that start-up race).
  * Returns immediately; the loop runs on its own stream. */
 int dsgd_start_async(dsgd_ctx *ctx, const double *w0, const int32_t *assigned, int64_t n_assigned, int32_t batch,
                      double lr, int32_t concurrency, int64_t max_updates, uint64_t seed);

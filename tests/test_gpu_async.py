@@ -125,8 +125,11 @@ def test_async_two_gpus_peer_writes(synth):
     a.peer_attach(1, b, REPLICA_SELF)
     b.peer_attach(0, a, REPLICA_SELF)
     b.peer_attach(2, a, REPLICA_MASTER)
-    a.start_async(w0, np.arange(0, 2000, dtype=np.int32), batch=1, lr=0.1, concurrency=8, max_updates=2000, seed=1)
-    b.start_async(w0, np.arange(2000, 4000, dtype=np.int32), batch=1, lr=0.1, concurrency=8, max_updates=2000, seed=2)
+    # initialise every replica first, then start the loops with w0 = None: a delta pushed by the faster worker
+    # before the slower one starts must not be overwritten
+    a.set_weights(w0); b.set_weights(w0)
+    a.start_async(None, np.arange(0, 2000, dtype=np.int32), batch=1, lr=0.1, concurrency=8, max_updates=2000, seed=1)
+    b.start_async(None, np.arange(2000, 4000, dtype=np.int32), batch=1, lr=0.1, concurrency=8, max_updates=2000, seed=2)
     t0 = time.time()
     while (a.async_running() or b.async_running()) and time.time() - t0 < 60:
         time.sleep(0.01)

@@ -18,7 +18,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, mode):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -28,16 +28,21 @@ def _worker(rank, world, port, q):
     from distributed_sgd_b200.utils import synthetic_rcv1
     from oracle.oracle import Oracle
 
+    if mode == "nccl":
+        os.environ["DSGD_NO_P2P"] = "1"
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     group = Group()
     data = synthetic_rcv1(n_rows=6000, seed=3)
-    n_train, lam, lr, batch, steps, V = 4800, 0.01, 0.5, 48, 20, 2
+    n_train, lam, lr, batch, steps = 4800, 0.01, 0.5, 48, 20
+    V = 2 if mode == "nccl" else 1      # the fused peer-memory kernel runs one worker per GPU
     ctx = NativeCtx(rank, data.dim, lam, rank=rank, world=world)
     ctx.load_csr(data.row_ptr, data.col, data.val, data.label)
     d = ctx.compute_dim_sparsity(n_train)
     uid = NativeCtx.comm_unique_id() if rank == 0 else b""
     ctx.comm_init(group.broadcast_bytes(uid, 0))
+    if mode == "p2p":
+        ctx.setup_peer_exchange(group)
     rng = np.random.default_rng(5)                       # same stream on every rank, like Random.setSeed(0)
     K = world * V                                         # V logical workers per GPU
     per = n_train // K
@@ -47,6 +52,13 @@ def _worker(rank, world, port, q):
     ctx.set_weights(np.zeros(data.dim))
     ctx.set_workers([batch] * V, K)
     losses = ctx.sync_steps(mine.reshape(-1), V * batch, steps, lr)
+    if mode == "p2p":   # a second call continues from the first one's state (global step counter, buffers)
+        half = steps // 2
+        ctx.set_weights(np.zeros(data.dim))
+        l1 = ctx.sync_steps(mine[:half].reshape(-1), V * batch, half, lr)
+        l2 = ctx.sync_steps(mine[half:].reshape(-1), V * batch, steps - half, lr)
+        assert np.array_equal(np.concatenate([l1, l2]), losses), "split run differs"
+        launches = ctx.launch_count()
     w = ctx.get_weights()
     orc = Oracle(data.row_ptr, data.col, data.val, data.label, data.dim, lam)
     orc.set_dim_sparsity(d)
@@ -55,12 +67,15 @@ def _worker(rank, world, port, q):
     # replicas must be bit-identical across GPUs
     blobs = group.all_gather_bytes(w.tobytes())
     same = all(b == blobs[0] for b in blobs)
+    if mode == "p2p":
+        ok = ok and bool(np.array_equal(ctx.get_weights(), w))
     q.put((rank, ok, same, float(np.abs(w - w_ref).max())))
     ctx.close()
     dist.destroy_process_group()
 
 
-def test_two_gpu_sync_matches_oracle():
+@pytest.mark.parametrize("mode", ["nccl", "p2p"])
+def test_two_gpu_sync_matches_oracle(mode):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -68,7 +83,7 @@ def test_two_gpu_sync_matches_oracle():
     ctxmp = mp.get_context("spawn")
     q = ctxmp.Queue()
     port = _free_port()
-    procs = [ctxmp.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctxmp.Process(target=_worker, args=(r, 2, port, q, mode)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
