@@ -200,7 +200,88 @@ class MasterSync(Master):
 
 
 class MasterAsync(Master):
-    """core/MasterAsync.scala -- filled in with the async device path."""
+    """core/MasterAsync.scala -- Hogwild: every worker runs its loop on its GPU and pushes deltas into every peer
+    replica and into the master replica (hosted on rank 0's GPU) over NVLink; the master logic polls the update
+    counter, evaluates the master replica on the test rows every `check_every` updates with a leaky average, keeps
+    the best weights, and stops on `n_train * max_epoch` updates or the early-stopping rule."""
 
-    def fit(self, *a, **kw) -> GradState:
-        raise NotImplementedError("async fit is not built yet")
+    def _attach_replicas(self):
+        from ..native import REPLICA_MASTER, REPLICA_SELF
+        W, r = self.group.world, self.group.rank
+        mine = self.ctx.ipc_export(REPLICA_SELF)
+        master = self.ctx.ipc_export(REPLICA_MASTER) if r == 0 else b""
+        handles = self.group.all_gather_bytes(mine)
+        master = self.group.broadcast_bytes(master, 0)
+        for k, h in enumerate(handles):
+            if k != r:
+                self.ctx.ipc_import(k, h)
+        if r != 0:
+            self.ctx.ipc_import(W, master)
+        self.group.barrier()
+
+    def fit(self, initial_weights: np.ndarray, max_epoch: int, batch_size: int, learning_rate: float,
+            stopping_criterion: EarlyStopping, split_strategy: Split = SplitStrategy.vanilla, check_every: int = 100,
+            leak_loss_coef: float = 0.9, *, concurrency: int = 1, poll_seconds: float = 0.05, seed: int = 0,
+            on_check: Optional[Callable[[int, dict], None]] = None) -> GradState:
+        """MasterAsync.fit (core/MasterAsync.scala:32-62) + startLossChecking (96-162) + updateGrad's stop rule
+        (164-177) + endComputation (87-94).  concurrency (extension): Hogwild lanes per GPU."""
+        import time
+        if not (0 <= leak_loss_coef <= 1):
+            raise ValueError("leaking coefficient must be between 0 and 1")      # MasterAsync.scala:97
+        if getattr(self, "_running", False):
+            raise RuntimeError("Cannot start async computation: a computation is already running")
+        W, r = self.group.world, self.group.rank
+        w0 = np.asarray(initial_weights, dtype=np.float64)
+        groups = split_strategy(self.n_train, W)
+        max_steps = self.n_train * max_epoch                                      # MasterAsync.scala:83
+        self.ctx.set_weights(w0)                     # every replica first, then the loops (no start-up race)
+        if r == 0:
+            self.ctx.async_host_master(w0)
+        if W > 1:
+            self._attach_replicas()
+        self._running = True
+        mine = groups[r] if r < len(groups) else range(0)
+        if len(mine):
+            self.slave.start_async(None, np.fromiter(mine, dtype=np.int32, count=len(mine)), batch_size, learning_rate,
+                                   concurrency=concurrency, max_updates=0, seed=seed + 1000 * r)
+        state = GradState.start_state(w0)
+        test_losses: List[float] = []
+        test_accs: List[float] = []
+        best_loss, best_w = float("inf"), None
+        last_step = -check_every                                                  # MasterAsync.scala:161
+        self.history = {"test_losses": test_losses, "test_accs": test_accs, "checks_at": []}
+        try:
+            while True:
+                updates = self.ctx.async_updates() if r == 0 else 0
+                updates = int(self.group.all_reduce_max(float(updates)))
+                if updates >= max_steps:                                          # MasterAsync.scala:171-174
+                    self.log("max number of steps reached: stopping computation")
+                    break
+                if updates - last_step < check_every:                             # latest computation was too close
+                    time.sleep(poll_seconds)                                      # (the reference waits 2.5 s)
+                    continue
+                w = self.ctx.async_master_weights()                               # innerGradState.grad
+                loss, acc = self.local_loss_accuracy(w, test_data=True)           # MasterAsync.scala:118-120
+                loss_s = leak_loss_coef * loss + (1 - leak_loss_coef) * (test_losses[0] if test_losses else loss)
+                acc_s = leak_loss_coef * acc + (1 - leak_loss_coef) * (test_accs[0] if test_accs else acc)
+                if best_loss > loss_s:                                            # MasterAsync.scala:130-139
+                    best_loss, best_w = loss_s, w
+                test_losses.insert(0, loss_s)
+                test_accs.insert(0, acc_s)
+                self.history["checks_at"].append(updates)
+                if on_check:
+                    on_check(updates, {"test_loss": loss_s, "test_acc": acc_s})
+                if stopping_criterion(test_losses):                               # MasterAsync.scala:146-152
+                    self.log("converged to target: stopping computation")
+                    break
+                last_step = updates
+        finally:
+            if len(mine):
+                self.slave.stop_async()                                           # endComputation: stopAsync to all
+            self._running = False
+            self.group.barrier()
+        if best_w is None:
+            # the reference would hand back its initial bestGrad (Vec.zeros(1)) here; we return what the master holds
+            best_w = self.ctx.async_master_weights()
+            best_loss = self.local_loss_accuracy(best_w, test_data=True)[0]
+        return state.replace_grad(best_w).finish(best_loss)                       # MasterAsync.scala:91

@@ -139,3 +139,24 @@ def test_async_two_gpus_peer_writes(synth):
     assert np.abs(wa - wm).max() < 1e-12 and np.abs(wb - wm).max() < 1e-12
     assert a.eval(4000, 5000, wm)[1] > 0.5
     a.close(); b.close()
+
+
+def test_master_async_fit_single_gpu(synth):
+    """MasterAsync.fit end to end on one GPU: device loop + polling master logic + leaky loss + stop rule."""
+    from distributed_sgd_b200 import MasterAsync, Slave, SparseSVM
+    from distributed_sgd_b200.ml import EarlyStopping
+    train, test = synth.split_at(4000)
+    model = SparseSVM(1e-5)
+    slave = Slave(0, 0, train, model, is_async=True, world=1, device=0, test_data=test)
+    master = MasterAsync(0, train, test, model, 1, slave=slave)
+    checks = []
+    state = master.fit(np.zeros(synth.dim), max_epoch=1, batch_size=1, learning_rate=0.1,
+                       stopping_criterion=EarlyStopping.no_improvement(patience=5, min_delta=0.01),
+                       check_every=500, leak_loss_coef=0.9, concurrency=8, poll_seconds=0.005,
+                       on_check=lambda u, m: checks.append((u, m["test_loss"])))
+    assert state.loss is not None and state.end is not None and state.updates == 1
+    assert len(checks) >= 2 and all(b[0] - a[0] >= 500 for a, b in zip(checks, checks[1:]))
+    assert state.loss == min(l for _, l in checks)                          # best smoothed loss is returned
+    assert master.local_loss_accuracy(state.grad, test_data=True)[1] > 0.55
+    assert not slave.ctx.async_running()
+    slave.stop()

@@ -260,3 +260,46 @@ def test_streaming_exact_fallback_decides_like_fp64():
     assert (loss, acc) == (loss_ref, acc_ref)
     np.testing.assert_array_equal(ctx.gradient(idx, w), orc.gradient(w, idx)[0])   # exact sums of 0.25/0.5/0.75/1.0
     ctx.close()
+
+
+@pytest.mark.parametrize("virtual_workers", [1, 3])
+def test_master_sync_fit_epochs_match_oracle(synth, virtual_workers):
+    """Master.fit through the Python mirror (Slave + MasterSync over the C ABI): per-epoch train/test loss and
+    accuracy lists and the final weights against the oracle driven with the same batch draws
+    (core/Master.scala:140-213)."""
+    from distributed_sgd_b200 import MasterSync, Slave, SparseSVM
+    from distributed_sgd_b200.ml import EarlyStopping
+    from oracle.oracle import Oracle
+    lam, lr, batch, epochs = 1e-3, 0.5, 100, 3
+    train, test = synth.split_at(4800)
+    train, _ = train.split_at(1200)                                        # keep the epoch short: 12 or 4 steps
+    model = SparseSVM(lam)
+    slave = Slave(0, 0, train, model, world=1, device=0, test_data=test)
+    master = MasterSync(0, train, test, model, 1, slave=slave, seed=0)
+    drawn = []
+    orig = master.draw_epoch
+    master.draw_epoch = lambda groups, bs, *a: drawn.append(orig(groups, bs, *a)) or drawn[-1]
+    state = master.fit(np.zeros(synth.dim), max_epochs=epochs, batch_size=batch, learning_rate=lr,
+                       stopping_criterion=EarlyStopping.no_improvement(patience=5, min_delta=0.01),
+                       virtual_workers=virtual_workers)
+    assert state.updates == epochs and len(drawn) == epochs
+    # the oracle over the same rows (train rows followed by test rows, as the Slave lays them out)
+    rp = np.concatenate([train.row_ptr, test.row_ptr[1:] + train.row_ptr[-1]])
+    orc = Oracle(rp, np.concatenate([train.col[:train.nnz], test.col[:test.nnz]]),
+                 np.concatenate([train.val[:train.nnz], test.val[:test.nnz]]),
+                 np.concatenate([train.label, test.label]), synth.dim, lam)
+    orc.set_dim_sparsity(orc.dim_sparsity(train.n_rows))
+    np.testing.assert_array_equal(model.dim_sparsity, orc.d)
+    w = np.zeros(synth.dim)
+    losses, accs, tlosses, taccs = [], [], [], []
+    for ep in drawn:
+        for step in ep:
+            w, _ = orc.sync_steps(w, np.concatenate(step), [len(b) for b in step], lr, n_steps=1)
+        l, a = orc.loss_acc(w, begin=0, n=train.n_rows); losses.append(l); accs.append(a)
+        l, a = orc.loss_acc(w, begin=train.n_rows, n=test.n_rows); tlosses.append(l); taccs.append(a)
+    np.testing.assert_allclose(master.history["losses"], losses, rtol=RTOL)
+    np.testing.assert_allclose(master.history["test_losses"], tlosses, rtol=RTOL)
+    assert master.history["accs"] == accs and master.history["test_accs"] == taccs
+    np.testing.assert_allclose(state.grad, w, rtol=1e-11, atol=1e-15)
+    assert state.loss == pytest.approx(losses[-1], rel=RTOL)
+    slave.stop()

@@ -1,0 +1,81 @@
+"""Host-side mirror of the reference's control logic (no GPU): config contract, split, early stopping, data."""
+import os
+
+import numpy as np
+import pytest
+
+from distributed_sgd_b200.ml import EarlyStopping, GradState, SplitStrategy
+from distributed_sgd_b200.utils import load_config, rcv1, synthetic_rcv1, write_rcv1
+from oracle import scala_semantics as S
+
+
+def test_config_defaults_match_application_conf():          # resources/application.conf:15-50
+    c = load_config(env={})
+    assert (c.batch_size, c.learning_rate, c.lam, c.node_count, c.max_epochs) == (100, 0.5, 1e-5, 3, 10)
+    assert (c.check_every, c.leaky_loss, c.patience, c.conv_delta, c.is_async, c.full) == (100, 0.9, 5, 0.01, False, False)
+    assert c.port == 4000 and c.host == "127.0.0.1" and c.master_host is None
+
+
+def test_config_env_overrides_and_file(tmp_path):
+    c = load_config(env={"DSGD_BATCH_SIZE": "256", "DSGD_ASYNC": "true", "DSGD_LAMBDA": "0.001", "DSGD_NODE_COUNT": "8"})
+    assert (c.batch_size, c.is_async, c.lam, c.node_count) == (256, True, 0.001, 8)
+    conf = tmp_path / "application.conf"
+    conf.write_text('dsgd {\n  batch-size = 100\n  batch-size = ${?DSGD_BATCH_SIZE}\n  lambda = 0.00001\n'
+                    '  async = false\n  async = ${?DSGD_ASYNC}\n  # comment\n  host = "10.0.0.1"\n}\nkamon { metric { } }\n')
+    c = load_config(str(conf), env={"DSGD_ASYNC": "yes"})
+    assert (c.batch_size, c.is_async, c.host) == (100, True, "10.0.0.1")
+    conf.write_text("dsgd {\n  bogus-key = 1\n}\n")
+    with pytest.raises(KeyError):
+        load_config(str(conf), env={})
+
+
+def test_vanilla_split_is_the_references():                  # core/ml/SplitStrategy.scala:13-14
+    for n, k in ((10, 4), (9, 4), (6, 2), (560000, 8), (101, 4), (5, 8)):
+        assert [list(r) for r in SplitStrategy.vanilla(n, k)] == S.split_vanilla(n, k)
+
+
+def test_early_stopping_mirrors_the_literal_restatement():   # core/ml/EarlyStopping.scala:13-46
+    rng = np.random.default_rng(0)
+    for patience, delta, min_steps in ((5, 0.01, None), (2, 0.0, None), (3, 0.1, 4), (1, 0.001, 10)):
+        a = EarlyStopping.no_improvement(patience, delta, min_steps)
+        b = S.early_stopping_no_improvement(patience, delta, min_steps)
+        for _ in range(200):
+            losses = rng.choice([0.5, 0.505, 0.6, 0.9, 0.3], size=int(rng.integers(0, 9))).tolist()
+            assert a(losses) == b(losses), (patience, delta, min_steps, losses)
+    assert EarlyStopping.target(0.3)([0.2, 0.9]) and not EarlyStopping.target(0.3)([0.4]) and not EarlyStopping.target(0.3)([])
+
+
+def test_grad_state():                                       # core/ml/GradState.scala:6-23
+    g = GradState.start_state(np.zeros(3))
+    g2 = g.replace_grad(np.ones(3)).finish(0.25)
+    assert g2.updates == 1 and g2.loss == 0.25 and g2.end is not None and g.end is None
+
+
+def test_synthetic_generator_is_deterministic_and_rcv1_shaped():
+    a, b = synthetic_rcv1(n_rows=3000, seed=4), synthetic_rcv1(n_rows=3000, seed=4)
+    assert np.array_equal(a.col, b.col) and np.array_equal(a.val, b.val) and np.array_equal(a.label, b.label)
+    c = synthetic_rcv1(n_rows=3000, seed=5)
+    assert not np.array_equal(a.col[:100], c.col[:100])
+    lens = np.diff(a.row_ptr)
+    assert a.dim == 47236 and lens.min() >= 1 and lens.max() <= 2000 and 70 < lens.mean() < 120
+    for r in range(0, 3000, 97):                              # sorted unique columns, L2-normalised positive rows
+        cols, vals = a.col[a.row_ptr[r]:a.row_ptr[r + 1]], a.val[a.row_ptr[r]:a.row_ptr[r + 1]]
+        assert np.all(np.diff(cols) > 0) and np.all(vals > 0) and abs(float(np.sum(vals.astype(np.float64) ** 2)) - 1) < 1e-5
+    assert 0.35 < (a.label > 0).mean() < 0.65 and set(np.unique(a.label)) == {-1, 1}
+    assert a.algorithmic_bytes() == 8 * a.nnz + 16 * a.n_rows
+    head, tail = a.split_at(2400)                             # Main.scala:52
+    assert head.n_rows == 2400 and tail.n_rows == 600 and head.nnz + tail.nnz == a.nnz and tail.row_ptr[0] == 0
+
+
+def test_rcv1_text_round_trip(tmp_path):                      # utils/Dataset.scala:19-45 (incl. label rule)
+    d = synthetic_rcv1(n_rows=300, seed=2)
+    write_rcv1(d, str(tmp_path), first_id=2286)
+    line = open(tmp_path / "lyrl2004_vectors_train.dat").readline()
+    assert line.startswith("2286  ") and ":" in line          # "<id>  <k>:<v> ..." (two separators: parts.drop(2))
+    back = rcv1(str(tmp_path), full=False)
+    assert back.n_rows == 300 and np.array_equal(back.col, d.col) and np.array_equal(back.val, d.val)
+    assert np.array_equal(back.label, d.label) and np.array_equal(back.row_ptr, d.row_ptr)
+    with open(tmp_path / "rcv1-v2.topics.qrels", "a") as f:   # the LAST line of a document decides (quirk Q10)
+        f.write("CCAT 2286 1\nGCAT 2287 1\n")
+    back = rcv1(str(tmp_path), full=False)
+    assert back.label[0] == 1 and back.label[1] == -1
