@@ -53,7 +53,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="samples per GPU per SGD step")
-    ap.add_argument("--mode", default="sync", choices=["sync"])
+    ap.add_argument("--mode", default="sync", choices=["sync", "async"])
+    ap.add_argument("--lanes", type=int, default=256, help="async: Hogwild lanes (warps) per GPU")
+    ap.add_argument("--async-updates", type=int, default=400000, help="async: updates per GPU per bench step")
     ap.add_argument("--rows", type=int, default=N_ROWS)
     ap.add_argument("--sgd-steps", type=int, default=0, help="SGD steps per bench step (0: one epoch at 1 worker)")
     ap.add_argument("--seed", type=int, default=0)
@@ -144,6 +146,94 @@ def cpu_leg(data, n_train, d, batch, workers, budget_s, threads, seed):
     return n_steps * batch * workers / dt, f"{n_steps} sync SGD steps x {workers} worker(s) x batch {batch}, {dt:.1f} s"
 
 
+def bench_async(args, ctx, data, n_train, d, group, rank, local_rank, world):
+    """BASELINE.json configs[3]: async Hogwild, one worker per GPU, lock-free peer replica writes over NVLink,
+    batch 1 by default.  A bench step = `--async-updates` worker iterations per GPU (device-side sampling)."""
+    import torch
+    from distributed_sgd_b200.native import REPLICA_MASTER, REPLICA_SELF
+    B = 1 if args.batch == 256 else args.batch        # the async configuration of BASELINE.json is batch 1
+    U = args.async_updates
+    w0 = np.zeros(data.dim)
+    per = n_train // world
+    assigned = np.arange(rank * per, (rank + 1) * per, dtype=np.int32)
+    ctx.set_weights(w0)
+    if rank == 0:
+        ctx.async_host_master(w0)
+    if world > 1:
+        handles = group.all_gather_bytes(ctx.ipc_export(REPLICA_SELF))
+        master = group.broadcast_bytes(ctx.ipc_export(REPLICA_MASTER) if rank == 0 else b"", 0)
+        for k, h in enumerate(handles):
+            if k != rank:
+                ctx.ipc_import(k, h)
+        if rank != 0:
+            ctx.ipc_import(world, master)
+    group.barrier()
+
+    def run(seed):
+        ctx.start_async(None, assigned, B, 0.1, concurrency=args.lanes, max_updates=U, seed=seed)
+        while ctx.async_running():
+            time.sleep(0.0005)
+        ctx.stop_async()
+        return ctx.async_elapsed_ms()
+
+    for i in range(args.warmup):
+        run(100 + i); group.barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = ctx.launch_count()
+    ms_dev, t0 = 0.0, time.perf_counter()
+    for i in range(args.steps):
+        ms_dev += run(200 + i)
+        group.barrier()
+    wall = time.perf_counter() - t0
+    launches = ctx.launch_count() - launches0
+    clock_info = clocks.stop() if rank == 0 else None
+    ms_dev = group.all_reduce_max(ms_dev)
+    wall = group.all_reduce_max(wall)
+    samples_total = args.steps * U * B * world
+    value = samples_total / (ms_dev * 1e-3)
+    # e2e: the public call with host buffers (assigned ids H2D, final master weights D2H), wall clock
+    e2e_value = samples_total / wall
+    w_master = ctx.async_master_weights() if rank == 0 else None
+    hbm_peak, peak_src = peaks()
+    mean_bytes = data.algorithmic_bytes() / data.n_rows
+    achieved = (args.steps * U * B * mean_bytes) / (ms_dev * 1e-3) / 1e9     # per GPU
+    cpu = None
+    if rank == 0:
+        from oracle.oracle import Oracle
+        orc = Oracle(data.row_ptr, data.col, data.val, data.label, data.dim, LAMBDA)
+        orc.set_dim_sparsity(d)
+        n_cpu = 20000
+        idx = np.random.default_rng(3).integers(0, n_train, size=n_cpu * B).astype(np.int32)
+        t = time.perf_counter(); orc.async_run(w0, idx, B, 0.1); dt = time.perf_counter() - t
+        cpu = {"value": n_cpu * B / dt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{n_cpu} sequential async iterations of batch {B} (one worker), {dt:.1f} s; the reference recomputes "
+                         "w.dimSparsity (47 236 products) every iteration (core/ml/SparseSVM.scala:31) and so does this port"}
+        loss, acc = ctx.eval(n_train, data.n_rows, w_master)
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"async Hogwild (configs[3]): RCV1-shaped synthetic, {DIM} feats, {args.rows} rows, batch {B}, "
+                                   f"one worker per GPU, {args.lanes} Hogwild lanes per GPU, peer replica writes over NVLink",
+                       "mode": "async", "batch": B, "updates_per_gpu_per_step": U, "lanes": args.lanes, "parallelism": f"dp{world}",
+                       "l2": "rows drawn at random from 0.43 GB of CSR (larger than the 126 MB L2)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(assigned.nbytes), "d2h_bytes_per_step": 0,
+                    "api": "dsgd_start_async ... dsgd_stop_async (C ABI)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_async_worker", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "note": "latency-bound by construction: each iteration is a dependent chain on one replica"},
+            "cpu_baseline": cpu, "clocks": clock_info,
+            "final_test_loss": loss, "final_test_acc": acc,
+        }))
+    ctx.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -192,14 +282,17 @@ def main():
     group = Group()
 
     data, n_train = make_data(args)
-    ctx = NativeCtx(local_rank, data.dim, LAMBDA, rank=rank, world=world)
+    ctx = NativeCtx(local_rank, data.dim, LAMBDA, rank=rank, world=world, is_async=(args.mode == "async"))
     ctx.load_csr(data.row_ptr, data.col, data.val, data.label)   # every slave holds every row (quirk Q13)
     d = ctx.compute_dim_sparsity(n_train)
-    if world > 1:
+    if world > 1 and args.mode == "sync":
         uid = NativeCtx.comm_unique_id() if rank == 0 else b""
         ctx.comm_init(group.broadcast_bytes(uid, 0))
         if not os.environ.get("DSGD_NO_P2P"):
             ctx.setup_peer_exchange(group)   # fused step: gradients summed out of peer memory over NVLink
+
+    if args.mode == "async":
+        return bench_async(args, ctx, data, n_train, d, group, rank, local_rank, world)
 
     B = args.batch
     S = args.sgd_steps or -(-n_train // B)            # one epoch of the 1-worker fit loop: ceil(560000 / 256) = 2188

@@ -89,6 +89,7 @@ struct dsgd_ctx {
   int64_t a_rows_cap = 0, a_assigned_cap = 0, a_replay_cap = 0;
   int32_t *u_idx = nullptr; double *u_val = nullptr; int64_t u_cap = 0;  // update_grad staging
   bool a_running = false;
+  cudaEvent_t a_ev0 = nullptr, a_ev1 = nullptr;
 
   // sync-mode exchange block shared with peers over NVLink: 3 gradient buffers (dim + 8 doubles each) + flag words
   double *xblk = nullptr;
@@ -266,6 +267,7 @@ extern "C" int dsgd_destroy(dsgd_ctx *ctx) {
   if (ctx->xblk) cudaFree(ctx->xblk);
   void *aptrs[] = {ctx->m_w, ctx->a_stop, ctx->a_cnt, ctx->a_scratch, ctx->a_rows, ctx->a_assigned, ctx->a_replay, ctx->u_idx, ctx->u_val};
   for (void *q : aptrs) if (q) cudaFree(q);
+  if (ctx->a_ev0) { cudaEventDestroy(ctx->a_ev0); cudaEventDestroy(ctx->a_ev1); }
   if (ctx->astream) cudaStreamDestroy(ctx->astream);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   void *ptrs[] = {ctx->rp16, ctx->pairs, ctx->label, ctx->w, ctx->g, ctx->d, ctx->w_req, ctx->w32, ctx->w32_req, ctx->n_exact, ctx->scal,
@@ -717,8 +719,9 @@ extern "C" int dsgd_comm_init(dsgd_ctx *ctx, const uint8_t id[DSGD_UNIQUE_ID_BYT
 // ---- persistent single-worker loop ------------------------------------------------------------------------
 constexpr int kPCons = 8, kPUpd = 6, kPStages = 8, kPStagePairs = 2560, kPMaxChunks = 128;
 using PSmem = PersistSmem<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks>;
-#define DSGD_PERSIST_KERNEL k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, false>
-#define DSGD_PERSIST_KERNEL_MULTI k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, true>
+#define DSGD_PERSIST_KERNEL k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 0>
+#define DSGD_PERSIST_KERNEL_MULTI2 k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 1>
+#define DSGD_PERSIST_KERNEL_MULTI k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 2>
 
 static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
   if (!ctx->p_ready) {
@@ -732,6 +735,7 @@ static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
     CU(cudaMalloc(&ctx->p_bar, sizeof(unsigned) * 4));
     CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
     CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL_MULTI, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
+    CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL_MULTI2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
     ctx->p_ready = true;
   }
   if (ctx->p_hinge_cap < n_steps) {
@@ -823,6 +827,7 @@ static int persist_run_multi(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t 
   NEED((uint64_t)G * (uint64_t)(2 * n_steps + 2) < (1ull << 32), DSGD_ERR_INVALID, "dsgd_sync_steps: too many steps for one launch");
   const size_t vd = sizeof(double) * (size_t)ctx->dim;
   CU(cudaMemcpyAsync(ctx->p_wbuf[ctx->x_step & 1], ctx->w, vd, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemsetAsync(ctx->p_hinge, 0, sizeof(unsigned) * (size_t)n_steps, ctx->stream));
   CU(cudaMemsetAsync(ctx->p_bar, 0, sizeof(unsigned) * 4, ctx->stream));
   PersistParams pp;
   memset(&pp, 0, sizeof pp);
@@ -854,8 +859,9 @@ static int persist_run_multi(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t 
   void *args[] = {&pp};
   auto *pe = prof_slot(ctx);
   if (pe) cudaEventRecord(pe->first, ctx->stream);
-  CU(cudaLaunchCooperativeKernel((void *)DSGD_PERSIST_KERNEL_MULTI, dim3(G), dim3((kPCons + kPUpd + 1) * 32), args, sizeof(PSmem),
-                                 ctx->stream));
+  static const bool two_barriers = getenv("DSGD_P2P_TWO_BARRIERS") != nullptr;
+  CU(cudaLaunchCooperativeKernel(two_barriers ? (void *)DSGD_PERSIST_KERNEL_MULTI2 : (void *)DSGD_PERSIST_KERNEL_MULTI, dim3(G),
+                                 dim3((kPCons + kPUpd + 1) * 32), args, sizeof(PSmem), ctx->stream));
   if (pe) cudaEventRecord(pe->second, ctx->stream);
   LAUNCHED();
   ctx->x_step += n_steps;
@@ -1170,7 +1176,10 @@ static int async_launch(dsgd_ctx *ctx, const double *w0, const int32_t *assigned
   ap.scratch = ctx->a_scratch; ap.batch_rows = ctx->a_rows; ap.n_lanes = lanes; ap.max_updates = max_updates; ap.seed = seed;
   ap.stop = ctx->a_stop; ap.claimed = ctx->a_cnt; ap.done = ctx->a_cnt + 1;
   CU(cudaStreamSynchronize(ctx->stream));  // inputs in place before the loop's own stream starts
+  if (!ctx->a_ev0) { CU(cudaEventCreate(&ctx->a_ev0)); CU(cudaEventCreate(&ctx->a_ev1)); }
+  CU(cudaEventRecord(ctx->a_ev0, st));
   k_async_worker<<<cdiv(lanes, 4), 128, 0, st>>>(ap);
+  CU(cudaEventRecord(ctx->a_ev1, st));
   LAUNCHED();
   CU(cudaGetLastError());
   return DSGD_OK;
@@ -1247,6 +1256,15 @@ extern "C" int dsgd_stop_async(dsgd_ctx *ctx) {
   LAUNCHED();
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(ctx->stream));
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_async_elapsed_ms(dsgd_ctx *ctx, float *elapsed_ms) {
+  if (!ctx || !elapsed_ms) return DSGD_ERR_INVALID;
+  NEED(ctx->a_ev0 && !ctx->a_running, DSGD_ERR_STATE, "dsgd_async_elapsed_ms: no finished async loop (stop it first)");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventSynchronize(ctx->a_ev1));
+  CU(cudaEventElapsedTime(elapsed_ms, ctx->a_ev0, ctx->a_ev1));
   return DSGD_OK;
 }
 

@@ -256,6 +256,7 @@ struct PersistSmem {
   uint64_t empty[kStages];
   uint64_t c_bar[2];
   double c_val[2];
+  double nrm_val[2];
   double red[kUpd][2];
   unsigned hinge_acc;
   int ok;
@@ -266,7 +267,7 @@ struct PersistSmem {
     if (p.tl && blockIdx.x == 0 && lane == 0 && t < 256) p.tl[t * 16 + (slot_)] = clock64(); \
   } while (0)
 
-template <int kCons, int kUpd, int kStages, int kStagePairs, int kMaxChunks, bool kMulti>
+template <int kCons, int kUpd, int kStages, int kStagePairs, int kMaxChunks, int kMode>
 __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(const PersistParams p) {
   using Smem = PersistSmem<kCons, kUpd, kStages, kStagePairs, kMaxChunks>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -375,9 +376,316 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
     return;
   }
 
-  if constexpr (kMulti) {
+  if constexpr (kMode == 2) {
     // =======================================================================================================
-    // world > 1: aggregate over GPUs inside the kernel, through peer memory.  Step T (global number):
+    // world > 1, ONE grid barrier per step: the cross-GPU form of the "on the fly" scheme of the single-GPU loop.
+    // Interval I_T (between grid barrier T-1 and T), W_T = weights step T differentiates at:
+    //   everybody : push this CTA's column slice of g_{T-1} to every peer's receive area as LL words (tag T)
+    //   consumers : W_T[col] = update(W_{T-1}[col], replies of all K workers for step T-1 at col) computed on the
+    //               fly -- own reply from local g_{T-1}, the peers' from the receive area (waiting on the tag if a
+    //               word has not landed yet); x.W_T; gate; RED y*x into g_T
+    //   updaters  : the same reduction over their slice -> W_T buffer; partials of c_T, ||W_T||^2; loss of step T-1;
+    //               zero the buffer g_{T+1} will use
+    // A peer can be at most one interval ahead (it needs this rank's g_T before it can finish I_{T+1}), so two
+    // receive parities suffice.  The first interval of a launch has no pending update (W_base is materialised).
+    // =======================================================================================================
+    const int K = p.world, me = p.rank;
+    const int slice = (p.dim + 1 + G - 1) / G;   // columns per CTA, plus ONE counter slot [dim] = hinge + 2^32 * samples
+    const int j_lo = min(blockIdx.x * slice, p.dim + 1), j_hi = min(j_lo + slice, p.dim + 1);
+    const int par_stride = p.xstride, snd_stride = 2 * p.xstride;
+    const double lr = p.lr, kd = (double)K;
+    const int64_t base = p.step_base;
+    unsigned phase = 0;
+
+    // reply of every worker at column j for the step whose tag is `tag` (own from Gp, peers' from the receive area),
+    // regularized on its own support and folded in rank order (core/Master.scala:194)
+    auto reduce_replies = [&](int j, const double *Gp, const unsigned long long *rcv, unsigned tag, double c, bool add_c,
+                              bool &ok) -> double {
+      double s = 0.0;
+      for (int k = 0; k < K; ++k) {
+        double raw;
+        if (k == me) {
+          raw = __ldcg(&Gp[j]);
+        } else {
+          unsigned spins = 0;
+          const long long t0 = clock64();
+          while (!ll_try_load(rcv + 2 * ((size_t)k * snd_stride + j), tag, raw)) {
+            if ((++spins & 255u) == 0u && (clock64() - t0 > p.timeout_cycles || *(volatile int *)p.abort_flag)) {
+              *(volatile int *)p.abort_flag = 1;
+              ok = false;
+              raw = 0.0;
+              break;
+            }
+          }
+        }
+        if (j == p.dim) {
+          s += raw;                                           // packed counters: plain sum
+        } else {
+          double v = filt(raw);
+          if (v != 0.0 && add_c) v = filt(v + c);
+          s = (k == 0) ? v : filt(s + v);
+        }
+      }
+      return s;
+    };
+    auto updated = [&](double wv, double s) -> double {      // w - lr * (sum / K), with the constructor filters
+      if (s != 0.0) {
+        const double mean = filt(s / kd);
+        const double step = filt(mean * lr);
+        wv = filt(wv - step);
+      }
+      return wv;
+    };
+
+    for (int64_t T = base; T <= base + S; ++T) {
+      const int64_t t = T - base;
+      const bool first = (T == base), last = (T == base + S);
+      const double *Wprev = p.wbuf[(T + 1) & 1];              // W_{T-1}
+      double *Wcur = p.wbuf[T & 1];                           // W_T (already materialised when `first`)
+      const double *Gprev = p.xg[(T + 2) % 3];                // g_{T-1}
+      double *Gcur = p.xg[T % 3];
+      double *Gzero = p.xg[(T + 1) % 3];
+      const int parp = (int)((T + 1) & 1);                    // receive parity of step T-1
+      const unsigned tag = (unsigned)T;                       // words of step T-1 carry tag T
+      const unsigned long long *rcv = reinterpret_cast<const unsigned long long *>(p.xrecv[me]) + 2 * (size_t)parp * par_stride;
+      const double *part_prev = p.partial + (size_t)((T + 1) & 1) * G * 2;   // partials of W_{T-1}
+      double *part_cur = p.partial + (size_t)(T & 1) * G * 2;
+      const unsigned c_par = (unsigned)((t >> 1) & 1);
+      bool ok = true;
+
+      // ---- push g_{T-1} (every sync warp; one column per thread) ----
+      if (!first) {
+        for (int j = j_lo + threadIdx.x; j < j_hi; j += kSyncThreads) {
+          const double v = __ldcg(&Gprev[j]);
+          for (int k = 0; k < K; ++k)
+            if (k != me)
+              ll_store(reinterpret_cast<unsigned long long *>(p.xrecv[k]) + 2 * ((size_t)me * snd_stride + (size_t)parp * par_stride + j), v, tag);
+        }
+      }
+
+      if (is_cons) {
+        if (!last) {
+          const int st = (int)(t % kStages);
+          auto &mt = sm.meta[st];
+          mbar_wait(&sm.full[st], (unsigned)((t / kStages) & 1), p.abort_flag, p.timeout_cycles);
+          const int n_ch = mt.n_chunks;
+          const uint2 *ring = &sm.ring[st][0];
+          double c_prev = 0.0;
+          bool add_c = false, have_c = false;
+          auto get_c = [&]() {
+            if (!have_c) {
+              mbar_wait(&sm.c_bar[t & 1], c_par, p.abort_flag, p.timeout_cycles);
+              c_prev = sm.c_val[t & 1];
+              add_c = (c_prev != 0.0) && (fabs(c_prev) > kEps);
+              have_c = true;
+            }
+          };
+          auto weight_at = [&](unsigned col) -> double {    // W_T[col]
+            if (first) return __ldcg(&Wcur[col]);
+            const double s = reduce_replies((int)col, Gprev, rcv, tag, c_prev, add_c, ok);
+            return updated(__ldcg(&Wprev[col]), s);
+          };
+          for (int c = warp; c < n_ch; c += kCons) {
+            const uint32_t off = mt.ch_off[c];
+            const int n = mt.ch_n[c];
+            const uint2 *src = (off & kChunkGlobal) ? (p.pairs + (off & ~kChunkGlobal)) : (ring + off);
+            // the chunk's gathers are issued in rounds so that their L2 latencies overlap: W_{T-1} and the own reply
+            // for all four pairs of a lane first, then one round of four LL loads per peer (rank order = fold order)
+            uint2 pr[4];
+            double wv[4], sacc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int k = u * 32 + lane;
+              pr[u] = (k < n) ? src[k] : make_uint2(0u, 0u);   // col 0 / val 0: inert, still a valid gather
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) wv[u] = __ldcg(&(first ? Wcur : Wprev)[pr[u].x]);
+            if (!first) {
+              get_c();
+              for (int k = 0; k < K; ++k) {
+                double raw[4];
+                if (k == me) {
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) raw[u] = __ldcg(&Gprev[pr[u].x]);
+                } else {
+                  const unsigned long long *rk = rcv + 2 * (size_t)k * snd_stride;
+                  bool got[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) got[u] = ll_try_load(rk + 2 * (size_t)pr[u].x, tag, raw[u]);
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    if (!got[u]) {
+                      unsigned spins = 0;
+                      const long long t0 = clock64();
+                      while (!ll_try_load(rk + 2 * (size_t)pr[u].x, tag, raw[u])) {
+                        if ((++spins & 255u) == 0u && (clock64() - t0 > p.timeout_cycles || *(volatile int *)p.abort_flag)) {
+                          *(volatile int *)p.abort_flag = 1;
+                          ok = false;
+                          raw[u] = 0.0;
+                          break;
+                        }
+                      }
+                    }
+                  }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  double v = filt(raw[u]);
+                  if (v != 0.0 && add_c) v = filt(v + c_prev);
+                  sacc[u] = (k == 0) ? v : filt(sacc[u] + v);
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) wv[u] = updated(wv[u], sacc[u]);
+            }
+            double acc = 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc += filt(filt((double)__uint_as_float(pr[u].y)) * wv[u]);
+            acc = warp_sum(acc);
+            if (lane == 0) mt.part[c] = acc;
+          }
+          named_bar_sync(2, kCons * 32);
+          unsigned hinge = 0;
+          for (int c = warp; c < n_ch; c += kCons) {
+            const int row = mt.ch_row[c];
+            const int firstc = mt.row_first[row], nch = mt.row_nch[row];
+            double dot = 0.0;
+            for (int i = 0; i < nch; ++i) dot += mt.part[firstc + i];
+            const int yi = mt.row_y[row];
+            const double y = (double)yi;
+            if (c == firstc && lane == 0) hinge += (unsigned)(1 - yi * ((dot > 0.0) ? -1 : ((dot < 0.0) ? 1 : 0)));
+            if (!(y * dot < 0.0)) {
+              const uint32_t off = mt.ch_off[c];
+              const int n = mt.ch_n[c];
+              const uint2 *src = (off & kChunkGlobal) ? (p.pairs + (off & ~kChunkGlobal)) : (ring + off);
+              for (int k = lane; k < n; k += 32) {
+                const uint2 pr = src[k];
+                const double gvv = filt(filt((double)__uint_as_float(pr.y)) * y);
+                if (gvv != 0.0) atomicAdd(&Gcur[pr.x], gvv);
+              }
+            }
+          }
+          for (int m = warp; m < mt.n_rows; m += kCons) {
+            const int nch = mt.row_nch[m];
+            if (nch == 0) {
+              if (lane == 0) hinge += 1u;
+            } else if (nch < 0) {  // row outside the chunk list: whole row from global memory
+              const uint2 *grow = p.pairs + (size_t)mt.row_b[m] * 2;
+              const int len = mt.row_len[m];
+              if (!first) get_c();
+              double acc = 0.0;
+              for (int k = lane; k < len; k += 32) {
+                const uint2 pr = __ldg(&grow[k]);
+                acc += filt(filt((double)__uint_as_float(pr.y)) * weight_at(pr.x));
+              }
+              const double dot = warp_sum(acc);
+              const int yi = mt.row_y[m];
+              const double y = (double)yi;
+              if (lane == 0) hinge += (unsigned)(1 - yi * ((dot > 0.0) ? -1 : ((dot < 0.0) ? 1 : 0)));
+              if (!(y * dot < 0.0))
+                for (int k = lane; k < len; k += 32) {
+                  const uint2 pr = __ldg(&grow[k]);
+                  const double gvv = filt(filt((double)__uint_as_float(pr.y)) * y);
+                  if (gvv != 0.0) atomicAdd(&Gcur[pr.x], gvv);
+                }
+            }
+          }
+          if (lane == 0 && hinge) atomicAdd(&sm.hinge_acc, hinge);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.empty[st]);
+        }
+      } else {
+        // ---- update warps ----
+        const int uw = warp - kCons;
+        double c_prev = 0.0, nrm_prev = 0.0;                  // of W_{T-1}
+        if (uw == 0) {
+          if (!first) {
+            if (T - 1 == base) {
+              c_prev = p.scal[kScalC];                        // W_base came from the host: k_prepare / previous launch
+              nrm_prev = p.scal[kScalNrm2];
+            } else {
+              double sd, sn;
+              sum_partials2(part_prev, G, lane, sd, sn);
+              c_prev = p.lambda * 2.0 * sd;
+              nrm_prev = sn;
+            }
+          }
+          if (lane == 0) {
+            sm.c_val[t & 1] = c_prev;
+            sm.nrm_val[t & 1] = nrm_prev;                     // ||W_{T-1}||^2 for the loss of step T-1
+            mbar_arrive(&sm.c_bar[t & 1]);
+          }
+          __syncwarp();
+        } else {
+          mbar_wait(&sm.c_bar[t & 1], c_par, p.abort_flag, p.timeout_cycles);
+          c_prev = sm.c_val[t & 1];
+        }
+        const bool add_c = (c_prev != 0.0) && (fabs(c_prev) > kEps);
+        double pd = 0.0, pn = 0.0;
+        const int ut = threadIdx.x - kCons * 32;              // 0 .. kUpd*32-1
+        for (int j = j_lo + ut; j < j_hi; j += kUpd * 32) {
+          if (!first) {
+            const double s = reduce_replies(j, Gprev, rcv, tag, c_prev, add_c, ok);
+            if (j == p.dim) {
+              if (p.losses) {  // loss of step T-1 on W_{T-1}
+                const double ns = floor(s / 4294967296.0);
+                p.losses[t - 1] = p.lambda * sm.nrm_val[t & 1] + (s - ns * 4294967296.0) / ns;
+              }
+            } else {
+              const double wn = updated(__ldcg(&Wprev[j]), s);
+              Wcur[j] = wn;
+              pd += filt(wn * __ldg(&p.d[j]));
+              pn += wn * wn;
+            }
+          }
+          Gzero[j] = 0.0;
+        }
+        pd = warp_sum(pd);
+        pn = warp_sum(pn);
+        if (lane == 0) { sm.red[uw][0] = pd; sm.red[uw][1] = pn; }
+        named_bar_sync(1, kUpd * 32);
+        if (uw == 0 && lane == 0 && !first) {
+          double sd = 0.0, sn = 0.0;
+#pragma unroll
+          for (int i = 0; i < kUpd; ++i) { sd += sm.red[i][0]; sn += sm.red[i][1]; }
+          part_cur[2 * blockIdx.x] = sd;
+          part_cur[2 * blockIdx.x + 1] = sn;
+        }
+      }
+      if (!ok) *(volatile int *)&sm.ok = 0;
+      // ---- grid barrier T (the CTA's hinge total and batch ride in slot [dim] of g_T) ----
+      named_bar_sync(3, kSyncThreads);
+      if (*(volatile int *)&sm.ok == 0) { *(volatile int *)p.abort_flag = 1; }
+      if (threadIdx.x == 0 && !last) {
+        const unsigned h = sm.hinge_acc;
+        if (h) { atomicAdd(&Gcur[p.dim], (double)h); sm.hinge_acc = 0u; }
+        if (blockIdx.x == 0) atomicAdd(&Gcur[p.dim], (double)B * 4294967296.0);
+      }
+      ++phase;
+      if (!grid_barrier(p.bar, phase * (unsigned)G, p.abort_flag, p.timeout_cycles, &sm.ok, kSyncThreads)) return;
+      if (*(volatile int *)p.abort_flag) return;
+    }
+    // epilogue: W_{base+S} is complete in wbuf[(base+S) & 1]; its c and norm come from the partials just written
+    {
+      const double *Wfin = p.wbuf[(base + S) & 1];
+      const int n_all = G * kSyncThreads;
+      for (int j = blockIdx.x * kSyncThreads + threadIdx.x; j < p.dim; j += n_all) {
+        const double wv = __ldcg(&Wfin[j]);
+        p.w_out[j] = wv;
+        p.w32_out[j] = (float)wv;
+      }
+      if (blockIdx.x == 0 && warp == 0 && S > 0) {
+        double sd, sn;
+        sum_partials2(p.partial + (size_t)((base + S) & 1) * G * 2, G, lane, sd, sn);
+        if (lane == 0) { p.scal[kScalC] = p.lambda * 2.0 * sd; p.scal[kScalNrm2] = sn; }
+      }
+    }
+    return;
+  }
+
+  if constexpr (kMode == 1) {
+    // =======================================================================================================
+    // world > 1, two grid barriers per step (kept for A/B; DSGD_P2P_TWO_BARRIERS=1).  Step T (global number):
     //   [A] consumers: x.W_T from the materialised W_T buffer; gate; RED y*x into this rank's g_T
     //       -- grid barrier 1 --
     //   [push] CTA b owns a contiguous slice of the columns on EVERY rank: it copies its slice of g_T into each

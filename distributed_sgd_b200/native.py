@@ -113,6 +113,7 @@ ABI = {
     "dsgd_async_replay": [_vp, _vp, _vp, _i32, _i64, _f64],
     "dsgd_async_running": [_vp, C.POINTER(C.c_int)],
     "dsgd_async_master_weights": [_vp, _vp],
+    "dsgd_async_elapsed_ms": [_vp, C.POINTER(C.c_float)],
     "dsgd_start_async": [_vp, _vp, _vp, _i64, _i32, _f64, _i32, _i64, _u64],
     "dsgd_stop_async": [_vp],
     "dsgd_update_grad": [_vp, _vp, _vp, _i64],
@@ -391,6 +392,11 @@ class NativeCtx:
         r = C.c_int()
         self._ck(self._l.dsgd_async_running(self._h, C.byref(r)))
         return bool(r.value)
+
+    def async_elapsed_ms(self) -> float:
+        ms = C.c_float()
+        self._ck(self._l.dsgd_async_elapsed_ms(self._h, C.byref(ms)))
+        return ms.value
 
     def async_master_weights(self) -> np.ndarray:
         out = np.zeros(self.dim, dtype=np.float64)

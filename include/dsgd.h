@@ -186,6 +186,8 @@ int dsgd_async_replay(dsgd_ctx *ctx, const double *w0, const int32_t *samples, i
 int dsgd_stop_async(dsgd_ctx *ctx);
 /* 1 while the device loop is running (it also ends by itself after max_updates). */
 int dsgd_async_running(dsgd_ctx *ctx, int *running);
+/* Device time of the last finished async loop (CUDA events on the loop's stream), for benchmarks. */
+int dsgd_async_elapsed_ms(dsgd_ctx *ctx, float *elapsed_ms);
 /* SlaveImpl.updateGrad / AsyncMasterGrpcImpl.updateGrad (core/Slave.scala:177-185; core/MasterAsync.scala:
  * 164-177): weights -= delta for a sparse delta given as (idx, val) pairs.  which selects the replica. */
 int dsgd_update_grad(dsgd_ctx *ctx, const int32_t *idx, const double *val, int64_t nnz);
