@@ -235,8 +235,8 @@ extern "C" int dsgd_create(dsgd_ctx **out, int device, int32_t dim, double lambd
   if ((e = cudaMalloc(&ctx->w_req, vd)) != cudaSuccess) return bail("cudaMalloc w_req", e);
   if ((e = cudaMalloc(&ctx->w32, sizeof(float) * (size_t)(dim + 4))) != cudaSuccess) return bail("cudaMalloc w32", e);
   if ((e = cudaMalloc(&ctx->w32_req, sizeof(float) * (size_t)(dim + 4))) != cudaSuccess) return bail("cudaMalloc w32_req", e);
-  if ((e = cudaMalloc(&ctx->n_exact, sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc n_exact", e);
-  cudaMemsetAsync(ctx->n_exact, 0, sizeof(unsigned long long), ctx->stream);
+  if ((e = cudaMalloc(&ctx->n_exact, sizeof(unsigned long long) * 2)) != cudaSuccess) return bail("cudaMalloc n_exact", e);
+  cudaMemsetAsync(ctx->n_exact, 0, sizeof(unsigned long long) * 2, ctx->stream);
   if ((e = cudaMalloc(&ctx->scal, sizeof(double) * kNumScal)) != cudaSuccess) return bail("cudaMalloc scal", e);
   if ((e = cudaMalloc(&ctx->cnt, sizeof(unsigned long long) * kNumCnt)) != cudaSuccess) return bail("cudaMalloc cnt", e);
   if ((e = cudaMalloc(&ctx->partial, sizeof(double) * 2 * (size_t)upd_blocks)) != cudaSuccess) return bail("cudaMalloc partial", e);
@@ -570,7 +570,8 @@ static int stream_launch(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t row_
   StreamParams sp;
   sp.rp16 = ctx->rp16; sp.units = reinterpret_cast<const uint4 *>(ctx->pairs); sp.label = ctx->label;
   sp.samples = samples_dev; sp.row_begin = row_begin; sp.n = n; sp.w = w_dev; sp.w32 = w32_dev; sp.dim = ctx->dim;
-  sp.g = g; sp.preds = preds; sp.cnt = ctx->cnt; sp.n_exact = ctx->n_exact;
+  sp.g = g; sp.preds = preds; sp.cnt = ctx->cnt; sp.n_exact = ctx->n_exact; sp.next_block = ctx->n_exact + 1;
+  CU(cudaMemsetAsync(ctx->n_exact + 1, 0, sizeof(unsigned long long), ctx->stream));
   const int64_t blocks32 = (n + 31) / 32;
   const int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, cdiv(blocks32, kStreamThreads / 32)));
   auto *pe = prof_slot(ctx);

@@ -1038,19 +1038,20 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
       // c_{t-1} = 2*lambda*(W_{t-1} . d): at t == 0 g_{-1} is all zero, so its value is irrelevant
       double c_prev = 0.0;
       if (uw == 0) {
+        double sn = 0.0;
         if (t > 0) {
-          double sd, sn;
+          double sd;
           sum_partials2(part_prev, G, lane, sd, sn);
           c_prev = p.lambda * 2.0 * sd;
-          // loss of step t-1 = lambda*||W_{t-1}||^2 + hinge_{t-1}/batch  (SparseSVM.scala:20-23)
-          if (p.losses && blockIdx.x == 0 && lane == 0)
-            p.losses[t - 1] = p.lambda * sn + (double)__ldcg(&p.hinge[t - 1]) / (double)B;
         }
-        if (lane == 0) {
+        if (lane == 0) {  // hand c over first: the consumers of this CTA are waiting for it
           sm.c_val[t & 1] = c_prev;
           mbar_arrive(&sm.c_bar[t & 1]);
         }
         DSGD_TL(9);
+        // loss of step t-1 = lambda*||W_{t-1}||^2 + hinge_{t-1}/batch  (SparseSVM.scala:20-23)
+        if (t > 0 && p.losses && blockIdx.x == 0 && lane == 0)
+          p.losses[t - 1] = p.lambda * sn + (double)__ldcg(&p.hinge[t - 1]) / (double)B;
       } else {
         mbar_wait(&sm.c_bar[t & 1], c_par, p.abort_flag, p.timeout_cycles);
         c_prev = sm.c_val[t & 1];

@@ -36,6 +36,7 @@ struct StreamParams {
   double *preds;           // per-sample predictions or nullptr
   unsigned long long *cnt; // kCntHinge / kCntCorrect
   unsigned long long *n_exact;  // how many rows took the exact fallback (diagnostic), may be nullptr
+  unsigned long long *next_block;  // work counter (zero on entry): blocks beyond the first wave are claimed dynamically
 };
 
 template <bool kScatter, bool kPreds>
@@ -91,11 +92,21 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
       y = (int)__ldg(&p.label[rid]);
     }
   };
+  // Work distribution: the first wave is static (block = warp id), later blocks are claimed from a global counter
+  // one step ahead (so the next block's bounds are prefetched while the current one is processed).  Rows are
+  // heavy-tailed (1..2000 non-zeros): dynamic claiming keeps the tail of the pass short.
+  auto claim = [&]() -> int64_t {
+    unsigned long long v = 0;
+    if (lane == 0) v = atomicAdd(p.next_block, 1ull);
+    return (int64_t)__shfl_sync(0xffffffffu, v, 0) + n_warps;
+  };
   uint32_t nb, ne; int ny; int64_t nrid;
-  load_block(warp_global, nb, ne, ny, nrid);
-  for (int64_t blk = warp_global; blk < n_blocks; blk += n_warps) {
+  int64_t blk = warp_global;
+  int64_t blk_next = (blk < n_blocks) ? claim() : n_blocks;
+  load_block(blk, nb, ne, ny, nrid);
+  for (; blk < n_blocks;) {
     const uint32_t cb = nb, ce = ne; const int cy = ny; const int64_t crid = nrid;
-    load_block(blk + n_warps, nb, ne, ny, nrid);
+    load_block(blk_next, nb, ne, ny, nrid);
     // 16 iterations: in iteration j the two halves take rows 2j and 2j+1 of the block.  A row is walked in
     // super-steps of kUnroll 128-bit loads per lane (kUnroll * 32 pairs per 16-lane group), all issued before the
     // first use: the bytes in flight per SM, not the instruction count, decide how close to the HBM roof this
@@ -120,8 +131,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
         for (int i = 0; i < kUnroll; ++i) {
           const float x0 = __uint_as_float(q[i].y), x1 = __uint_as_float(q[i].w);
           const float w0 = ws[q[i].x], w1 = ws[q[i].z];
-          acc += (double)x0 * (double)w0;
-          acc += (double)x1 * (double)w1;
+          // fp32 x fp32 products are exact in fp64 (24 + 24 significant bits), so a fused multiply-add rounds
+          // exactly like multiply-then-add: same bits as the unfused form, one instruction less
+          acc = fma((double)x0, (double)w0, acc);
+          acc = fma((double)x1, (double)w1, acc);
           asum += fabsf(x0) + fabsf(x1);
         }
       }
@@ -169,6 +182,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
         }
       }
     }
+    blk = blk_next;
+    blk_next = (blk < n_blocks) ? claim() : n_blocks;
   }
   // ---- counters: lane -> warp -> CTA -> one atomic per CTA ----
   hinge = __reduce_add_sync(0xffffffffu, hinge);

@@ -150,9 +150,9 @@ def test_master_async_fit_single_gpu(synth):
     slave = Slave(0, 0, train, model, is_async=True, world=1, device=0, test_data=test)
     master = MasterAsync(0, train, test, model, 1, slave=slave)
     checks = []
-    state = master.fit(np.zeros(synth.dim), max_epoch=1, batch_size=1, learning_rate=0.1,
+    state = master.fit(np.zeros(synth.dim), max_epoch=40, batch_size=1, learning_rate=0.1,
                        stopping_criterion=EarlyStopping.no_improvement(patience=5, min_delta=0.01),
-                       check_every=500, leak_loss_coef=0.9, concurrency=8, poll_seconds=0.005,
+                       check_every=500, leak_loss_coef=0.9, concurrency=2, poll_seconds=0.0005,
                        on_check=lambda u, m: checks.append((u, m["test_loss"])))
     assert state.loss is not None and state.end is not None and state.updates == 1
     assert len(checks) >= 2 and all(b[0] - a[0] >= 500 for a, b in zip(checks, checks[1:]))
