@@ -78,12 +78,16 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device: int):
-        self.device, self.rows, self.proc = device, [], None
+        self.device, self.rows, self.proc, self.first = device, [], None, 0
+
+    def mark(self):
+        """Samples before this call (GPU idle while nvidia-smi starts) are not used."""
+        self.first = len(self.rows)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -98,7 +102,7 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except Exception:
@@ -313,12 +317,14 @@ def main():
     # ---- leg 1: device-resident (value) ---------------------------------------------------------------
     ctx.set_weights(np.zeros(data.dim))
     ctx.stage_samples(samples_np.reshape(-1))
+    clocks = ClockSampler(local_rank)   # sampled every 20 ms over the warm-up (same workload) and the timed region
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.25)                # nvidia-smi needs a moment to start reporting
+        clocks.mark()
     for i in range(args.warmup):
         ctx.sync_steps_staged(i * S * B, B, S, LR, want_losses=True)
     barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     launches0 = ctx.launch_count()
     ctx.timer_start()
     for i in range(args.warmup, total_steps):
