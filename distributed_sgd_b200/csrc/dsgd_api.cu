@@ -96,6 +96,7 @@ struct dsgd_ctx {
   double *peer_x[kMaxWorld] = {};
   bool peer_x_ipc[kMaxWorld] = {};
   int64_t x_step = 0;   // global step counter of the fused multi-GPU kernel (identical on every rank)
+  unsigned long long *x_llw = nullptr;  // weights in LL form, two parities (mode 3)
 
   // sampled per-launch timing of the gradient kernel
   int32_t prof_every = 0;
@@ -265,6 +266,7 @@ extern "C" int dsgd_destroy(dsgd_ctx *ctx) {
   for (int r = 0; r < kMaxWorld; ++r)
     if (ctx->peer_x[r] && ctx->peer_x_ipc[r]) cudaIpcCloseMemHandle(ctx->peer_x[r]);
   if (ctx->xblk) cudaFree(ctx->xblk);
+  if (ctx->x_llw) cudaFree(ctx->x_llw);
   void *aptrs[] = {ctx->m_w, ctx->a_stop, ctx->a_cnt, ctx->a_scratch, ctx->a_rows, ctx->a_assigned, ctx->a_replay, ctx->u_idx, ctx->u_val};
   for (void *q : aptrs) if (q) cudaFree(q);
   if (ctx->a_ev0) { cudaEventDestroy(ctx->a_ev0); cudaEventDestroy(ctx->a_ev1); }
@@ -723,6 +725,7 @@ using PSmem = PersistSmem<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks>;
 #define DSGD_PERSIST_KERNEL k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 0>
 #define DSGD_PERSIST_KERNEL_MULTI2 k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 1>
 #define DSGD_PERSIST_KERNEL_MULTI k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 2>
+#define DSGD_PERSIST_KERNEL_MULTI3 k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 3>
 
 static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
   if (!ctx->p_ready) {
@@ -737,6 +740,7 @@ static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
     CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
     CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL_MULTI, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
     CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL_MULTI2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
+    CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL_MULTI3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
     ctx->p_ready = true;
   }
   if (ctx->p_hinge_cap < n_steps) {
@@ -860,12 +864,28 @@ static int persist_run_multi(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t 
   void *args[] = {&pp};
   auto *pe = prof_slot(ctx);
   if (pe) cudaEventRecord(pe->first, ctx->stream);
-  static const bool two_barriers = getenv("DSGD_P2P_TWO_BARRIERS") != nullptr;
-  CU(cudaLaunchCooperativeKernel(two_barriers ? (void *)DSGD_PERSIST_KERNEL_MULTI2 : (void *)DSGD_PERSIST_KERNEL_MULTI, dim3(G),
-                                 dim3((kPCons + kPUpd + 1) * 32), args, sizeof(PSmem), ctx->stream));
+  // variants kept for A/B measurements: DSGD_P2P_MODE=1 two grid barriers per step, 2 one barrier with the K-way
+  // reduction done by the consumers per gathered non-zero, 3 (default) one barrier with LL-word weights
+  static const int mode_env = getenv("DSGD_P2P_MODE") ? atoi(getenv("DSGD_P2P_MODE")) : 3;
+  // mode 3 updates one column per thread: the CTA's column slice must fit the barrier-synchronised threads
+  const int mode = (mode_env == 3 && cdiv(ctx->dim + 1, G) > (kPCons + kPUpd) * 32) ? 2 : mode_env;
+  void *fn = mode == 1 ? (void *)DSGD_PERSIST_KERNEL_MULTI2 : mode == 2 ? (void *)DSGD_PERSIST_KERNEL_MULTI : (void *)DSGD_PERSIST_KERNEL_MULTI3;
+  if (mode == 3) {
+    if (!ctx->x_llw) {
+      CU(cudaMalloc(&ctx->x_llw, 2 * 2 * sizeof(unsigned long long) * (size_t)(ctx->dim + kReplicaPad)));
+      CU(cudaMemsetAsync(ctx->x_llw, 0, 2 * 2 * sizeof(unsigned long long) * (size_t)(ctx->dim + kReplicaPad), ctx->stream));
+    }
+    pp.llw[0] = ctx->x_llw;
+    pp.llw[1] = ctx->x_llw + 2 * (size_t)(ctx->dim + kReplicaPad);
+    // the kernel's first interval reads the host-provided weights from wbuf[0]
+    CU(cudaMemcpyAsync(ctx->p_wbuf[0], ctx->w, vd, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  CU(cudaLaunchCooperativeKernel(fn, dim3(G), dim3((kPCons + kPUpd + 1) * 32), args, sizeof(PSmem), ctx->stream));
   if (pe) cudaEventRecord(pe->second, ctx->stream);
   LAUNCHED();
-  ctx->x_step += n_steps;
+  // +3: the next launch must not meet LL words carrying tags this one used (the host may install new weights in
+  // between), and a multiple of 3 keeps the rotation of the three gradient buffers (the dirty one is re-zeroed before use)
+  ctx->x_step += n_steps + 3;
   return DSGD_OK;
 }
 

@@ -64,6 +64,7 @@ struct PersistParams {
   double *xrecv[kMaxWorld];                    // xrecv[k]: receive area of rank k: [sender][parity][dim + 8]; [rank] is local
   unsigned long long *xflag[kMaxWorld];        // xflag[k]: flag words of rank k: [sender][cta]; [rank] is local
   int xstride;                                 // dim + 8
+  unsigned long long *llw[2];                  // mode 3: weights as LL words (16 B per column), double-buffered by step parity
 };
 
 // ---- PTX helpers: mbarrier + TMA bulk copy -------------------------------------------------------------
@@ -258,6 +259,7 @@ struct PersistSmem {
   double c_val[2];
   double nrm_val[2];
   double red[kUpd][2];
+  double red_all[kCons + kUpd][2];
   unsigned hinge_acc;
   int ok;
 };
@@ -372,6 +374,276 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
       b0 = b1; e0 = e1; y0 = y1;
       load_win(id_next, b1, e1, y1);
       id_next = load_id(t + 3);
+    }
+    return;
+  }
+
+  if constexpr (kMode == 3) {
+    // =======================================================================================================
+    // world > 1, one grid barrier per step, weights handed from the update warps to the consumers as LL words.
+    // Interval I_T (between grid barrier T-1 and T), W_T = weights step T differentiates at:
+    //   everybody : push this CTA's column slice of g_{T-1} to every peer's receive area as LL words (tag T)
+    //   updaters  : per column of the CTA's slice: wait for the K replies of step T-1 (own from local g_{T-1}, the
+    //               peers' from the receive area), regularize each on its own support and fold them in rank order
+    //               (core/Master.scala:194), W_T = W_{T-1} - lr*sum/K, published as an LL word (tag T+1)
+    //               into the weight buffer of parity T; partials of c_T, ||W_T||^2; loss of step T-1; zero g_{T+1}'s buffer
+    //   consumers : ONE 16-byte gather per non-zero -- the LL word of W_T[col] (spinning on its tag if the column's
+    //               update has not landed yet); x.W_T; gate; RED y*x into g_T
+    // The K-way reduction is done once per column instead of once per gathered non-zero, and nothing but the
+    // updaters ever waits for c.  A peer can be at most one interval ahead: two parities suffice everywhere.
+    // =======================================================================================================
+    const int K = p.world, me = p.rank;
+    const int slice = (p.dim + 1 + G - 1) / G;   // columns per CTA, plus ONE counter slot [dim] = hinge + 2^32 * samples
+    const int j_lo = min(blockIdx.x * slice, p.dim + 1), j_hi = min(j_lo + slice, p.dim + 1);
+    const int par_stride = p.xstride, snd_stride = 2 * p.xstride;
+    const double lr = p.lr, kd = (double)K;
+    const int64_t base = p.step_base;
+    unsigned phase = 0;
+
+    for (int64_t T = base; T <= base + S; ++T) {
+      const int64_t t = T - base;
+      const bool first = (T == base), last = (T == base + S);
+      const unsigned long long *LWprev = p.llw[(T + 1) & 1];  // LL words of W_{T-1}, tag T
+      unsigned long long *LWcur = p.llw[T & 1];               // LL words of W_T, tag T+1
+      const double *Gprev = p.xg[(T + 2) % 3];                // g_{T-1}
+      double *Gcur = p.xg[T % 3];
+      double *Gzero = p.xg[(T + 1) % 3];
+      const int parp = (int)((T + 1) & 1);                    // receive parity of step T-1
+      const unsigned gtag = (unsigned)T;                      // g words of step T-1 carry tag T
+      const unsigned wtag = (unsigned)(T + 1);                // W_T words carry tag T+1
+      const unsigned long long *rcv = reinterpret_cast<const unsigned long long *>(p.xrecv[me]) + 2 * (size_t)parp * par_stride;
+      const double *part_prev = p.partial + (size_t)((T + 1) & 1) * G * 2;   // partials of W_{T-1}
+      double *part_cur = p.partial + (size_t)(T & 1) * G * 2;
+      const unsigned c_par = (unsigned)((t >> 1) & 1);
+      bool ok = true;
+      auto spin_ll = [&](const unsigned long long *src, unsigned tag, double &v) {
+        unsigned spins = 0;
+        const long long t0 = clock64();
+        while (!ll_try_load(src, tag, v)) {
+          if ((++spins & 255u) == 0u && (clock64() - t0 > p.timeout_cycles || *(volatile int *)p.abort_flag)) {
+            *(volatile int *)p.abort_flag = 1;
+            ok = false;
+            v = 0.0;
+            break;
+          }
+        }
+      };
+
+      // ---- push g_{T-1} (every sync warp; one column per thread) ----
+      if (!first) {
+        for (int j = j_lo + threadIdx.x; j < j_hi; j += kSyncThreads) {
+          const double v = __ldcg(&Gprev[j]);
+          for (int k = 0; k < K; ++k)
+            if (k != me)
+              ll_store(reinterpret_cast<unsigned long long *>(p.xrecv[k]) + 2 * ((size_t)me * snd_stride + (size_t)parp * par_stride + j), v, gtag);
+        }
+      }
+
+      // ---- c_{T-1}: summed by update warp 0, handed to every sync warp of the CTA through shared memory ----
+      double c_prev = 0.0;                                    // of W_{T-1}
+      if (warp == kCons) {
+        double nrm_prev = 0.0;
+        if (!first) {
+          if (T - 1 == base) {
+            c_prev = p.scal[kScalC];                          // W_base came from the host: k_prepare / previous launch
+            nrm_prev = p.scal[kScalNrm2];
+          } else {
+            double sd, sn;
+            sum_partials2(part_prev, G, lane, sd, sn);
+            c_prev = p.lambda * 2.0 * sd;
+            nrm_prev = sn;
+          }
+        }
+        if (lane == 0) {
+          sm.c_val[t & 1] = c_prev;
+          sm.nrm_val[t & 1] = nrm_prev;                       // ||W_{T-1}||^2 for the loss of step T-1
+          mbar_arrive(&sm.c_bar[t & 1]);
+        }
+        __syncwarp();
+      } else {
+        mbar_wait(&sm.c_bar[t & 1], c_par, p.abort_flag, p.timeout_cycles);
+        c_prev = sm.c_val[t & 1];
+      }
+      // ---- column update, one column per sync thread: all K replies and W_{T-1}[j] are requested at once ----
+      double pd = 0.0, pn = 0.0;
+      {
+        const bool add_c = (c_prev != 0.0) && (fabs(c_prev) > kEps);
+        const int j = j_lo + threadIdx.x;                     // slice <= kSyncThreads columns (checked on the host)
+        if (j < j_hi) {
+          if (first) {
+            // W_base arrives as plain doubles from the host (wbuf): publish it in LL form, no update pending
+            if (j < p.dim) ll_store(LWcur + 2 * (size_t)j, __ldcg(&p.wbuf[0][j]), wtag);
+          } else {
+            double raw[kMaxWorld];
+            bool got[kMaxWorld];
+            double wn = 0.0;
+            bool got_w = true;
+            if (j < p.dim) got_w = ll_try_load(LWprev + 2 * (size_t)j, gtag, wn);   // W_{T-1}[j] carries tag T
+#pragma unroll
+            for (int k = 0; k < kMaxWorld; ++k) {
+              got[k] = true;
+              raw[k] = 0.0;
+              if (k < K) {
+                if (k == me) raw[k] = __ldcg(&Gprev[j]);
+                else got[k] = ll_try_load(rcv + 2 * ((size_t)k * snd_stride + j), gtag, raw[k]);
+              }
+            }
+            if (!got_w) spin_ll(LWprev + 2 * (size_t)j, gtag, wn);
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < kMaxWorld; ++k) {
+              if (k < K) {
+                if (!got[k]) spin_ll(rcv + 2 * ((size_t)k * snd_stride + j), gtag, raw[k]);
+                if (j == p.dim) {
+                  s += raw[k];                                // packed counters: plain sum
+                } else {
+                  double v = filt(raw[k]);
+                  if (v != 0.0 && add_c) v = filt(v + c_prev);
+                  s = (k == 0) ? v : filt(s + v);
+                }
+              }
+            }
+            if (j == p.dim) {
+              if (p.losses) {  // loss of step T-1 on W_{T-1}
+                const double ns = floor(s / 4294967296.0);
+                p.losses[t - 1] = p.lambda * sm.nrm_val[t & 1] + (s - ns * 4294967296.0) / ns;
+              }
+            } else {
+              if (s != 0.0) {
+                const double mean = filt(s / kd);
+                const double step = filt(mean * lr);
+                wn = filt(wn - step);
+              }
+              ll_store(LWcur + 2 * (size_t)j, wn, wtag);
+              pd = filt(wn * __ldg(&p.d[j]));
+              pn = wn * wn;
+            }
+          }
+          Gzero[j] = 0.0;
+        }
+        pd = warp_sum(pd);
+        pn = warp_sum(pn);
+        if (lane == 0) { sm.red_all[warp][0] = pd; sm.red_all[warp][1] = pn; }   // summed by thread 0 before the grid barrier
+      }
+
+      if (is_cons) {
+        if (!last) {
+          const int st = (int)(t % kStages);
+          auto &mt = sm.meta[st];
+          mbar_wait(&sm.full[st], (unsigned)((t / kStages) & 1), p.abort_flag, p.timeout_cycles);
+          const int n_ch = mt.n_chunks;
+          const uint2 *ring = &sm.ring[st][0];
+          for (int c = warp; c < n_ch; c += kCons) {
+            const uint32_t off = mt.ch_off[c];
+            const int n = mt.ch_n[c];
+            const uint2 *src = (off & kChunkGlobal) ? (p.pairs + (off & ~kChunkGlobal)) : (ring + off);
+            uint2 pr[4];
+            double wv[4];
+            bool got[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int k = u * 32 + lane;
+              pr[u] = (k < n) ? src[k] : make_uint2(0u, 0u);   // col 0 / val 0: inert, still a valid gather
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) got[u] = ll_try_load(LWcur + 2 * (size_t)pr[u].x, wtag, wv[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (!got[u]) spin_ll(LWcur + 2 * (size_t)pr[u].x, wtag, wv[u]);
+            double acc = 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc += filt(filt((double)__uint_as_float(pr[u].y)) * wv[u]);
+            acc = warp_sum(acc);
+            if (lane == 0) mt.part[c] = acc;
+          }
+          named_bar_sync(2, kCons * 32);
+          unsigned hinge = 0;
+          for (int c = warp; c < n_ch; c += kCons) {
+            const int row = mt.ch_row[c];
+            const int firstc = mt.row_first[row], nch = mt.row_nch[row];
+            double dot = 0.0;
+            for (int i = 0; i < nch; ++i) dot += mt.part[firstc + i];
+            const int yi = mt.row_y[row];
+            const double y = (double)yi;
+            if (c == firstc && lane == 0) hinge += (unsigned)(1 - yi * ((dot > 0.0) ? -1 : ((dot < 0.0) ? 1 : 0)));
+            if (!(y * dot < 0.0)) {
+              const uint32_t off = mt.ch_off[c];
+              const int n = mt.ch_n[c];
+              const uint2 *src = (off & kChunkGlobal) ? (p.pairs + (off & ~kChunkGlobal)) : (ring + off);
+              for (int k = lane; k < n; k += 32) {
+                const uint2 pr = src[k];
+                const double gvv = filt(filt((double)__uint_as_float(pr.y)) * y);
+                if (gvv != 0.0) atomicAdd(&Gcur[pr.x], gvv);
+              }
+            }
+          }
+          for (int m = warp; m < mt.n_rows; m += kCons) {
+            const int nch = mt.row_nch[m];
+            if (nch == 0) {
+              if (lane == 0) hinge += 1u;
+            } else if (nch < 0) {  // row outside the chunk list: whole row from global memory
+              const uint2 *grow = p.pairs + (size_t)mt.row_b[m] * 2;
+              const int len = mt.row_len[m];
+              double acc = 0.0;
+              for (int k = lane; k < len; k += 32) {
+                const uint2 pr = __ldg(&grow[k]);
+                double wv;
+                spin_ll(LWcur + 2 * (size_t)pr.x, wtag, wv);
+                acc += filt(filt((double)__uint_as_float(pr.y)) * wv);
+              }
+              const double dot = warp_sum(acc);
+              const int yi = mt.row_y[m];
+              const double y = (double)yi;
+              if (lane == 0) hinge += (unsigned)(1 - yi * ((dot > 0.0) ? -1 : ((dot < 0.0) ? 1 : 0)));
+              if (!(y * dot < 0.0))
+                for (int k = lane; k < len; k += 32) {
+                  const uint2 pr = __ldg(&grow[k]);
+                  const double gvv = filt(filt((double)__uint_as_float(pr.y)) * y);
+                  if (gvv != 0.0) atomicAdd(&Gcur[pr.x], gvv);
+                }
+            }
+          }
+          if (lane == 0 && hinge) atomicAdd(&sm.hinge_acc, hinge);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.empty[st]);
+        }
+      }
+      if (!ok) *(volatile int *)&sm.ok = 0;
+      // ---- grid barrier T (the CTA's hinge total and batch ride in slot [dim] of g_T) ----
+      named_bar_sync(3, kSyncThreads);
+      if (*(volatile int *)&sm.ok == 0) { *(volatile int *)p.abort_flag = 1; }
+      if (threadIdx.x == 0 && !first) {   // per-CTA partials of c_T, ||W_T||^2: warps in index order (deterministic)
+        double sd = 0.0, sn = 0.0;
+#pragma unroll
+        for (int i = 0; i < kCons + kUpd; ++i) { sd += sm.red_all[i][0]; sn += sm.red_all[i][1]; }
+        part_cur[2 * blockIdx.x] = sd;
+        part_cur[2 * blockIdx.x + 1] = sn;
+      }
+      if (threadIdx.x == 0 && !last) {
+        const unsigned h = sm.hinge_acc;
+        if (h) { atomicAdd(&Gcur[p.dim], (double)h); sm.hinge_acc = 0u; }
+        if (blockIdx.x == 0) atomicAdd(&Gcur[p.dim], (double)B * 4294967296.0);
+      }
+      ++phase;
+      if (!grid_barrier(p.bar, phase * (unsigned)G, p.abort_flag, p.timeout_cycles, &sm.ok, kSyncThreads)) return;
+      if (*(volatile int *)p.abort_flag) return;
+    }
+    // epilogue: W_{base+S} sits in LL form (tag base+S+1) in llw[(base+S) & 1]; publish it as plain resident weights
+    {
+      const unsigned long long *LW = p.llw[(base + S) & 1];
+      const unsigned wtag = (unsigned)(base + S + 1);
+      const int n_all = G * kSyncThreads;
+      for (int j = blockIdx.x * kSyncThreads + threadIdx.x; j < p.dim; j += n_all) {
+        double wv = 0.0;
+        ll_try_load(LW + 2 * (size_t)j, wtag, wv);             // complete: written before the last grid barrier
+        p.w_out[j] = wv;
+        p.w32_out[j] = (float)wv;
+      }
+      if (blockIdx.x == 0 && warp == 0 && S > 0) {
+        double sd, sn;
+        sum_partials2(p.partial + (size_t)((base + S) & 1) * G * 2, G, lane, sd, sn);
+        if (lane == 0) { p.scal[kScalC] = p.lambda * 2.0 * sd; p.scal[kScalNrm2] = sn; }
+      }
     }
     return;
   }
