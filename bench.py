@@ -280,9 +280,11 @@ def main():
     from distributed_sgd_b200.native import NativeCtx
 
     torch.cuda.set_device(local_rank)
+    # stdout carries exactly ONE JSON line: keep NCCL's banner out of it, and use gloo for the control plane (a few
+    # small host-side exchanges; the data path is the kernels' own peer-memory exchange)
+    os.environ["NCCL_DEBUG"] = "WARN"
     if world > 1:
-        dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world,
-                                device_id=torch.device("cuda", local_rank))
+        dist.init_process_group(backend="gloo", rank=rank, world_size=world)
     group = Group()
 
     data, n_train = make_data(args)
@@ -290,9 +292,10 @@ def main():
     ctx.load_csr(data.row_ptr, data.col, data.val, data.label)   # every slave holds every row (quirk Q13)
     d = ctx.compute_dim_sparsity(n_train)
     if world > 1 and args.mode == "sync":
-        uid = NativeCtx.comm_unique_id() if rank == 0 else b""
-        ctx.comm_init(group.broadcast_bytes(uid, 0))
-        if not os.environ.get("DSGD_NO_P2P"):
+        if os.environ.get("DSGD_NO_P2P"):    # general path: NCCL allreduce between the kernels of a step
+            uid = NativeCtx.comm_unique_id() if rank == 0 else b""
+            ctx.comm_init(group.broadcast_bytes(uid, 0))
+        else:
             ctx.setup_peer_exchange(group)   # fused step: gradients summed out of peer memory over NVLink
 
     if args.mode == "async":
