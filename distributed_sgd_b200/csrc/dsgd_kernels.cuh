@@ -326,16 +326,4 @@ __global__ void __launch_bounds__(256) k_to_f32(const double *__restrict__ src, 
   if (j < n) dst[j] = (float)src[j];
 }
 
-// weights -= delta for a sparse delta (core/Slave.scala:177-185; core/ml/GradState.scala:8)
-__global__ void __launch_bounds__(256) k_apply_sparse_delta(double *__restrict__ w, float *__restrict__ w32,
-                                                            const int32_t *__restrict__ idx,
-                                                            const double *__restrict__ val, int64_t nnz) {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < nnz) {
-    const double v = filt(val[k]);
-    if (v != 0.0) atomicAdd(&w[idx[k]], -v);
-  }
-  (void)w32;
-}
-
 }  // namespace dsgd

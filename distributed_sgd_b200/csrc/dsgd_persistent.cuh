@@ -229,7 +229,6 @@ __device__ __forceinline__ bool grid_barrier(unsigned *bar, unsigned target, int
   return *(volatile int *)smem_ok != 0;
 }
 
-constexpr int kChunkPairs_unused_guard = 0;
 constexpr int kChunkPairs = 128;             // 4 pairs per lane per chunk
 constexpr uint32_t kChunkGlobal = 1u << 31;  // chunk offset flag: read from global, the row did not fit the stage
 constexpr int kMaxRowsPerCta = 32;           // rows of one step per CTA (one producer lane each)
