@@ -303,3 +303,28 @@ def test_master_sync_fit_epochs_match_oracle(synth, virtual_workers):
     np.testing.assert_allclose(state.grad, w, rtol=1e-11, atol=1e-15)
     assert state.loss == pytest.approx(losses[-1], rel=RTOL)
     slave.stop()
+
+
+def test_grpc_slave_service_on_the_gpu(synth):
+    """The reference's `Slave` wire service backed by the device context: a Gradient / Forward RPC returns what the
+    oracle computes (keys 1-based on the wire)."""
+    from distributed_sgd_b200.core import wire
+    rng = np.random.default_rng(21)
+    ctx, orc = make_pair(synth, lam=1e-3, n_train=4800)
+    server, port = wire.serve_slave(wire.SlaveServicer(ctx, n_train=4800, is_async=False), 0)
+    try:
+        stub = wire.SlaveStub(f"127.0.0.1:{port}")
+        M = stub.M
+        w = rand_w(rng, synth.dim, 0.2, 0.1)
+        idx = rng.choice(4800, size=100, replace=False).astype(np.int32)
+        rep = stub.Gradient(M.GradientRequest(weights=wire.dense_to_sparse(M, w, synth.dim), samples=idx.tolist()))
+        g = wire.sparse_to_dense(rep.gradUpdate, synth.dim)
+        g_ref, _ = orc.gradient(w, idx)
+        assert (g == 0).tolist() == (g_ref == 0).tolist()
+        np.testing.assert_allclose(g, g_ref, rtol=RTOL, atol=0)
+        rep = stub.Forward(M.ForwardRequest(samples=idx.tolist(), weights=wire.dense_to_sparse(M, w, synth.dim)))
+        np.testing.assert_array_equal(np.array(rep.predictions), orc.forward(w, idx))
+        stub.close()
+    finally:
+        server.stop(0)
+    ctx.close()
