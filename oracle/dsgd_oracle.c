@@ -241,19 +241,104 @@ static int one_sync_step(step_ctx *sc, const dsgd_oracle_csr *a, double lambda, 
   return 0;
 }
 
+/* Threaded form: K persistent worker threads (the reference serves its gradient requests from a fixed thread pool,
+ * utils/Pool.scala:13), two barriers per step; thread 0 plays the master between them. */
+typedef struct {
+  step_ctx *sc;
+  const dsgd_oracle_csr *a;
+  double lambda, lr;
+  const double *d;
+  double *w;
+  const int32_t *idx;
+  const int32_t *counts;
+  int64_t n_steps, per_step;
+  double *losses_out;
+  pthread_barrier_t *bar;
+  int32_t k;
+  int *rc;
+} pool_arg;
+
+static void aggregate_and_update(step_ctx *sc, const dsgd_oracle_csr *a, double lambda, double *w, double lr,
+                                 double *loss_out, int64_t total) {
+  const int32_t K = sc->K;
+  if (loss_out) {
+    double h = 0.0;
+    for (int32_t k = 0; k < K; ++k) h += sc->jobs[k].hinge;
+    *loss_out = lambda * norm_squared(w, a->dim) + h / (double)total;
+  }
+  scratch_t *S = &sc->sum;
+  int32_t nts = 0;
+  for (int32_t k = 0; k < K; ++k) {
+    scratch_t *s = &sc->ws[k];
+    for (int32_t t = 0; t < sc->jobs[k].n_touched; ++t) {
+      int32_t j = s->touched[t];
+      if (s->g[j] == 0.0) continue;
+      if (!S->mark[j]) { S->mark[j] = 1; S->touched[nts++] = j; }
+      S->g[j] = filt(S->g[j] + s->g[j]);
+    }
+    scratch_reset(s, sc->jobs[k].n_touched);
+  }
+  for (int32_t t = 0; t < nts; ++t) {
+    int32_t j = S->touched[t];
+    double mean = filt(S->g[j] / (double)K);
+    double step = filt(mean * lr);
+    w[j] = filt(w[j] - step);
+  }
+  scratch_reset(S, nts);
+}
+
+static void *pool_thread(void *p) {
+  pool_arg *g = (pool_arg *)p;
+  step_ctx *sc = g->sc;
+  for (int64_t s = 0; s < g->n_steps; ++s) {
+    if (g->k == 0) {  /* the master prepares the K requests: same weights, hence the same c, for everybody */
+      const double c = reg_scalar(g->lambda, g->w, g->d, g->a->dim);
+      int64_t off = 0;
+      for (int32_t k = 0; k < sc->K; ++k) {
+        worker_job *j = &sc->jobs[k];
+        j->a = g->a; j->w = g->w; j->c = c; j->idx = g->idx + s * g->per_step + off; j->n = g->counts[k]; j->s = &sc->ws[k];
+        off += g->counts[k];
+      }
+    }
+    pthread_barrier_wait(g->bar);
+    worker_thread(&sc->jobs[g->k]);
+    pthread_barrier_wait(g->bar);
+    if (g->k == 0)
+      aggregate_and_update(sc, g->a, g->lambda, g->w, g->lr, g->losses_out ? g->losses_out + s : NULL, g->per_step);
+  }
+  return NULL;
+}
+
 int dsgd_oracle_sync_steps(const dsgd_oracle_csr *a, double lambda, const double *d, double *w,
                            const int32_t *idx, const int32_t *counts, int32_t n_workers, double lr,
                            int64_t n_steps, double *losses_out, int32_t threads) {
   if (n_workers <= 0) return -3;
   int64_t per_step = 0;
-  for (int32_t k = 0; k < n_workers; ++k) per_step += counts[k];
+  for (int32_t k = 0; k < n_workers; ++k) {
+    if (counts[k] <= 0) return -3; /* empty slice => Vec.sum throws => fit fails (quirk Q7) */
+    per_step += counts[k];
+  }
   if (check_idx(a, idx, per_step * n_steps)) return -2;
   step_ctx sc;
   if (step_ctx_init(&sc, n_workers, a->dim)) return -1;
   int rc = 0;
-  for (int64_t s = 0; s < n_steps && rc == 0; ++s)
-    rc = one_sync_step(&sc, a, lambda, d, w, idx + s * per_step, counts, lr, losses_out ? losses_out + s : NULL,
-                       threads);
+  if (threads > 1 && n_workers > 1 && n_steps > 0) {
+    pthread_barrier_t bar;
+    pthread_barrier_init(&bar, NULL, (unsigned)n_workers);
+    pool_arg *args = (pool_arg *)calloc((size_t)n_workers, sizeof(pool_arg));
+    for (int32_t k = 0; k < n_workers; ++k) {
+      pool_arg g = {&sc, a, lambda, lr, d, w, idx, counts, n_steps, per_step, losses_out, &bar, k, &rc};
+      args[k] = g;
+    }
+    for (int32_t k = 1; k < n_workers; ++k) pthread_create(&sc.tids[k], NULL, pool_thread, &args[k]);
+    pool_thread(&args[0]);
+    for (int32_t k = 1; k < n_workers; ++k) pthread_join(sc.tids[k], NULL);
+    pthread_barrier_destroy(&bar);
+    free(args);
+  } else {
+    for (int64_t s = 0; s < n_steps && rc == 0; ++s)
+      rc = one_sync_step(&sc, a, lambda, d, w, idx + s * per_step, counts, lr, losses_out ? losses_out + s : NULL, 1);
+  }
   step_ctx_free(&sc);
   return rc;
 }
