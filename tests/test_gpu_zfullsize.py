@@ -85,7 +85,8 @@ def test_sync_epoch_at_full_size_is_reproducible(full):
     np.testing.assert_allclose(np.concatenate([la, lb]), l1, rtol=1e-9)
     np.testing.assert_allclose(w2, w1, rtol=1e-8, atol=1e-12)
     loss, acc = ctx.eval(n_train, data.n_rows)
-    assert (loss, acc) == ctx.eval(n_train, data.n_rows, w2)               # resident vs request weights
+    loss_r, acc_r = ctx.eval(n_train, data.n_rows, w2)                      # resident vs request weights:
+    assert acc == acc_r and loss == pytest.approx(loss_r, rel=1e-12)        # ||w||^2 is reduced in a different (fixed) order
     assert np.isfinite(loss) and 0.0 <= acc <= 1.0 and np.all(np.isfinite(w2)) and np.count_nonzero(w2) > 10_000
 
 
@@ -98,7 +99,8 @@ def test_main_scenario_sync_and_async():
     rep = scenario(cfg, data, rank=0, world=1, device=0, log=lambda s: None)
     assert rep["initial_loss"] == 1.0 and rep["initial_accuracy"] == 0.0    # w0 = 0 (Main.scala:74-78)
     assert len(rep["history"]["losses"]) == 3 and len(rep["history"]["test_accs"]) == 3 and rep["updates"] == 3
-    assert rep["final_test_loss"] == rep["history"]["test_losses"][-1]      # Main.scala:115-116 re-evaluates the returned weights
+    # Main.scala:115-116 re-evaluates the returned weights
+    assert rep["final_test_loss"] == pytest.approx(rep["history"]["test_losses"][-1], rel=1e-12)
     assert 0.0 <= rep["final_test_accuracy"] <= 1.0 and rep["final_weights_nonzero"] > 0
     cfg = load_config(env={"DSGD_ASYNC": "true", "DSGD_BATCH_SIZE": "1", "DSGD_MAX_EPOCHS": "5", "DSGD_CHECK_EVERY": "2000",
                            "DSGD_LEARNING_RATE": "0.1"})
