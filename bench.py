@@ -428,6 +428,8 @@ def main():
             "cpu_baseline": cpu,
             "clocks": clock_info,
             "final_batch_loss": float(last_losses[-1]),
+            # fingerprints of the device-resident leg, for tools/verify_bench_loss.py (oracle replay of the same run)
+            "final_weights_l1": float(np.abs(w_after).sum()), "final_weights_nnz": int(np.count_nonzero(w_after)),
         }
         print(json.dumps(out))
     ctx.close()

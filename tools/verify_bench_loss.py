@@ -25,3 +25,7 @@ t = time.time()
 w, losses = orc.sync_steps(np.zeros(data.dim), idx, [B] * K, bench.LR, n_steps=total * S, threads=K)
 print(f"oracle: {total*S} steps x {K} workers in {time.time()-t:.1f} s; last-step loss {losses[-1]!r}; bench line {line['final_batch_loss']!r}; "
       f"rel diff {abs(losses[-1]-line['final_batch_loss'])/abs(losses[-1]):.3e}")
+if "final_weights_l1" in line:
+    l1 = float(np.abs(w).sum())
+    print(f"final weights: oracle l1 {l1!r} nnz {int(np.count_nonzero(w))}; bench l1 {line['final_weights_l1']!r} nnz {line['final_weights_nnz']}; "
+          f"rel diff {abs(l1-line['final_weights_l1'])/l1:.3e}")
