@@ -757,6 +757,7 @@ static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
 static int persist_grid(const dsgd_ctx *ctx, int64_t batch) {
   const int g_min = cdiv(batch, kMaxRowsPerCta);
   if (g_min > ctx->sm_count) return 0;
+  if (ctx->n_pairs >= (1ll << 31)) return 0;  // chunk descriptors carry a 31-bit global pair index
   if (const char *e = getenv("DSGD_PERSIST_CTAS")) {
     const int g = atoi(e);
     if (g > 0) return std::max(g_min, std::min(g, ctx->sm_count));
