@@ -335,7 +335,6 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
         if (lane >= o) { ps += a; cs += c2; }
       }
       const int my_pair = ps - len, my_chunk = cs - nch;
-      const int tot_chunks = __shfl_sync(0xffffffffu, cs, 31);
       const bool listed = (my_chunk + nch) <= kMaxChunks;           // prefix property: later rows miss too
       const bool in_ring = listed && (my_pair + len) <= kStagePairs;
       if (lane < n_r) {
@@ -358,9 +357,13 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
       unsigned ring_bytes = my_bytes;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) ring_bytes += __shfl_xor_sync(0xffffffffu, ring_bytes, o);
+      // chunks actually written to the list: everything up to the first row that did not fit it
+      int listed_chunks = (lane < n_r && listed) ? (my_chunk + nch) : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) listed_chunks = max(listed_chunks, __shfl_xor_sync(0xffffffffu, listed_chunks, o));
       if (lane == 0) {
         mt.n_rows = n_r;
-        mt.n_chunks = tot_chunks < kMaxChunks ? tot_chunks : kMaxChunks;
+        mt.n_chunks = listed_chunks;
       }
       __syncwarp();  // every lane's metadata is written before lane 0 arrives on the full barrier
       if (lane == 0) {
