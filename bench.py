@@ -114,6 +114,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def sync_config(args, world, n_train, B, S):
+    """The `config` object of a sync line -- shared by the GPU arm and the reference arm so that they name the same
+    workload."""
+    return {"workload": f"sync SGD (configs[{1 if world == 1 else 2}]): RCV1-shaped synthetic, {DIM} feats, "
+                        f"{args.rows} rows ({n_train} train), ~0.2% nnz, batch {B} per GPU",
+            "mode": "sync", "batch_per_gpu": B, "sgd_steps_per_bench_step": S, "lambda": LAMBDA, "lr": LR,
+            "parallelism": f"dp{world}", "l2": "inputs (train CSR 0.43 GB) larger than the 126 MB L2; rows drawn at random",
+            "values": "fp32", "state": "fp64"}
+
+
 def make_data(args):
     from distributed_sgd_b200.utils import synthetic_rcv1
     data = synthetic_rcv1(n_rows=args.rows, dim=DIM, seed=args.seed)
@@ -268,8 +278,7 @@ def main():
             "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"sync SGD, RCV1-shaped synthetic ({DIM} feats, {args.rows} rows, ~0.2% nnz), batch "
-                                   f"{args.batch} per worker, {workers} worker(s)", "mode": "sync", "batch": args.batch},
+            "config": sync_config(args, workers, n_train, args.batch, args.sgd_steps or -(-n_train // args.batch)),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": desc + " per step; fp64 array restatement of the Scala path (no JVM in this image)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -414,11 +423,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"sync SGD (configs[{1 if world == 1 else 2}]): RCV1-shaped synthetic, {DIM} feats, "
-                                   f"{args.rows} rows ({n_train} train), ~0.2% nnz, batch {B} per GPU",
-                       "mode": "sync", "batch_per_gpu": B, "sgd_steps_per_bench_step": S, "lambda": LAMBDA, "lr": LR,
-                       "parallelism": f"dp{world}", "l2": "inputs (train CSR 0.43 GB) larger than the 126 MB L2; rows drawn at random",
-                       "values": "fp32", "state": "fp64"},
+            "config": sync_config(args, world, n_train, B, S),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(S * B * 4), "d2h_bytes_per_step": int(S * 8),
                     "api": "dsgd_sync_steps (C ABI, pinned host buffers)", "matches_device_leg": same},
             "gpu_launches": int(launches),
