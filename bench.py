@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="samples per GPU per SGD step")
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU per step (default: 256 sync, 1 async)")
     ap.add_argument("--mode", default="sync", choices=["sync", "async"])
     ap.add_argument("--lanes", type=int, default=256, help="async: Hogwild lanes (warps) per GPU")
     ap.add_argument("--async-updates", type=int, default=400000, help="async: updates per GPU per bench step")
@@ -60,7 +60,10 @@ def parse():
     ap.add_argument("--sgd-steps", type=int, default=0, help="SGD steps per bench step (0: one epoch at 1 worker)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.batch is None:
+        a.batch = 256 if a.mode == "sync" else 1        # BASELINE.json configs[1]/[2] and configs[3]
+    return a
 
 
 def peaks():
@@ -166,7 +169,7 @@ def bench_async(args, ctx, data, n_train, d, group, rank, local_rank, world):
     batch 1 by default.  A bench step = `--async-updates` worker iterations per GPU (device-side sampling)."""
     import torch
     from distributed_sgd_b200.native import REPLICA_MASTER, REPLICA_SELF
-    B = 1 if args.batch == 256 else args.batch        # the async configuration of BASELINE.json is batch 1
+    B = args.batch
     U = args.async_updates
     w0 = np.zeros(data.dim)
     per = n_train // world
