@@ -137,3 +137,38 @@ def test_persistent_loop_with_rows_that_overflow_the_tma_stage(batch):
     np.testing.assert_allclose(losses, losses_ref, rtol=1e-12)
     np.testing.assert_allclose(ctx.get_weights(), w_ref, rtol=1e-10, atol=1e-14)
     ctx.close()
+
+
+# ---- golden fixtures (tests/golden/*.json, from the literal restatement of the Scala arithmetic) through the CUDA path ----
+from test_golden import FIXTURES, flat_draws, load  # noqa: E402
+import os  # noqa: E402
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p) for p in FIXTURES])
+def test_cuda_path_reproduces_golden(path):
+    from distributed_sgd_b200.native import NativeCtx
+    f = load(path)
+    ctx = NativeCtx(0, f["dim"], f["lambda"])
+    ctx.load_csr(f["row_ptr"], f["col"], f["val"], f["label"])
+    d = ctx.compute_dim_sparsity(f["n_train"])
+    np.testing.assert_array_equal(d, f["dim_sparsity_weight_space"])
+    ctx.set_weights(np.zeros(f["dim"]))
+    ctx.set_workers([f["B"]] * f["K"], f["K"])                                               # K logical workers on one GPU
+    losses = ctx.sync_steps(flat_draws(f), f["B"] * f["K"], len(f["draws"]), f["lr"])
+    np.testing.assert_allclose(losses, f["step_losses"], rtol=1e-12)
+    w = ctx.get_weights()
+    np.testing.assert_allclose(w, f["final_weights"], rtol=1e-11, atol=1e-15)
+    g = ctx.gradient(f["probe"], np.array(f["final_weights"]))
+    assert (g == 0).tolist() == (np.array(f["probe_gradient"]) == 0).tolist()
+    np.testing.assert_allclose(g, f["probe_gradient"], rtol=1e-12, atol=0)
+    np.testing.assert_array_equal(ctx.forward(f["probe"], np.array(f["final_weights"])), f["probe_predictions"])
+    n = len(f["label"])
+    loss, acc = ctx.eval(f["n_train"], n, np.array(f["final_weights"]))
+    assert acc == f["test_accuracy"] and loss == pytest.approx(f["test_loss"], rel=1e-12)
+    ctx.close()
+    actx = NativeCtx(0, f["dim"], f["lambda"], is_async=True)
+    actx.load_csr(f["row_ptr"], f["col"], f["val"], f["label"])
+    actx.set_dim_sparsity(np.array(f["dim_sparsity_weight_space"]))
+    actx.async_replay(np.zeros(f["dim"]), np.array(f["async_samples"], np.int32), 1, f["lr"])
+    np.testing.assert_allclose(actx.get_weights(), f["async_final_weights"], rtol=1e-9, atol=1e-13)
+    actx.close()
