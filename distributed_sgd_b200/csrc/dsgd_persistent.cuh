@@ -431,6 +431,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
         }
       };
 
+      if (warp == 0) DSGD_TL(0);
       // ---- push g_{T-1} (every sync warp; one column per thread) ----
       if (!first) {
         for (int j = j_lo + threadIdx.x; j < j_hi; j += kSyncThreads) {
@@ -441,6 +442,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
         }
       }
 
+      if (warp == 0) DSGD_TL(1);
       // ---- c_{T-1}: summed by update warp 0, handed to every sync warp of the CTA through shared memory ----
       double c_prev = 0.0;                                    // of W_{T-1}
       if (warp == kCons) {
@@ -466,6 +468,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
         mbar_wait(&sm.c_bar[t & 1], c_par, p.abort_flag, p.timeout_cycles);
         c_prev = sm.c_val[t & 1];
       }
+      if (warp == 0) DSGD_TL(2);
       // ---- column update, one column per sync thread: all K replies and W_{T-1}[j] are requested at once ----
       double pd = 0.0, pn = 0.0;
       {
@@ -527,12 +530,14 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
         pn = warp_sum(pn);
         if (lane == 0) { sm.red_all[warp][0] = pd; sm.red_all[warp][1] = pn; }   // summed by thread 0 before the grid barrier
       }
+      if (warp == 0) DSGD_TL(3);
 
       if (is_cons) {
         if (!last) {
           const int st = (int)(t % kStages);
           auto &mt = sm.meta[st];
           mbar_wait(&sm.full[st], (unsigned)((t / kStages) & 1), p.abort_flag, p.timeout_cycles);
+          if (warp == 0) DSGD_TL(4);
           const int n_ch = mt.n_chunks;
           const uint2 *ring = &sm.ring[st][0];
           for (int c = warp; c < n_ch; c += kCons) {
@@ -558,6 +563,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
             acc = warp_sum(acc);
             if (lane == 0) mt.part[c] = acc;
           }
+          if (warp == 0) DSGD_TL(5);
           named_bar_sync(2, kCons * 32);
           unsigned hinge = 0;
           for (int c = warp; c < n_ch; c += kCons) {
@@ -608,6 +614,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
           if (lane == 0 && hinge) atomicAdd(&sm.hinge_acc, hinge);
           __syncwarp();
           if (lane == 0) mbar_arrive(&sm.empty[st]);
+          if (warp == 0) DSGD_TL(8);
         }
       }
       if (!ok) *(volatile int *)&sm.ok = 0;
@@ -627,7 +634,9 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
         if (blockIdx.x == 0) atomicAdd(&Gcur[p.dim], (double)B * 4294967296.0);
       }
       ++phase;
-      if (!grid_barrier(p.bar, phase * (unsigned)G, p.abort_flag, p.timeout_cycles, &sm.ok, kSyncThreads)) return;
+      if (!grid_barrier(p.bar, phase * (unsigned)G, p.abort_flag, p.timeout_cycles, &sm.ok, kSyncThreads,
+                        (p.tl && blockIdx.x == 0 && t < 256) ? p.tl + t * 16 + 6 : nullptr))
+        return;
       if (*(volatile int *)p.abort_flag) return;
     }
     // epilogue: W_{base+S} sits in LL form (tag base+S+1) in llw[(base+S) & 1]; publish it as plain resident weights

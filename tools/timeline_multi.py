@@ -33,8 +33,14 @@ def worker(rank, world, port, B):
         l = lib(); l.dsgd_debug_timeline.argtypes = [C.c_void_p, C.c_void_p]
         assert l.dsgd_debug_timeline(ctx._h, tl.ctypes.data_as(C.c_void_p)) == 0
         tl = tl[:4096].reshape(256, 16)
-        names = {0: "step start", 1: "stage full", 2: "rows done (pass 2)", 3: "grid barrier 1 passed", 4: "push + flags issued",
-                 5: "peer flags seen (+fence)", 8: "reduce + update slice done", 9: "partials published", 10: "grid barrier 2 passed"}
+        mode = int(os.environ.get("DSGD_P2P_MODE", "3"))
+        if mode == 3:   # stamps of CTA 0 / warp 0 in the LL-word kernel
+            names = {0: "interval start", 1: "push of g_{T-1} issued", 2: "c received", 3: "column update done (W_T word published)",
+                     4: "stage full (rows landed)", 5: "pass 1 done (dots; waited on W_T words)", 8: "pass 2 done (scatter issued)",
+                     6: "CTA synced, arriving at grid barrier", 7: "grid barrier passed"}
+        else:
+            names = {0: "step start", 1: "stage full", 2: "rows done (pass 2)", 3: "grid barrier 1 passed", 4: "push + flags issued",
+                     5: "peer flags seen (+fence)", 8: "reduce + update slice done", 9: "partials published", 10: "grid barrier 2 passed"}
         t = tl[50:250]
         print(f"world {world} batch {B}: {ms*1e3/S:.2f} us/step; step period {np.mean(np.diff(tl[50:250,0])):.0f} cycles")
         for k in sorted(names):
