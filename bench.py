@@ -431,8 +431,12 @@ def main():
                     "api": "dsgd_sync_steps (C ABI, pinned host buffers)", "matches_device_leg": same},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_per_launch, "kernel_ms": k_ms, "launches_sampled": int(k_n),
+                         "unit": "GB/s", "frac": achieved / hbm_peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture in
+                         # profiles/r1c_summary.md: 67.21 MB for a 300-step launch at batch 256 = 224 KB per SGD step
+                         "traffic": (float(S) * 67.21e6 / 300.0 * (B / 256.0)) if k_n == args.steps else None,
+                         "traffic_source": "ncu capture of a 300-step launch (profiles/r1c_summary.md), scaled to this launch",
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_per_launch, "kernel_ms": k_ms, "launches_sampled": int(k_n),
                          "whole_step_frac": step_frac},
             "roofline_streaming": streaming,
             "cpu_baseline": cpu,
