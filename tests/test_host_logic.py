@@ -79,3 +79,71 @@ def test_rcv1_text_round_trip(tmp_path):                      # utils/Dataset.sc
         f.write("CCAT 2286 1\nGCAT 2287 1\n")
     back = rcv1(str(tmp_path), full=False)
     assert back.label[0] == 1 and back.label[1] == -1
+
+
+class _RecCtx:
+    """Stand-in device context that records what MasterSync would send to the GPU (no arithmetic)."""
+
+    def __init__(self, dim):
+        self.dim, self.calls = dim, []
+
+    def set_weights(self, w):
+        pass
+
+    def get_weights(self):
+        return np.zeros(self.dim)
+
+    def set_workers(self, counts, k_total):
+        self.calls.append(("workers", list(map(int, counts)), int(k_total)))
+
+    def sync_steps(self, samples, n_per_step, n_steps, lr, want_losses=True):
+        self.calls.append(("steps", np.array(samples).reshape(n_steps, n_per_step).copy()))
+        return np.zeros(n_steps)
+
+    def eval_counts(self, lo, hi, w=None):
+        return hi - lo, 0, 0.0
+
+
+def _master(n_train, n_test=5, dim=8):
+    from types import SimpleNamespace
+    from distributed_sgd_b200.core.master import MasterSync
+    from distributed_sgd_b200.ml import SparseSVM
+    from distributed_sgd_b200.utils.dataset import Data
+    stub = lambda n: Data(np.arange(n + 1, dtype=np.int64), np.zeros(n, np.int32), np.ones(n, np.float32), np.ones(n, np.int8), dim)
+    slave = SimpleNamespace(ctx=_RecCtx(dim), world=1, is_async=False, n_train=n_train, n_test=n_test, dim=dim)
+    return MasterSync(0, stub(n_train), stub(n_test), SparseSVM(0.1), 1, slave=slave, seed=0), slave.ctx
+
+
+def test_master_sync_epoch_structure_and_reference_quirks():
+    """core/Master.scala:135-138,179-188: an epoch is ceil(maxSamples / B) steps; every step takes a fresh draw of each
+    worker's own range; the tail slices are shorter (Q5); vanilla(9, 4) yields 3 groups, so only 3 workers are asked and
+    the mean divides by 3."""
+    m, ctx = _master(n_train=9)
+    m.fit(np.zeros(8), max_epochs=1, batch_size=2, learning_rate=0.5, stopping_criterion=lambda l: False, virtual_workers=4)
+    workers = [c for c in ctx.calls if c[0] == "workers"]
+    steps = [c[1] for c in ctx.calls if c[0] == "steps"]
+    assert workers[0] == ("workers", [2, 2, 2], 3)                      # 3 groups of 3 rows -> 3 requests, divisor 3
+    assert steps[0].shape == (1, 6) and steps[1].shape == (1, 3)        # steps at offsets 0 and 2: slices of 2, then of 1
+    for k in range(3):                                                  # each worker samples its own contiguous range
+        assert set(steps[0][0, 2 * k:2 * k + 2]) <= set(range(3 * k, 3 * k + 3))
+    assert len(set(steps[0][0])) == 6                                   # without replacement inside a slice
+    assert m.history["losses"] == [1.0] and m.history["test_accs"] == [0.0]
+
+
+def test_master_sync_empty_slice_fails_like_the_reference():
+    """Quirk Q7: groups of 3, 3, 3, 1 rows with batch 2 -> at offset 2 the short group's slice is empty, Vec.sum throws
+    and the whole fit fails (math/Vec.scala:129 via core/Master.scala:187)."""
+    m, ctx = _master(n_train=10)
+    with pytest.raises(ValueError, match="empty list"):
+        m.fit(np.zeros(8), max_epochs=1, batch_size=2, learning_rate=0.5, stopping_criterion=lambda l: False, virtual_workers=4)
+
+
+def test_master_sync_stops_on_criterion_and_max_epochs():
+    m, ctx = _master(n_train=8)
+    seen = []
+    state = m.fit(np.zeros(8), max_epochs=5, batch_size=4, learning_rate=0.5,
+                  stopping_criterion=lambda losses: seen.append(list(losses)) or len(losses) >= 2)
+    assert state.updates == 2 and len(m.history["test_losses"]) == 2    # stopped by the criterion after 2 epochs
+    assert seen[0] == [] and len(seen[-1]) == 2                         # the criterion sees the newest-first test losses
+    state = m.fit(np.zeros(8), max_epochs=3, batch_size=4, learning_rate=0.5, stopping_criterion=lambda l: False)
+    assert state.updates == 3 and state.loss == m.history["losses"][-1]
