@@ -29,7 +29,8 @@ class Master:
     """core/Master.scala:19-255 (abstract).  `Master.apply` (Master.scala:259-271) is `Master.create`."""
 
     def __init__(self, node: int, data: Data, test_data: Data, model: SparseSVM, expected_node_count: int, *,
-                 slave: Slave, group: Optional[Group] = None, seed: int = 0, log: Optional[Callable[[str], None]] = None):
+                 slave: Slave, group: Optional[Group] = None, seed: int = 0, log: Optional[Callable[[str], None]] = None,
+                 jvm_exact: bool = False):
         self.node, self.model, self.expected_node_count = node, model, expected_node_count
         self.n_train, self.n_test = data.n_rows, test_data.n_rows
         self.dim = data.dim
@@ -42,6 +43,12 @@ class Master:
             raise ValueError("the Slave must hold the same train/test rows as the Master")
         # Random.setSeed(0) (Main.scala:32): one stream, identical on every rank
         self.rng = np.random.default_rng(seed)
+        # jvm_exact: draw the batches with java.util.Random(seed) + Scala 2.12's Random.shuffle, the stream a reference
+        # run consumes; default: numpy's generator (statistically the same draws, much faster)
+        self.jvm = None
+        if jvm_exact:
+            from ..utils.jvm_random import JvmRandom
+            self.jvm = JvmRandom(seed)
         self.log = log or (lambda s: None)
         if self.group.world > 1 and not slave.is_async:
             # NCCL communicator (general path: several logical workers per GPU) ...
@@ -131,6 +138,11 @@ class MasterSync(Master):
         every worker a fresh shuffle of its range, sliced at [batch, batch + batchSize) (Master.scala:
         184-187, quirk Q5).  A slice of a fresh permutation is a uniform draw without replacement of
         min(batchSize, len - batch) elements.  Returns a list of steps, each a list of per-worker arrays."""
+        if self.jvm is not None:
+            n, size = groups[-1].stop, len(groups[0])
+            if [(g.start, g.stop) for g in groups] != [(a, min(a + size, n)) for a in range(0, n, size)]:
+                raise ValueError("jvm_exact draws are defined for SplitStrategy.vanilla groups")
+            return self.jvm.sync_epoch(n, len(groups), batch_size, group_size=size)
         max_samples = max(len(g) for g in groups)
         steps = []
         for batch in range(0, max_samples, batch_size):

@@ -238,3 +238,63 @@ int dsgd_rcv1_write(const char *vectors_path, const char *qrels_path, int64_t n_
   fclose(fv); fclose(fq);
   return 0;
 }
+
+/* ---- JVM-exact batch draws ------------------------------------------------------------
+ * The reference seeds scala.util.Random (a wrapper of java.util.Random) with 0 (Main.scala:32) and, in every sync
+ * step, shuffles each worker's index range afresh and slices it (core/Master.scala:184-187).  These functions
+ * reproduce that stream: java.util.Random's 48-bit LCG (seed scrambling, next(bits), nextInt(bound)) and
+ * scala.util.Random.shuffle of Scala 2.12 (Fisher-Yates from the top: for n = len down to 2: swap(n - 1, nextInt(n))).
+ * Pinned in tests on java.util.Random's well-known outputs; the shuffle order itself cannot be cross-checked here
+ * (no JVM in this image). */
+#define JR_MULT 0x5DEECE66DULL
+#define JR_MASK ((1ULL << 48) - 1)
+
+void dsgd_jrandom_seed(uint64_t *state, int64_t seed) { *state = ((uint64_t)seed ^ JR_MULT) & JR_MASK; }
+
+static inline int32_t jr_next(uint64_t *state, int bits) {
+  *state = (*state * JR_MULT + 0xBULL) & JR_MASK;
+  return (int32_t)(*state >> (48 - bits));
+}
+
+/* bound <= 0: nextInt(); else nextInt(bound) */
+int32_t dsgd_jrandom_next_int(uint64_t *state, int32_t bound) {
+  if (bound <= 0) return jr_next(state, 32);
+  int32_t r = jr_next(state, 31);
+  const int32_t m = bound - 1;
+  if ((bound & m) == 0) return (int32_t)(((int64_t)bound * (int64_t)r) >> 31);
+  for (int32_t u = r; (int32_t)((uint32_t)u - (uint32_t)(r = u % bound) + (uint32_t)m) < 0; u = jr_next(state, 31)) {}
+  return r;
+}
+
+void dsgd_scala_shuffle_i32(uint64_t *state, int32_t *buf, int64_t len) {
+  for (int64_t n = len; n >= 2; --n) {
+    const int32_t k = dsgd_jrandom_next_int(state, (int32_t)n);
+    const int32_t tmp = buf[n - 1]; buf[n - 1] = buf[k]; buf[k] = tmp;
+  }
+}
+
+/* One epoch of Master.fit's draws for `n_groups` contiguous groups of `group_size` rows (the last may be shorter),
+ * n_rows in total: for batch = 0, B, 2B, ... < max group length: for each group: shuffle a fresh copy of its range, take
+ * [batch, batch + B).  out[(step * n_groups + k) * B + i] = row id or -1 where the slice is shorter.  Returns steps. */
+int64_t dsgd_jvm_sync_epoch(uint64_t *state, int64_t n_rows, int64_t group_size, int32_t batch_size, int32_t *out,
+                            int64_t out_capacity) {
+  if (n_rows <= 0 || group_size <= 0 || batch_size <= 0) return -1;
+  const int64_t n_groups = (n_rows + group_size - 1) / group_size;
+  const int64_t max_len = group_size < n_rows ? group_size : n_rows;
+  const int64_t steps = (max_len + batch_size - 1) / batch_size;
+  if (steps * n_groups * batch_size > out_capacity) return -2;
+  int32_t *buf = (int32_t *)malloc(sizeof(int32_t) * (size_t)max_len);
+  if (!buf) return -3;
+  for (int64_t s = 0; s < steps; ++s) {
+    const int64_t batch = s * batch_size;
+    for (int64_t k = 0; k < n_groups; ++k) {
+      const int64_t lo = k * group_size, hi = (lo + group_size < n_rows) ? lo + group_size : n_rows, len = hi - lo;
+      for (int64_t i = 0; i < len; ++i) buf[i] = (int32_t)(lo + i);
+      dsgd_scala_shuffle_i32(state, buf, len);
+      int32_t *dst = out + (s * n_groups + k) * batch_size;
+      for (int64_t i = 0; i < batch_size; ++i) dst[i] = (batch + i < len) ? buf[batch + i] : -1;
+    }
+  }
+  free(buf);
+  return steps;
+}

@@ -147,3 +147,55 @@ def test_master_sync_stops_on_criterion_and_max_epochs():
     assert seen[0] == [] and len(seen[-1]) == 2                         # the criterion sees the newest-first test losses
     state = m.fit(np.zeros(8), max_epochs=3, batch_size=4, learning_rate=0.5, stopping_criterion=lambda l: False)
     assert state.updates == 3 and state.loss == m.history["losses"][-1]
+
+
+def test_jvm_random_known_answers():
+    """java.util.Random's well-known outputs: seed 0 -> nextInt() = -1155484576, -723955400, 1033096058, ...;
+    seed 0 -> nextInt(100) = 60, 48, 29, 47, 15; seed 42 -> nextInt(10) = 0, 3, 8, 4, 0, 5, 5, 8, 9, 3."""
+    from distributed_sgd_b200.utils.jvm_random import JvmRandom
+    r = JvmRandom(0)
+    assert [r.next_int() for _ in range(5)] == [-1155484576, -723955400, 1033096058, -1690734402, -1557280266]
+    r = JvmRandom(0)
+    assert [r.next_int(100) for _ in range(5)] == [60, 48, 29, 47, 15]
+    r = JvmRandom(42)
+    assert [r.next_int(10) for _ in range(10)] == [0, 3, 8, 4, 0, 5, 5, 8, 9, 3]
+    r = JvmRandom(42)
+    assert r.next_int() == -1170105035
+    r = JvmRandom(7)
+    assert all(0 <= r.next_int(16) < 16 for _ in range(100))           # power-of-two bound takes the multiply path
+
+
+def test_scala_shuffle_and_epoch_draws():
+    """scala.util.Random.shuffle (2.12): Fisher-Yates from the top with nextInt(n); the epoch helper equals shuffling a
+    fresh copy of every group at every step and slicing it (core/Master.scala:184-187)."""
+    from distributed_sgd_b200.utils.jvm_random import JvmRandom
+    a, b = JvmRandom(0), JvmRandom(0)
+    xs = list(range(10, 20))
+    buf = list(xs)
+    for n in range(len(buf), 1, -1):                                   # the algorithm, spelled out with next_int
+        k = b.next_int(n)
+        buf[n - 1], buf[k] = buf[k], buf[n - 1]
+    assert a.shuffle(xs).tolist() == buf and sorted(buf) == xs
+    a, b = JvmRandom(0), JvmRandom(0)
+    steps = a.sync_epoch(10, 4, 2)                                     # groups 3,3,3,1 -> steps at offsets 0 and 2
+    assert len(steps) == 2 and [len(g) for g in steps[0]] == [2, 2, 2, 1] and [len(g) for g in steps[1]] == [1, 1, 1, 0]
+    groups = [range(0, 3), range(3, 6), range(6, 9), range(9, 10)]
+    for s, batch in enumerate((0, 2)):
+        for k, g in enumerate(groups):
+            assert steps[s][k].tolist() == b.shuffle(list(g))[batch:batch + 2].tolist()
+
+
+def test_master_sync_jvm_exact_draws():
+    from types import SimpleNamespace
+    from distributed_sgd_b200.core.master import MasterSync
+    from distributed_sgd_b200.ml import SparseSVM
+    from distributed_sgd_b200.utils.dataset import Data
+    from distributed_sgd_b200.utils.jvm_random import JvmRandom
+    stub = lambda n: Data(np.arange(n + 1, dtype=np.int64), np.zeros(n, np.int32), np.ones(n, np.float32), np.ones(n, np.int8), 8)
+    slave = SimpleNamespace(ctx=_RecCtx(8), world=1, is_async=False, n_train=12, n_test=5, dim=8)
+    m = MasterSync(0, stub(12), stub(5), SparseSVM(0.1), 1, slave=slave, seed=0, jvm_exact=True)
+    m.fit(np.zeros(8), max_epochs=1, batch_size=3, learning_rate=0.5, stopping_criterion=lambda l: False, virtual_workers=2)
+    steps = [c[1] for c in slave.ctx.calls if c[0] == "steps"]
+    ref = JvmRandom(0).sync_epoch(12, 2, 3)
+    got = np.concatenate([s.reshape(-1) for s in steps]).tolist()
+    assert got == [int(i) for st in ref for g in st for i in g]
