@@ -109,36 +109,6 @@ def test_main_scenario_sync_and_async():
     assert rep["final_test_accuracy"] > 0.5 and rep["final_weights_nonzero"] > 0
 
 
-@pytest.mark.parametrize("batch", [256, 1500])
-def test_persistent_loop_with_rows_that_overflow_the_tma_stage(batch):
-    """Very long rows (1800-2000 non-zeros each): with two rows per CTA the second one no longer fits the 20 KB
-    shared-memory stage and is read from global memory chunk by chunk (batch 256); with ~10 rows per CTA the chunk
-    list overflows too and whole rows take the warp-per-row slow path (batch 1500).  Same trajectory as the oracle."""
-    from distributed_sgd_b200.native import NativeCtx
-    from oracle.oracle import Oracle
-    rng = np.random.default_rng(batch)
-    dim, n = 47236, 1600
-    lens = rng.integers(1800, 2001, size=n)
-    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-    col = np.concatenate([np.sort(rng.choice(dim, size=int(l), replace=False)) for l in lens]).astype(np.int32)
-    val = (np.abs(rng.standard_normal(len(col))) * 0.02 + 1e-3).astype(np.float32)
-    lab = rng.choice(np.array([-1, 1], dtype=np.int8), size=n)
-    lam, lr, steps = 1e-3, 0.05, 6
-    ctx = NativeCtx(0, dim, lam)
-    ctx.load_csr(rp, col, val, lab)
-    orc = Oracle(rp, col, val, lab, dim, lam)
-    d = orc.dim_sparsity(n)
-    orc.set_dim_sparsity(d)
-    ctx.set_dim_sparsity(d)
-    idx = np.stack([rng.choice(n, size=batch, replace=False) for _ in range(steps)]).astype(np.int32).reshape(-1)
-    w_ref, losses_ref = orc.sync_steps(np.zeros(dim), idx, [batch], lr, n_steps=steps)
-    ctx.set_weights(np.zeros(dim))
-    losses = ctx.sync_steps(idx, batch, steps, lr)
-    np.testing.assert_allclose(losses, losses_ref, rtol=1e-12)
-    np.testing.assert_allclose(ctx.get_weights(), w_ref, rtol=1e-10, atol=1e-14)
-    ctx.close()
-
-
 # ---- golden fixtures (tests/golden/*.json, from the literal restatement of the Scala arithmetic) through the CUDA path ----
 from test_golden import FIXTURES, flat_draws, load  # noqa: E402
 import os  # noqa: E402
@@ -172,3 +142,33 @@ def test_cuda_path_reproduces_golden(path):
     actx.async_replay(np.zeros(f["dim"]), np.array(f["async_samples"], np.int32), 1, f["lr"])
     np.testing.assert_allclose(actx.get_weights(), f["async_final_weights"], rtol=1e-9, atol=1e-13)
     actx.close()
+
+
+@pytest.mark.parametrize("batch", [256, 1500])
+def test_persistent_loop_with_rows_that_overflow_the_tma_stage(batch):
+    """Very long rows (1800-2000 non-zeros each): with two rows per CTA the second one no longer fits the 20 KB
+    shared-memory stage and is read from global memory chunk by chunk (batch 256); with ~10 rows per CTA the chunk
+    list overflows too and whole rows take the warp-per-row slow path (batch 1500).  Same trajectory as the oracle."""
+    from distributed_sgd_b200.native import NativeCtx
+    from oracle.oracle import Oracle
+    rng = np.random.default_rng(batch)
+    dim, n = 47236, 1600
+    lens = rng.integers(1800, 2001, size=n)
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    col = np.concatenate([np.sort(rng.choice(dim, size=int(l), replace=False)) for l in lens]).astype(np.int32)
+    val = (np.abs(rng.standard_normal(len(col))) * 0.02 + 1e-3).astype(np.float32)
+    lab = rng.choice(np.array([-1, 1], dtype=np.int8), size=n)
+    lam, lr, steps = 1e-3, 0.05, 6
+    ctx = NativeCtx(0, dim, lam)
+    ctx.load_csr(rp, col, val, lab)
+    orc = Oracle(rp, col, val, lab, dim, lam)
+    d = orc.dim_sparsity(n)
+    orc.set_dim_sparsity(d)
+    ctx.set_dim_sparsity(d)
+    idx = np.stack([rng.choice(n, size=batch, replace=False) for _ in range(steps)]).astype(np.int32).reshape(-1)
+    w_ref, losses_ref = orc.sync_steps(np.zeros(dim), idx, [batch], lr, n_steps=steps)
+    ctx.set_weights(np.zeros(dim))
+    losses = ctx.sync_steps(idx, batch, steps, lr)
+    np.testing.assert_allclose(losses, losses_ref, rtol=1e-12)
+    np.testing.assert_allclose(ctx.get_weights(), w_ref, rtol=1e-10, atol=1e-14)
+    ctx.close()
