@@ -72,6 +72,8 @@ struct dsgd_ctx {
   unsigned *p_hinge = nullptr;
   int64_t p_hinge_cap = 0;
   unsigned *p_bar = nullptr;   // [0]: barrier counter, [1]: abort flag
+  unsigned *p_bar_flags = nullptr;  // DSGD_PERSIST_OPT & 1: release flag lines of the flag barrier
+  double *p_push = nullptr;         // DSGD_PERSIST_OPT & 2: pushed partials [2][G][G][2]
   bool p_ready = false;
   long long *p_tl = nullptr;   // debug timeline (DSGD_PERSIST_TIMELINE)
 
@@ -274,7 +276,8 @@ extern "C" int dsgd_destroy(dsgd_ctx *ctx) {
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   void *ptrs[] = {ctx->rp16, ctx->pairs, ctx->label, ctx->w, ctx->g, ctx->d, ctx->w_req, ctx->w32, ctx->w32_req, ctx->n_exact, ctx->scal,
                   ctx->cnt, ctx->partial, ctx->out2, ctx->gsum, ctx->p_wbuf[0], ctx->p_wbuf[1], ctx->p_gbuf[0],
-                  ctx->p_gbuf[1], ctx->p_gbuf[2], ctx->p_partial, ctx->p_hinge, ctx->p_bar, ctx->samples, ctx->losses, ctx->preds};
+                  ctx->p_gbuf[1], ctx->p_gbuf[2], ctx->p_partial, ctx->p_hinge, ctx->p_bar, ctx->p_bar_flags, ctx->p_push, ctx->samples,
+                  ctx->losses, ctx->preds};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -726,6 +729,21 @@ using PSmem = PersistSmem<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks>;
 #define DSGD_PERSIST_KERNEL_MULTI2 k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 1>
 #define DSGD_PERSIST_KERNEL_MULTI k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 2>
 #define DSGD_PERSIST_KERNEL_MULTI3 k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 3>
+// experimental single-GPU variants (DSGD_PERSIST_OPT=1..3; dsgd_persistent.cuh, kOpt): not the default until measured
+typedef void (*persist_kernel_t)(const PersistParams);
+static persist_kernel_t persist_variant(int opt) {
+  switch (opt) {
+    case 1: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 0, 1>;
+    case 2: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 0, 2>;
+    case 3: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 0, 3>;
+    default: return DSGD_PERSIST_KERNEL;
+  }
+}
+static int persist_opt() {
+  const char *e = getenv("DSGD_PERSIST_OPT");
+  const int v = e ? atoi(e) : 0;
+  return (v >= 0 && v <= 3) ? v : 0;
+}
 
 static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
   if (!ctx->p_ready) {
@@ -741,6 +759,10 @@ static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
     CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL_MULTI, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
     CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL_MULTI2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
     CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL_MULTI3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
+    for (int opt = 1; opt <= 3; ++opt)
+      CU(cudaFuncSetAttribute((const void *)persist_variant(opt), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
+    CU(cudaMalloc(&ctx->p_bar_flags, sizeof(unsigned) * kBarFlagStride * (size_t)(ctx->sm_count / kBarGroup + 1)));
+    CU(cudaMalloc(&ctx->p_push, sizeof(double) * 2 * 2 * (size_t)ctx->sm_count * (size_t)ctx->sm_count));
     ctx->p_ready = true;
   }
   if (ctx->p_hinge_cap < n_steps) {
@@ -786,6 +808,9 @@ static int persist_run(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t n_per_
   pp.w_out = ctx->w; pp.w32_out = ctx->w32; pp.scal = ctx->scal;
   pp.bar = ctx->p_bar; pp.abort_flag = reinterpret_cast<int *>(ctx->p_bar + 1);
   pp.lambda = ctx->lambda; pp.lr = lr; pp.k_den = 1.0;
+  const int opt = persist_opt();
+  if (opt & 1) CU(cudaMemsetAsync(ctx->p_bar_flags, 0, sizeof(unsigned) * kBarFlagStride * (size_t)(ctx->sm_count / kBarGroup + 1), ctx->stream));
+  pp.bar_flags = ctx->p_bar_flags; pp.push = ctx->p_push;
   pp.tl = nullptr;
   if (getenv("DSGD_PERSIST_TIMELINE")) {
     if (!ctx->p_tl) CU(cudaMalloc(&ctx->p_tl, sizeof(long long) * (256 * 16 + 4 * 160 * 2)));
@@ -796,7 +821,7 @@ static int persist_run(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t n_per_
   void *args[] = {&pp};
   auto *pe = prof_slot(ctx);
   if (pe) cudaEventRecord(pe->first, ctx->stream);
-  CU(cudaLaunchCooperativeKernel((void *)DSGD_PERSIST_KERNEL, dim3(G), dim3((kPCons + kPUpd + 1) * 32), args, sizeof(PSmem),
+  CU(cudaLaunchCooperativeKernel((void *)persist_variant(opt), dim3(G), dim3((kPCons + kPUpd + 1) * 32), args, sizeof(PSmem),
                                  ctx->stream));
   if (pe) cudaEventRecord(pe->second, ctx->stream);
   LAUNCHED();

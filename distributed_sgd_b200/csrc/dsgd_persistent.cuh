@@ -65,6 +65,9 @@ struct PersistParams {
   unsigned long long *xflag[kMaxWorld];        // xflag[k]: flag words of rank k: [sender][cta]; [rank] is local
   int xstride;                                 // dim + 8
   unsigned long long *llw[2];                  // mode 3: weights as LL words (16 B per column), double-buffered by step parity
+  // ---- experimental variants (template parameter kOpt; not the default path) ----
+  unsigned *bar_flags;                         // kOpt & 1: release flags of the grid barrier, one 128-byte line per kBarGroup CTAs, zero on entry
+  double *push;                                // kOpt & 2: pushed partials [2 parities][dest CTA][src CTA][2]
 };
 
 // ---- PTX helpers: mbarrier + TMA bulk copy -------------------------------------------------------------
@@ -229,6 +232,55 @@ __device__ __forceinline__ bool grid_barrier(unsigned *bar, unsigned target, int
   return *(volatile int *)smem_ok != 0;
 }
 
+// ---- variant kOpt & 1: grid barrier with separate arrival counter and release flags -------------------------------
+// In grid_barrier() every CTA polls the word the arrivals are added to, so 148 pollers and 148 arrivals queue on one
+// L2 line (measured: 1.2-1.6 us from the last arrival to the release, profiles/r1c_summary.md).  Here nobody polls the
+// counter: the arrival is an atom that returns the count, the LAST arriver raises one flag per group of kBarGroup
+// CTAs (each on its own 128-byte line) and everybody else polls only its group's flag.
+constexpr int kBarGroup = 8;
+constexpr int kBarFlagStride = 32;  // unsigned words per flag line
+__device__ __forceinline__ unsigned atom_acq_rel_gpu_add(unsigned *p, unsigned v) {
+  unsigned old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void st_relaxed_gpu(unsigned *p, unsigned v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ bool grid_barrier_flags(unsigned *bar, unsigned *flags, unsigned phase, unsigned n_cta,
+                                                   int *abort_flag, long long timeout, int *smem_ok, int n_sync_threads,
+                                                   long long *tl = nullptr, bool tl_ns = false) {
+  named_bar_sync(3, n_sync_threads);
+  if (threadIdx.x == 0) {
+    if (tl) tl[0] = tl_ns ? global_ns() : clock64();
+    int ok = 1;
+    const unsigned old = atom_acq_rel_gpu_add(bar, 1u);  // release: this CTA's writes; acquire: every earlier arrival's
+    if (old + 1u == phase * n_cta) {
+      fence_acq_rel_gpu();                               // fence + relaxed stores: a release pattern per flag
+      const unsigned n_groups = (n_cta + kBarGroup - 1) / kBarGroup;
+      for (unsigned g = 0; g < n_groups; ++g) st_relaxed_gpu(flags + g * kBarFlagStride, phase);
+    } else {
+      const unsigned *f = flags + (blockIdx.x / kBarGroup) * kBarFlagStride;
+      const long long t0 = clock64();
+      unsigned spins = 0;
+      while ((int)(ld_relaxed_gpu(f) - phase) < 0) {     // the flag only ever steps from phase - 1 to phase
+        if ((++spins & 1023u) == 0u) {
+          if (clock64() - t0 > timeout || *(volatile int *)abort_flag) {
+            *(volatile int *)abort_flag = 1;
+            ok = 0;
+            break;
+          }
+        }
+      }
+      fence_acq_rel_gpu();
+    }
+    *smem_ok = ok;
+    if (tl) tl[1] = tl_ns ? global_ns() : clock64();
+  }
+  named_bar_sync(3, n_sync_threads);
+  return *(volatile int *)smem_ok != 0;
+}
+
 constexpr int kChunkPairs = 128;             // 4 pairs per lane per chunk
 constexpr uint32_t kChunkGlobal = 1u << 31;  // chunk offset flag: read from global, the row did not fit the stage
 constexpr int kMaxRowsPerCta = 32;           // rows of one step per CTA (one producer lane each)
@@ -268,7 +320,10 @@ struct PersistSmem {
     if (p.tl && blockIdx.x == 0 && lane == 0 && t < 256) p.tl[t * 16 + (slot_)] = clock64(); \
   } while (0)
 
-template <int kCons, int kUpd, int kStages, int kStagePairs, int kMaxChunks, int kMode>
+// kOpt (mode 0 only): bit 0 = grid_barrier_flags instead of grid_barrier; bit 1 = per-CTA partials of c / ||w||^2 are
+// PUSHED to a private area of every CTA instead of 148 CTAs reading the same 2.4 KB (measured: c is handed over 1 880
+// cycles after the barrier).  Same values summed in the same order: results are bit-identical to kOpt == 0.
+template <int kCons, int kUpd, int kStages, int kStagePairs, int kMaxChunks, int kMode, int kOpt = 0>
 __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(const PersistParams p) {
   using Smem = PersistSmem<kCons, kUpd, kStages, kStagePairs, kMaxChunks>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1196,8 +1251,9 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
     const double *Gprev = p.gbuf[(t + 2) % 3];
     double *Gcur = p.gbuf[t % 3];
     double *Gzero = p.gbuf[(t + 1) % 3];
-    const double *part_prev = p.partial + (size_t)((t + 1) & 1) * G * 2;
-    double *part_cur = p.partial + (size_t)(t & 1) * G * 2;
+    const double *part_prev = (kOpt & 2) ? p.push + ((size_t)((t + 1) & 1) * G + blockIdx.x) * G * 2   // this CTA's private copy
+                                         : p.partial + (size_t)((t + 1) & 1) * G * 2;
+    double *part_cur = (kOpt & 2) ? p.push + (size_t)(t & 1) * G * G * 2 : p.partial + (size_t)(t & 1) * G * 2;
     const unsigned c_par = (unsigned)((t >> 1) & 1);
 
     if (is_cons) {
@@ -1352,7 +1408,14 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
       pn = warp_sum(pn);
       if (lane == 0) { sm.red[uw][0] = pd; sm.red[uw][1] = pn; }
       named_bar_sync(1, kUpd * 32);
-      if (uw == 0 && lane == 0) {
+      if constexpr (kOpt & 2) {
+        // every update thread sums the CTA's kUpd pairs (same order) and stores them into the areas of the CTAs it serves
+        double sd = 0.0, sn = 0.0;
+#pragma unroll
+        for (int i = 0; i < kUpd; ++i) { sd += sm.red[i][0]; sn += sm.red[i][1]; }
+        for (int dest = threadIdx.x - kCons * 32; dest < G; dest += kUpd * 32)
+          *reinterpret_cast<double2 *>(part_cur + ((size_t)dest * G + blockIdx.x) * 2) = make_double2(sd, sn);
+      } else if (uw == 0 && lane == 0) {
         double sd = 0.0, sn = 0.0;
 #pragma unroll
         for (int i = 0; i < kUpd; ++i) { sd += sm.red[i][0]; sn += sm.red[i][1]; }
@@ -1377,7 +1440,12 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
       if (t >= 100 && t < 104) { tl_slot = p.tl + 4096 + ((t - 100) * 160 + blockIdx.x) * 2; tl_ns = true; }
       else if (blockIdx.x == 0 && t < 256) tl_slot = p.tl + t * 16 + 6;
     }
-    if (!grid_barrier(p.bar, phase * (unsigned)G, p.abort_flag, p.timeout_cycles, &sm.ok, kSyncThreads, tl_slot, tl_ns)) return;
+    if constexpr (kOpt & 1) {
+      if (!grid_barrier_flags(p.bar, p.bar_flags, phase, (unsigned)G, p.abort_flag, p.timeout_cycles, &sm.ok, kSyncThreads,
+                              tl_slot, tl_ns)) return;
+    } else {
+      if (!grid_barrier(p.bar, phase * (unsigned)G, p.abort_flag, p.timeout_cycles, &sm.ok, kSyncThreads, tl_slot, tl_ns)) return;
+    }
   }
 
   // ---- epilogue: W_S is complete in wbuf[S & 1]; publish it as the resident weights, clear g_{S-1} ----------
@@ -1391,7 +1459,8 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
       Glast[j] = 0.0;
     }
     if (blockIdx.x == 0 && warp == kCons) {
-      const double *part = p.partial + (size_t)(S & 1) * G * 2;
+      const double *part = (kOpt & 2) ? p.push + (size_t)(S & 1) * G * G * 2   // CTA 0's private copy
+                                      : p.partial + (size_t)(S & 1) * G * 2;
       double sd, sn;
       sum_partials2(part, G, lane, sd, sn);
       if (lane == 0) {

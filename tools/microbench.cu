@@ -79,6 +79,75 @@ __global__ void k_pingpong(unsigned *flags, int iters, long long *out) {
   }
 }
 
+
+// 5. the flag barrier of dsgd_persistent.cuh (kOpt & 1): arrivals on a counter nobody polls, last arriver raises one
+//    flag per group of GROUP CTAs.  PRE_RED: every thread issues one fp64 RED before arriving (what a step does).
+__device__ __forceinline__ unsigned atom_acq_rel_gpu_add(unsigned *p, unsigned v) {
+  unsigned old; asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory"); return old;
+}
+template <int GROUP, bool PRE_RED, bool FLAGS>
+__global__ void k_barrier2(unsigned *bar, unsigned *flags, double *buf, int iters, long long *out) {
+  __shared__ int dummy;
+  unsigned a = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u;
+  long long t0 = clock64();
+  for (int it = 1; it <= iters; ++it) {
+    if (PRE_RED) { a = a * 1664525u + 1013904223u; atomicAdd(&buf[(a >> 8) % 47236], 1.0); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned target = (unsigned)it * gridDim.x;
+      if (FLAGS) {
+        const unsigned old = atom_acq_rel_gpu_add(bar, 1u);
+        if (old + 1u == target) {
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");
+          for (unsigned g = 0; g < (gridDim.x + GROUP - 1) / GROUP; ++g)
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(flags + g * 32), "r"((unsigned)it) : "memory");
+        } else {
+          const unsigned *f = flags + (blockIdx.x / GROUP) * 32;
+          while ((int)(ld_relaxed_gpu(f) - (unsigned)it) < 0) {}
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        }
+      } else {
+        red_release_gpu_add(bar, 1u);
+        while (ld_relaxed_gpu(bar) < target) {}
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      }
+      dummy = it;
+    }
+    __syncthreads();
+  }
+  long long t1 = clock64();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out = (t1 - t0) / iters;
+}
+
+// 6. scattered 8-byte gathers from an L2-resident vector (the weight gathers of a step): loads per SM-cycle
+__global__ void k_gather(const double *buf, int n_addr, int reps, long long *out, double *sink) {
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned a = tid * 2654435761u;
+  double acc = 0.0;
+  long long t0 = clock64();
+  for (int r = 0; r < reps; r += 4) {
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { a = a * 1664525u + 1013904223u; v[u] = __ldcg(&buf[(a >> 8) % n_addr]); }
+    acc += (v[0] + v[1]) + (v[2] + v[3]);
+  }
+  long long t1 = clock64();
+  if (acc == 12345.678) *sink = acc;
+  if (tid == 0) *out = (t1 - t0);
+}
+
+// 7. hardware cluster barrier (one cluster; release/acquire vs relaxed arrive)
+template <bool RELAXED>
+__global__ void k_cluster_barrier(int iters, long long *out) {
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    if (RELAXED) asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+    else asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+  long long t1 = clock64();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out = (t1 - t0) / iters;
+}
+
 int main() {
   int dev = 0; CK(cudaSetDevice(dev));
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, dev));
@@ -124,6 +193,45 @@ int main() {
       k_red<float><<<blocks, 256>>>(bf, n_addr, reps, out); CK(cudaDeviceSynchronize()); long long b = *out;
       double total = (double)blocks * 256 * reps;
       printf("RED n_addr=%7d blocks=%3d: f64 %lld cyc (%.3f cyc/op chip-wide), f32 %lld cyc (%.3f)\n", n_addr, blocks, a, a / total, b, b / total);
+    }
+  }
+  // ---- round-2 questions ----
+  unsigned *flags; CK(cudaMalloc(&flags, 32 * 4 * 256));
+  {
+    const int G = prop.multiProcessorCount; int iters = 2000;
+    auto run = [&](void *fn, const char *name) {
+      CK(cudaMemset(bar, 0, 1024)); CK(cudaMemset(flags, 0, 32 * 4 * 256));
+      void *args[] = {&bar, &flags, &bd, &iters, &out};
+      CK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(448), args, 0, 0)); CK(cudaDeviceSynchronize());
+      printf("barrier2 G=%d x448thr %-44s %lld cyc\n", G, name, *out);
+    };
+    run((void *)k_barrier2<8, false, false>, "counter polled by all (as shipped):");
+    run((void *)k_barrier2<1, false, true>, "flags, one per CTA:");
+    run((void *)k_barrier2<8, false, true>, "flags, one per 8 CTAs:");
+    run((void *)k_barrier2<32, false, true>, "flags, one per 32 CTAs:");
+    run((void *)k_barrier2<8, true, false>, "counter polled by all + 1 RED/thread:");
+    run((void *)k_barrier2<8, true, true>, "flags per 8 CTAs + 1 RED/thread:");
+  }
+  for (int threads : {256, 1024})
+    for (int blocks : {8, 16, 32, 74, 148}) {
+      int reps = 64, n_addr = 47236;
+      k_red<double><<<blocks, threads>>>(bd, n_addr, reps, out); CK(cudaDeviceSynchronize()); long long a = *out;
+      k_gather<<<blocks, threads>>>(bd, n_addr, reps, out, bd + n_addr); CK(cudaDeviceSynchronize()); long long b = *out;
+      const double per_sm = (double)threads * reps;
+      printf("scattered 8 B over 47236 doubles, %3d CTAs x %4d thr: RED.f64 %.3f /SM-cycle, ld.cg %.3f /SM-cycle\n", blocks, threads,
+             per_sm / a, per_sm / b);
+    }
+  for (int csz : {8, 16}) {
+    for (int relaxed = 0; relaxed < 2; ++relaxed) {
+      void *fn = relaxed ? (void *)k_cluster_barrier<true> : (void *)k_cluster_barrier<false>;
+      if (csz > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
+      cudaLaunchConfig_t cfg = {}; cfg.gridDim = dim3(csz); cfg.blockDim = dim3(448);
+      cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = csz; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+      cfg.attrs = &at; cfg.numAttrs = 1;
+      int iters = 2000;
+      cudaError_t e = relaxed ? cudaLaunchKernelEx(&cfg, k_cluster_barrier<true>, iters, out) : cudaLaunchKernelEx(&cfg, k_cluster_barrier<false>, iters, out);
+      if (e != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { printf("cluster barrier size %d: %s\n", csz, cudaGetErrorString(cudaGetLastError())); continue; }
+      printf("cluster barrier, 1 cluster of %2d CTAs x448thr, %s: %lld cyc\n", csz, relaxed ? "relaxed" : "release/acquire", *out);
     }
   }
   return 0;

@@ -1,0 +1,28 @@
+#!/bin/bash
+# Round-2 opener: ONE gpurun call that (1) re-runs the GPU suite, (2) runs the latency microbenchmarks behind the design
+# questions of DESIGN.md section 8, (3) checks parity and measures the bench line for every experimental variant of the
+# persistent kernel (DSGD_PERSIST_OPT, dsgd_persistent.cuh kOpt) and (4) prints CTA 0's step timeline for each.
+#   gpurun --timeout 1500 -- 'bash tools/r2_first_call.sh'
+# Everything lands in gpurun_out/r2_*.txt|json.  Nothing here is a bench value of record (bench.py alone is).
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+[ -x tools/microbench ] || (cd tools && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o microbench microbench.cu)
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_tests.txt 2>&1; echo "gpu tests rc=$?"; tail -3 gpurun_out/r2_tests.txt
+timeout 300 ./tools/microbench > gpurun_out/r2_microbench.txt 2>&1; echo "microbench rc=$?"
+for opt in 0 1 2 3; do
+  export DSGD_PERSIST_OPT=$opt
+  timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_zfullsize.py -q -m gpu -k "trajectory or epoch or golden or overflow" \
+      > gpurun_out/r2_parity_opt$opt.txt 2>&1; echo "parity opt=$opt rc=$?"
+  timeout 300 python bench.py --steps 2000 --warmup 3 > gpurun_out/r2_bench_opt$opt.json 2> gpurun_out/r2_bench_opt$opt.err; echo "bench opt=$opt rc=$?"
+  timeout 120 python tools/timeline.py 256 > gpurun_out/r2_timeline_opt$opt.txt 2>&1
+  python - <<PY
+import json
+try:
+    j = json.loads(open("gpurun_out/r2_bench_opt$opt.json").read().strip().splitlines()[-1])
+    print("opt=$opt value=%.4g e2e=%.4g ms_per_step=%.5f frac=%.4f" % (j["value"], j["e2e"]["value"], j["ms_per_step"], j["roofline"]["frac"]))
+except Exception as e:
+    print("opt=$opt bench line unreadable:", e)
+PY
+done
+unset DSGD_PERSIST_OPT
