@@ -16,6 +16,7 @@
 #include "dsgd_kernels.cuh"
 #include "dsgd_persistent.cuh"
 #include "dsgd_stream.cuh"
+#include "dsgd_stream_x.cuh"
 #include "dsgd_async.cuh"
 #include <cstdlib>
 
@@ -74,6 +75,11 @@ struct dsgd_ctx {
   unsigned *p_bar = nullptr;   // [0]: barrier counter, [1]: abort flag
   unsigned *p_bar_flags = nullptr;  // DSGD_PERSIST_OPT & 1: release flag lines of the flag barrier
   double *p_push = nullptr;         // DSGD_PERSIST_OPT & 2: pushed partials [2][G][G][2]
+  uint32_t *hot_bits = nullptr;     // DSGD_STREAM_OPT & 2: hot-column bitmap / slot prefix / slot -> column (dsgd_stream.cuh)
+  uint16_t *hot_prefix = nullptr;
+  int32_t *hot_cols = nullptr;
+  int n_hot = 0;
+  bool stream_opt_ready = false;
   bool p_ready = false;
   long long *p_tl = nullptr;   // debug timeline (DSGD_PERSIST_TIMELINE)
 
@@ -276,7 +282,7 @@ extern "C" int dsgd_destroy(dsgd_ctx *ctx) {
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   void *ptrs[] = {ctx->rp16, ctx->pairs, ctx->label, ctx->w, ctx->g, ctx->d, ctx->w_req, ctx->w32, ctx->w32_req, ctx->n_exact, ctx->scal,
                   ctx->cnt, ctx->partial, ctx->out2, ctx->gsum, ctx->p_wbuf[0], ctx->p_wbuf[1], ctx->p_gbuf[0],
-                  ctx->p_gbuf[1], ctx->p_gbuf[2], ctx->p_partial, ctx->p_hinge, ctx->p_bar, ctx->p_bar_flags, ctx->p_push, ctx->samples,
+                  ctx->p_gbuf[1], ctx->p_gbuf[2], ctx->p_partial, ctx->p_hinge, ctx->p_bar, ctx->p_bar_flags, ctx->p_push, ctx->hot_bits, ctx->hot_prefix, ctx->hot_cols, ctx->samples,
                   ctx->losses, ctx->preds};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -562,9 +568,114 @@ static bool stream_eligible(const dsgd_ctx *ctx, int64_t n) {
   return !off && n >= kStreamMinRows && (size_t)ctx->dim * sizeof(float) + 1024 <= 227u * 1024u;
 }
 
+// experimental variants of the streaming kernel (DSGD_STREAM_OPT: 1 = fp32 fast path, 2 = hot-column accumulators for
+// the scatter, 3 = both; dsgd_stream.cuh, kOpt): not the default until measured
+static int stream_opt() {
+  const char *e = getenv("DSGD_STREAM_OPT");
+  const int v = e ? atoi(e) : 0;
+  return (v >= 0 && v <= 3) ? v : 0;
+}
+typedef void (*stream_kernel_t)(const StreamParamsX);
+template <bool kScatter, bool kPreds>
+static stream_kernel_t stream_variant(int opt) {
+  if constexpr (!kScatter) {
+    return k_stream_rows_x<kScatter, kPreds, 1>;
+  } else {
+    switch (opt) {
+      case 2: return k_stream_rows_x<kScatter, kPreds, 2>;
+      case 3: return k_stream_rows_x<kScatter, kPreds, 3>;
+      default: return k_stream_rows_x<kScatter, kPreds, 1>;
+    }
+  }
+}
+// the kHotSlots most frequent columns (over all loaded rows) get a shared-memory slot: bitmap, per-word slot prefix and
+// slot -> column list, built once on the host from the column histogram
+static int stream_hot_prepare(dsgd_ctx *ctx) {
+  if (ctx->hot_bits) return DSGD_OK;
+  unsigned *df = nullptr;
+  CU(cudaMalloc(&df, sizeof(unsigned) * (size_t)ctx->dim));
+  CU(cudaMemsetAsync(df, 0, sizeof(unsigned) * (size_t)ctx->dim, ctx->stream));
+  if (ctx->n_pairs > 0) {
+    const int blocks = (int)std::min<int64_t>(cdiv(ctx->n_pairs, 256), (int64_t)ctx->sm_count * 16);
+    k_col_hist<<<blocks, 256, 0, ctx->stream>>>(ctx->pairs, ctx->n_pairs, df);
+    LAUNCHED();
+  }
+  std::vector<unsigned> hist((size_t)ctx->dim);
+  CU(cudaMemcpyAsync(hist.data(), df, sizeof(unsigned) * (size_t)ctx->dim, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaFree(df));
+  std::vector<int32_t> order((size_t)ctx->dim);
+  for (int j = 0; j < ctx->dim; ++j) order[(size_t)j] = j;
+  const size_t n_hot = std::min<size_t>((size_t)kHotSlots, (size_t)ctx->dim);
+  std::partial_sort(order.begin(), order.begin() + (ptrdiff_t)n_hot, order.end(),
+                    [&](int32_t a, int32_t b) { return hist[(size_t)a] != hist[(size_t)b] ? hist[(size_t)a] > hist[(size_t)b] : a < b; });
+  const size_t words = ((size_t)ctx->dim + 31) / 32;
+  std::vector<uint32_t> bits(words, 0u);
+  for (size_t i = 0; i < n_hot; ++i)
+    if (hist[(size_t)order[i]] > 0) bits[(size_t)order[i] >> 5] |= 1u << (order[i] & 31);
+  std::vector<uint16_t> prefix(words);
+  std::vector<int32_t> cols;
+  for (size_t wd = 0; wd < words; ++wd) {
+    prefix[wd] = (uint16_t)cols.size();
+    for (int b = 0; b < 32; ++b)
+      if (bits[wd] >> b & 1u) cols.push_back((int32_t)(wd * 32 + (size_t)b));   // slot order = column order
+  }
+  if (cols.empty()) cols.push_back(0);
+  CU(cudaMalloc(&ctx->hot_bits, sizeof(uint32_t) * words));
+  CU(cudaMalloc(&ctx->hot_prefix, sizeof(uint16_t) * words));
+  CU(cudaMalloc(&ctx->hot_cols, sizeof(int32_t) * cols.size()));
+  CU(cudaMemcpy(ctx->hot_bits, bits.data(), sizeof(uint32_t) * words, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(ctx->hot_prefix, prefix.data(), sizeof(uint16_t) * words, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(ctx->hot_cols, cols.data(), sizeof(int32_t) * cols.size(), cudaMemcpyHostToDevice));
+  int n = 0;
+  for (size_t wd = 0; wd < words; ++wd) n += __builtin_popcount(bits[wd]);
+  ctx->n_hot = n;
+  return DSGD_OK;
+}
+
 template <bool kScatter, bool kPreds>
 static int stream_launch(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t row_begin, int64_t n, const double *w_dev,
                          const float *w32_dev, double *g, double *preds) {
+  int opt = stream_opt();
+  if (!kScatter) opt &= 1;
+  if ((opt & 2) && stream_smem_bytes(ctx->dim, 2) + 256 > 227u * 1024u) opt &= 1;   // no room for the slots beside the weights
+  if (opt) {
+    if (!ctx->stream_opt_ready) {
+      for (int o = 1; o <= 3; ++o) {
+        CU(cudaFuncSetAttribute((const void *)stream_variant<false, false>(o), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem_bytes(ctx->dim, 0)));
+        CU(cudaFuncSetAttribute((const void *)stream_variant<false, true>(o), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem_bytes(ctx->dim, 0)));
+        const size_t sm = (o & 2) && stream_smem_bytes(ctx->dim, 2) + 256 <= 227u * 1024u ? stream_smem_bytes(ctx->dim, 2) : stream_smem_bytes(ctx->dim, 0);
+        CU(cudaFuncSetAttribute((const void *)stream_variant<true, false>(o), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      }
+      ctx->stream_opt_ready = true;
+    }
+    if (opt & 2) {
+      int rc = stream_hot_prepare(ctx);
+      if (rc) return rc;
+    }
+    // a launch of the hot-column variant covers at most kHotMaxRows rows (limb headroom)
+    const int64_t max_rows = (opt & 2) ? kHotMaxRows : n;
+    for (int64_t off = 0; off < n; off += max_rows) {
+      const int64_t m = std::min<int64_t>(max_rows, n - off);
+      StreamParamsX sp;
+      memset(&sp, 0, sizeof sp);
+      sp.rp16 = ctx->rp16; sp.units = reinterpret_cast<const uint4 *>(ctx->pairs); sp.label = ctx->label;
+      sp.samples = samples_dev ? samples_dev + off : nullptr; sp.row_begin = row_begin + off; sp.n = m;
+      sp.w = w_dev; sp.w32 = w32_dev; sp.dim = ctx->dim;
+      sp.g = g; sp.preds = preds ? preds + off : nullptr; sp.cnt = ctx->cnt; sp.n_exact = ctx->n_exact; sp.next_block = ctx->n_exact + 1;
+      sp.hot_bits = ctx->hot_bits; sp.hot_prefix = ctx->hot_prefix; sp.hot_cols = ctx->hot_cols; sp.n_hot = ctx->n_hot;
+      CU(cudaMemsetAsync(ctx->n_exact + 1, 0, sizeof(unsigned long long), ctx->stream));
+      const int64_t blocks32 = (m + 31) / 32;
+      const int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, cdiv(blocks32, kStreamThreads / 32)));
+      auto *pe = prof_slot(ctx);
+      if (pe) cudaEventRecord(pe->first, ctx->stream);
+      stream_variant<kScatter, kPreds>(opt)<<<grid, kStreamThreads, stream_smem_bytes(ctx->dim, opt), ctx->stream>>>(sp);
+      if (pe) cudaEventRecord(pe->second, ctx->stream);
+      LAUNCHED();
+      CU(cudaGetLastError());
+    }
+    return DSGD_OK;
+  }
   const size_t smem = (size_t)ctx->dim * sizeof(float);
   if (!ctx->stream_ready) {
     CU(cudaFuncSetAttribute(k_stream_rows<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,8 +1,9 @@
 #!/bin/bash
 # Round-2 opener: ONE gpurun call that (1) re-runs the GPU suite, (2) runs the latency microbenchmarks behind the design
 # questions of DESIGN.md section 8, (3) checks parity and measures the bench line for every experimental variant of the
-# persistent kernel (DSGD_PERSIST_OPT, dsgd_persistent.cuh kOpt) and (4) prints CTA 0's step timeline for each.
-#   gpurun --timeout 1500 -- 'bash tools/r2_first_call.sh'
+# persistent kernel (DSGD_PERSIST_OPT, dsgd_persistent.cuh kOpt), (4) prints CTA 0's step timeline for each and (5) does
+# the same parity + bandwidth check for the streaming-pass variants (DSGD_STREAM_OPT, dsgd_stream_x.cuh).
+#   gpurun --timeout 2400 -- 'bash tools/r2_first_call.sh'
 # Everything lands in gpurun_out/r2_*.txt|json.  Nothing here is a bench value of record (bench.py alone is).
 set -u
 cd "$(dirname "$0")/.."
@@ -26,3 +27,12 @@ except Exception as e:
 PY
 done
 unset DSGD_PERSIST_OPT
+# streaming pass variants (dsgd_stream_x.cuh): 1 = fp32 fast path, 2 = hot-column accumulators (scatter), 3 = both
+for opt in 0 1 2 3; do
+  export DSGD_STREAM_OPT=$opt
+  timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_zfullsize.py -q -m gpu \
+      -k "streaming or eval or gradient or zero_weights or additive or shards" > gpurun_out/r2_stream_parity_opt$opt.txt 2>&1
+  echo "stream parity opt=$opt rc=$?"
+  timeout 300 python tools/stream_bw.py > gpurun_out/r2_stream_bw_opt$opt.txt 2>&1; echo "--- DSGD_STREAM_OPT=$opt"; cat gpurun_out/r2_stream_bw_opt$opt.txt
+done
+unset DSGD_STREAM_OPT
