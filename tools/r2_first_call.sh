@@ -15,7 +15,7 @@ for opt in 0 1 2 3; do
   export DSGD_PERSIST_OPT=$opt
   timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_zfullsize.py -q -m gpu -k "trajectory or epoch or golden or overflow" \
       > gpurun_out/r2_parity_opt$opt.txt 2>&1; echo "parity opt=$opt rc=$?"
-  timeout 300 python bench.py --steps 2000 --warmup 3 > gpurun_out/r2_bench_opt$opt.json 2> gpurun_out/r2_bench_opt$opt.err; echo "bench opt=$opt rc=$?"
+  timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_opt$opt.json 2> gpurun_out/r2_bench_opt$opt.err; echo "bench opt=$opt rc=$?"
   timeout 120 python tools/timeline.py 256 > gpurun_out/r2_timeline_opt$opt.txt 2>&1
   python - <<PY
 import json
