@@ -840,6 +840,7 @@ using PSmem = PersistSmem<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks>;
 #define DSGD_PERSIST_KERNEL_MULTI2 k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 1>
 #define DSGD_PERSIST_KERNEL_MULTI k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 2>
 #define DSGD_PERSIST_KERNEL_MULTI3 k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 3>
+#define DSGD_PERSIST_KERNEL_MULTI4 k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 4>  // experimental
 // experimental single-GPU variants (DSGD_PERSIST_OPT=1..3; dsgd_persistent.cuh, kOpt): not the default until measured
 typedef void (*persist_kernel_t)(const PersistParams);
 static persist_kernel_t persist_variant(int opt) {
@@ -870,6 +871,7 @@ static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
     CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL_MULTI, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
     CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL_MULTI2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
     CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL_MULTI3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
+    CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL_MULTI4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
     for (int opt = 1; opt <= 3; ++opt)
       CU(cudaFuncSetAttribute((const void *)persist_variant(opt), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
     CU(cudaMalloc(&ctx->p_bar_flags, sizeof(unsigned) * kBarFlagStride * (size_t)(ctx->sm_count / kBarGroup + 1)));
@@ -942,9 +944,11 @@ static int persist_run(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t n_per_
 // ---- fused multi-GPU loop: all ranks run the persistent kernel and exchange gradients through peer memory ----
 // exported block of a rank: receive area [sender][parity][dim + 8] doubles, then flag words [sender][cta] (u64)
 constexpr int kXFlagCtas = 192;
-static size_t xblk_doubles(const dsgd_ctx *ctx) {  // an LL element is 16 bytes = 2 doubles' worth
+static size_t xblk_llw_offset(const dsgd_ctx *ctx) {  // an LL element is 16 bytes = 2 doubles' worth
   return 2 * (size_t)kMaxWorld * 2 * (size_t)(ctx->dim + kReplicaPad) + (size_t)kMaxWorld * kXFlagCtas;
 }
+// ... followed (DSGD_P2P_MODE=4) by the rank's two LL weight buffers, which the column owners on the peers store into
+static size_t xblk_doubles(const dsgd_ctx *ctx) { return xblk_llw_offset(ctx) + 2 * 2 * (size_t)(ctx->dim + kReplicaPad); }
 
 static int xblk_ensure(dsgd_ctx *ctx) {
   if (ctx->xblk) return DSGD_OK;
@@ -1005,8 +1009,19 @@ static int persist_run_multi(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t 
   // reduction done by the consumers per gathered non-zero, 3 (default) one barrier with LL-word weights
   static const int mode_env = getenv("DSGD_P2P_MODE") ? atoi(getenv("DSGD_P2P_MODE")) : 3;
   // mode 3 updates one column per thread: the CTA's column slice must fit the barrier-synchronised threads
-  const int mode = (mode_env == 3 && cdiv(ctx->dim + 1, G) > (kPCons + kPUpd) * 32) ? 2 : mode_env;
-  void *fn = mode == 1 ? (void *)DSGD_PERSIST_KERNEL_MULTI2 : mode == 2 ? (void *)DSGD_PERSIST_KERNEL_MULTI : (void *)DSGD_PERSIST_KERNEL_MULTI3;
+  const int mode = ((mode_env == 3 || mode_env == 4) && cdiv(ctx->dim + 1, G) > (kPCons + kPUpd) * 32) ? 2 : mode_env;
+  void *fn = mode == 1 ? (void *)DSGD_PERSIST_KERNEL_MULTI2 : mode == 2 ? (void *)DSGD_PERSIST_KERNEL_MULTI
+           : mode == 4 ? (void *)DSGD_PERSIST_KERNEL_MULTI4 : (void *)DSGD_PERSIST_KERNEL_MULTI3;
+  if (mode == 4) {
+    // LL weight buffers live in the exported block so that the column owners on the peers can store into them
+    for (int r = 0; r < ctx->world; ++r) {
+      double *blk = (r == ctx->rank) ? ctx->xblk : ctx->peer_x[r];
+      unsigned long long *llw = reinterpret_cast<unsigned long long *>(blk + xblk_llw_offset(ctx));
+      pp.xllw[r][0] = llw;
+      pp.xllw[r][1] = llw + 2 * (size_t)(ctx->dim + kReplicaPad);
+    }
+    CU(cudaMemcpyAsync(ctx->p_wbuf[0], ctx->w, vd, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
   if (mode == 3) {
     if (!ctx->x_llw) {
       CU(cudaMalloc(&ctx->x_llw, 2 * 2 * sizeof(unsigned long long) * (size_t)(ctx->dim + kReplicaPad)));

@@ -68,7 +68,9 @@ struct PersistParams {
   // ---- experimental variants (template parameter kOpt; not the default path) ----
   unsigned *bar_flags;                         // kOpt & 1: release flags of the grid barrier, one 128-byte line per kBarGroup CTAs, zero on entry
   double *push;                                // kOpt & 2: pushed partials [2 parities][dest CTA][src CTA][2]
+  unsigned long long *xllw[kMaxWorld][2];      // mode 4: every rank's LL weight buffers (inside its exported block); [rank] is local
 };
+static_assert(sizeof(PersistParams) <= 4000, "kernel parameter space is 4 KB");
 
 // ---- PTX helpers: mbarrier + TMA bulk copy -------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -431,6 +433,307 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
       b0 = b1; e0 = e1; y0 = y1;
       load_win(id_next, b1, e1, y1);
       id_next = load_id(t + 3);
+    }
+    return;
+  }
+
+  if constexpr (kMode == 4) {
+    // =======================================================================================================
+    // EXPERIMENTAL (DSGD_P2P_MODE=4; written after the round's GPU budget ran out, never run): mode 3 with COLUMN
+    // OWNERSHIP.  Mode 3 stores every rank's whole dense gradient into every peer ((K-1) * 756 KB per rank and step:
+    // 5.3 MB at K = 8, >= 5.9 us of NVLink time) and every rank repeats the K-way reduction for all columns.  Here rank r
+    // owns columns [r * cpr, (r + 1) * cpr), cpr = ceil(dim / K):
+    //   everybody : push this CTA's column slice of g_{T-1} as LL words (tag T), each column ONLY to its owner
+    //   owners    : (update warps) per owned column: the K replies of step T-1 (own from local g_{T-1}, the peers' from
+    //               the receive area), regularized on their own support and folded in rank order, W_T = W_{T-1} -
+    //               lr*sum/K, stored as an LL word (tag T+1) into the weight buffer of parity T of EVERY rank
+    //   collectors: (update warps, after their owner duty) read W_T over the CTA's slice of ALL columns as the words
+    //               arrive: partials of c_T and ||W_T||^2 in the same order on every rank; zero g_{T+1}'s buffer.  Nobody
+    //               leaves interval T before every owner delivered all of W_T: that is the flow control that keeps
+    //               two receive parities sufficient.
+    //   consumers : as in mode 3 -- one LL gather of W_T[col] per non-zero, spinning on the tag
+    // The packed counter slot [dim] (hinge + 2^32 * samples) still goes to every peer: every rank reports the loss.
+    // Bytes per rank and step: 2 * (K-1)/K * 756 KB (1.3 MB at K = 8) instead of (K-1) * 756 KB.
+    // =======================================================================================================
+    const int K = p.world, me = p.rank;
+    const int slice = (p.dim + 1 + G - 1) / G;   // columns per CTA, plus ONE counter slot [dim] = hinge + 2^32 * samples
+    const int j_lo = min(blockIdx.x * slice, p.dim + 1), j_hi = min(j_lo + slice, p.dim + 1);
+    const int par_stride = p.xstride, snd_stride = 2 * p.xstride;
+    const double lr = p.lr, kd = (double)K;
+    const int64_t base = p.step_base;
+    unsigned phase = 0;
+    const int cpr = (p.dim + K - 1) / K;                                        // columns per owner
+    const int r_lo = min(me * cpr, p.dim), r_hi = min(r_lo + cpr, p.dim);      // this rank's columns
+    const int oslice = (cpr + G - 1) / G;                                       // ... of which this CTA's
+    const int o_lo = min(r_lo + (int)blockIdx.x * oslice, r_hi), o_hi = min(o_lo + oslice, r_hi);
+    const int ut = (int)threadIdx.x - kCons * 32;                               // index among the update threads (< 0: consumer)
+
+    for (int64_t T = base; T <= base + S; ++T) {
+      const int64_t t = T - base;
+      const bool first = (T == base), last = (T == base + S);
+      const unsigned long long *LWprev = p.xllw[me][(T + 1) & 1];  // LL words of W_{T-1}, tag T
+      unsigned long long *LWcur = p.xllw[me][T & 1];               // LL words of W_T, tag T+1
+      const double *Gprev = p.xg[(T + 2) % 3];                // g_{T-1}
+      double *Gcur = p.xg[T % 3];
+      double *Gzero = p.xg[(T + 1) % 3];
+      const int parp = (int)((T + 1) & 1);                    // receive parity of step T-1
+      const unsigned gtag = (unsigned)T;                      // g words of step T-1 carry tag T
+      const unsigned wtag = (unsigned)(T + 1);                // W_T words carry tag T+1
+      const unsigned long long *rcv = reinterpret_cast<const unsigned long long *>(p.xrecv[me]) + 2 * (size_t)parp * par_stride;
+      const double *part_prev = p.partial + (size_t)((T + 1) & 1) * G * 2;   // partials of W_{T-1}
+      double *part_cur = p.partial + (size_t)(T & 1) * G * 2;
+      const unsigned c_par = (unsigned)((t >> 1) & 1);
+      bool ok = true;
+      auto spin_ll = [&](const unsigned long long *src, unsigned tag, double &v) {
+        unsigned spins = 0;
+        const long long t0 = clock64();
+        while (!ll_try_load(src, tag, v)) {
+          if ((++spins & 255u) == 0u && (clock64() - t0 > p.timeout_cycles || *(volatile int *)p.abort_flag)) {
+            *(volatile int *)p.abort_flag = 1;
+            ok = false;
+            v = 0.0;
+            break;
+          }
+        }
+      };
+
+      if (warp == 0) DSGD_TL(0);
+      // ---- push g_{T-1} (every sync warp; one column per thread) ----
+      if (!first) {
+        for (int j = j_lo + threadIdx.x; j < j_hi; j += kSyncThreads) {
+          const double v = __ldcg(&Gprev[j]);
+          const size_t slot = 2 * ((size_t)me * snd_stride + (size_t)parp * par_stride + j);
+          if (j == p.dim) {                                     // counters: to everybody
+            for (int k = 0; k < K; ++k)
+              if (k != me) ll_store(reinterpret_cast<unsigned long long *>(p.xrecv[k]) + slot, v, gtag);
+          } else {
+            const int o = j / cpr;                              // gradient entries: to the column's owner only
+            if (o != me) ll_store(reinterpret_cast<unsigned long long *>(p.xrecv[o]) + slot, v, gtag);
+          }
+        }
+      }
+
+      if (warp == 0) DSGD_TL(1);
+      // ---- c_{T-1}: summed by update warp 0, handed to every sync warp of the CTA through shared memory ----
+      double c_prev = 0.0;                                    // of W_{T-1}
+      if (warp == kCons) {
+        double nrm_prev = 0.0;
+        if (!first) {
+          if (T - 1 == base) {
+            c_prev = p.scal[kScalC];                          // W_base came from the host: k_prepare / previous launch
+            nrm_prev = p.scal[kScalNrm2];
+          } else {
+            double sd, sn;
+            sum_partials2(part_prev, G, lane, sd, sn);
+            c_prev = p.lambda * 2.0 * sd;
+            nrm_prev = sn;
+          }
+        }
+        if (lane == 0) {
+          sm.c_val[t & 1] = c_prev;
+          sm.nrm_val[t & 1] = nrm_prev;                       // ||W_{T-1}||^2 for the loss of step T-1
+          mbar_arrive(&sm.c_bar[t & 1]);
+        }
+        __syncwarp();
+      } else if (is_upd) {                                      // consumers never need c here
+        mbar_wait(&sm.c_bar[t & 1], c_par, p.abort_flag, p.timeout_cycles);
+        c_prev = sm.c_val[t & 1];
+      }
+      if (warp == 0) DSGD_TL(2);
+      // ---- first interval: W_base (plain doubles from the host, identical on every rank) goes into LL form locally ----
+      double pd = 0.0, pn = 0.0;
+      if (first) {
+        const int j = j_lo + threadIdx.x;                     // slice <= kSyncThreads columns (checked on the host)
+        if (j < j_hi) {
+          if (j < p.dim) ll_store(LWcur + 2 * (size_t)j, __ldcg(&p.wbuf[0][j]), wtag);
+          Gzero[j] = 0.0;
+        }
+      } else if (is_upd) {
+        const bool add_c = (c_prev != 0.0) && (fabs(c_prev) > kEps);
+        // ---- owner duty: reduce the K replies of every owned column of this CTA, update, deliver W_T to every rank ----
+        for (int jo = o_lo + ut; jo < o_hi; jo += kUpd * 32) {
+          double raw[kMaxWorld];
+          bool got[kMaxWorld];
+          double wn = 0.0;
+          bool got_w = ll_try_load(LWprev + 2 * (size_t)jo, gtag, wn);            // own word of W_{T-1}[jo] carries tag T
+#pragma unroll
+          for (int k = 0; k < kMaxWorld; ++k) {
+            got[k] = true;
+            raw[k] = 0.0;
+            if (k < K) {
+              if (k == me) raw[k] = __ldcg(&Gprev[jo]);
+              else got[k] = ll_try_load(rcv + 2 * ((size_t)k * snd_stride + jo), gtag, raw[k]);
+            }
+          }
+          if (!got_w) spin_ll(LWprev + 2 * (size_t)jo, gtag, wn);
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < kMaxWorld; ++k) {
+            if (k < K) {
+              if (!got[k]) spin_ll(rcv + 2 * ((size_t)k * snd_stride + jo), gtag, raw[k]);
+              double v = filt(raw[k]);
+              if (v != 0.0 && add_c) v = filt(v + c_prev);
+              s = (k == 0) ? v : filt(s + v);
+            }
+          }
+          if (s != 0.0) {
+            const double mean = filt(s / kd);
+            const double step = filt(mean * lr);
+            wn = filt(wn - step);
+          }
+          for (int k = 0; k < K; ++k) ll_store(p.xllw[k][T & 1] + 2 * (size_t)jo, wn, wtag);   // [me] is LWcur
+        }
+        // ---- collector duty: W_T over the CTA's slice of ALL columns, as the owners' words arrive ----
+        for (int j = j_lo + ut; j < j_hi; j += kUpd * 32) {
+          if (j == p.dim) {
+            double s = 0.0;                                     // packed counters of step T-1: plain sum over the ranks
+            for (int k = 0; k < K; ++k) {
+              double v;
+              if (k == me) v = __ldcg(&Gprev[j]);
+              else spin_ll(rcv + 2 * ((size_t)k * snd_stride + j), gtag, v);
+              s += v;
+            }
+            if (p.losses) {  // loss of step T-1 on W_{T-1}
+              const double ns = floor(s / 4294967296.0);
+              p.losses[t - 1] = p.lambda * sm.nrm_val[t & 1] + (s - ns * 4294967296.0) / ns;
+            }
+          } else {
+            double wn;
+            spin_ll(LWcur + 2 * (size_t)j, wtag, wn);
+            pd += filt(wn * __ldg(&p.d[j]));
+            pn += wn * wn;
+          }
+          Gzero[j] = 0.0;
+        }
+      }
+      pd = warp_sum(pd);
+      pn = warp_sum(pn);
+      if (lane == 0) { sm.red_all[warp][0] = pd; sm.red_all[warp][1] = pn; }   // summed by thread 0 before the grid barrier
+      if (warp == 0) DSGD_TL(3);
+
+      if (is_cons) {
+        if (!last) {
+          const int st = (int)(t % kStages);
+          auto &mt = sm.meta[st];
+          mbar_wait(&sm.full[st], (unsigned)((t / kStages) & 1), p.abort_flag, p.timeout_cycles);
+          if (warp == 0) DSGD_TL(4);
+          const int n_ch = mt.n_chunks;
+          const uint2 *ring = &sm.ring[st][0];
+          for (int c = warp; c < n_ch; c += kCons) {
+            const uint32_t off = mt.ch_off[c];
+            const int n = mt.ch_n[c];
+            const uint2 *src = (off & kChunkGlobal) ? (p.pairs + (off & ~kChunkGlobal)) : (ring + off);
+            uint2 pr[4];
+            double wv[4];
+            bool got[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int k = u * 32 + lane;
+              pr[u] = (k < n) ? src[k] : make_uint2(0u, 0u);   // col 0 / val 0: inert, still a valid gather
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) got[u] = ll_try_load(LWcur + 2 * (size_t)pr[u].x, wtag, wv[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (!got[u]) spin_ll(LWcur + 2 * (size_t)pr[u].x, wtag, wv[u]);
+            double acc = 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc += filt(filt((double)__uint_as_float(pr[u].y)) * wv[u]);
+            acc = warp_sum(acc);
+            if (lane == 0) mt.part[c] = acc;
+          }
+          if (warp == 0) DSGD_TL(5);
+          named_bar_sync(2, kCons * 32);
+          unsigned hinge = 0;
+          for (int c = warp; c < n_ch; c += kCons) {
+            const int row = mt.ch_row[c];
+            const int firstc = mt.row_first[row], nch = mt.row_nch[row];
+            double dot = 0.0;
+            for (int i = 0; i < nch; ++i) dot += mt.part[firstc + i];
+            const int yi = mt.row_y[row];
+            const double y = (double)yi;
+            if (c == firstc && lane == 0) hinge += (unsigned)(1 - yi * ((dot > 0.0) ? -1 : ((dot < 0.0) ? 1 : 0)));
+            if (!(y * dot < 0.0)) {
+              const uint32_t off = mt.ch_off[c];
+              const int n = mt.ch_n[c];
+              const uint2 *src = (off & kChunkGlobal) ? (p.pairs + (off & ~kChunkGlobal)) : (ring + off);
+              for (int k = lane; k < n; k += 32) {
+                const uint2 pr = src[k];
+                const double gvv = filt(filt((double)__uint_as_float(pr.y)) * y);
+                if (gvv != 0.0) atomicAdd(&Gcur[pr.x], gvv);
+              }
+            }
+          }
+          for (int m = warp; m < mt.n_rows; m += kCons) {
+            const int nch = mt.row_nch[m];
+            if (nch == 0) {
+              if (lane == 0) hinge += 1u;
+            } else if (nch < 0) {  // row outside the chunk list: whole row from global memory
+              const uint2 *grow = p.pairs + (size_t)mt.row_b[m] * 2;
+              const int len = mt.row_len[m];
+              double acc = 0.0;
+              for (int k = lane; k < len; k += 32) {
+                const uint2 pr = __ldg(&grow[k]);
+                double wv;
+                spin_ll(LWcur + 2 * (size_t)pr.x, wtag, wv);
+                acc += filt(filt((double)__uint_as_float(pr.y)) * wv);
+              }
+              const double dot = warp_sum(acc);
+              const int yi = mt.row_y[m];
+              const double y = (double)yi;
+              if (lane == 0) hinge += (unsigned)(1 - yi * ((dot > 0.0) ? -1 : ((dot < 0.0) ? 1 : 0)));
+              if (!(y * dot < 0.0))
+                for (int k = lane; k < len; k += 32) {
+                  const uint2 pr = __ldg(&grow[k]);
+                  const double gvv = filt(filt((double)__uint_as_float(pr.y)) * y);
+                  if (gvv != 0.0) atomicAdd(&Gcur[pr.x], gvv);
+                }
+            }
+          }
+          if (lane == 0 && hinge) atomicAdd(&sm.hinge_acc, hinge);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.empty[st]);
+          if (warp == 0) DSGD_TL(8);
+        }
+      }
+      if (!ok) *(volatile int *)&sm.ok = 0;
+      // ---- grid barrier T (the CTA's hinge total and batch ride in slot [dim] of g_T) ----
+      named_bar_sync(3, kSyncThreads);
+      if (*(volatile int *)&sm.ok == 0) { *(volatile int *)p.abort_flag = 1; }
+      if (threadIdx.x == 0 && !first) {   // per-CTA partials of c_T, ||W_T||^2: warps in index order (deterministic)
+        double sd = 0.0, sn = 0.0;
+#pragma unroll
+        for (int i = 0; i < kCons + kUpd; ++i) { sd += sm.red_all[i][0]; sn += sm.red_all[i][1]; }
+        part_cur[2 * blockIdx.x] = sd;
+        part_cur[2 * blockIdx.x + 1] = sn;
+      }
+      if (threadIdx.x == 0 && !last) {
+        const unsigned h = sm.hinge_acc;
+        if (h) { atomicAdd(&Gcur[p.dim], (double)h); sm.hinge_acc = 0u; }
+        if (blockIdx.x == 0) atomicAdd(&Gcur[p.dim], (double)B * 4294967296.0);
+      }
+      ++phase;
+      if (!grid_barrier(p.bar, phase * (unsigned)G, p.abort_flag, p.timeout_cycles, &sm.ok, kSyncThreads,
+                        (p.tl && blockIdx.x == 0 && t < 256) ? p.tl + t * 16 + 6 : nullptr))
+        return;
+      if (*(volatile int *)p.abort_flag) return;
+    }
+    // epilogue: W_{base+S} sits in LL form (tag base+S+1) in llw[(base+S) & 1]; publish it as plain resident weights
+    {
+      const unsigned long long *LW = p.xllw[me][(base + S) & 1];
+      const unsigned wtag = (unsigned)(base + S + 1);
+      const int n_all = G * kSyncThreads;
+      for (int j = blockIdx.x * kSyncThreads + threadIdx.x; j < p.dim; j += n_all) {
+        double wv = 0.0;
+        ll_try_load(LW + 2 * (size_t)j, wtag, wv);             // complete: written before the last grid barrier
+        p.w_out[j] = wv;
+        p.w32_out[j] = (float)wv;
+      }
+      if (blockIdx.x == 0 && warp == 0 && S > 0) {
+        double sd, sn;
+        sum_partials2(p.partial + (size_t)((base + S) & 1) * G * 2, G, lane, sd, sn);
+        if (lane == 0) { p.scal[kScalC] = p.lambda * 2.0 * sd; p.scal[kScalNrm2] = sn; }
+      }
     }
     return;
   }
