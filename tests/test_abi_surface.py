@@ -53,3 +53,28 @@ def test_product_never_imports_the_oracle():
             elif f.endswith((".cu", ".cuh", ".c", ".h")):
                 assert not pat_c.search(open(path).read()), f"{path} includes the oracle"
     assert "oracle" not in open(os.path.join(pkg, "csrc", "Makefile")).read()
+
+
+def test_jni_shim_type_checks_and_covers_every_native(tmp_path):
+    """distributed_sgd_b200/jni/dsgd_jni.c against include/dsgd.h through a stand-in jni.h (no JDK in the image): it
+    compiles warning-free, and it exports exactly one Java_..._<name> per `@native def` of DsgdNative.scala."""
+    import re
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    obj = str(tmp_path / "dsgd_jni.o")
+    subprocess.run([cc, "-std=gnu11", "-Wall", "-Wextra", "-Wno-unused-parameter", "-Werror", "-fPIC", "-DDSGD_HAVE_JNI",
+                    "-I" + os.path.join(root, "tests", "jni_mock"), "-I" + os.path.join(root, "include"), "-c",
+                    os.path.join(root, "distributed_sgd_b200", "jni", "dsgd_jni.c"), "-o", obj], check=True)
+    syms = subprocess.run(["nm", "-g", "--defined-only", obj], check=True, capture_output=True, text=True).stdout
+    exported = {m.group(1) for m in re.finditer(r" T Java_epfl_distributed_nativ_DsgdNative_00024_(\w+)", syms)}
+    scala = open(os.path.join(root, "distributed_sgd_b200", "jni", "DsgdNative.scala")).read()
+    natives = set(re.findall(r"@native def (\w+)\(", scala))
+    assert natives and exported == natives
+    undefined = subprocess.run(["nm", "-u", obj], check=True, capture_output=True, text=True).stdout
+    called = set(re.findall(r"U (dsgd_\w+)", undefined))
+    header = open(os.path.join(root, "include", "dsgd.h")).read()
+    assert called and all(re.search(r"\b%s\(" % c, header) for c in called)     # only functions the header declares
