@@ -3,15 +3,19 @@
 # questions of DESIGN.md section 8, (3) checks parity and measures the bench line for every experimental variant of the
 # persistent kernel (DSGD_PERSIST_OPT, dsgd_persistent.cuh kOpt), (4) prints CTA 0's step timeline for each and (5) does
 # the same parity + bandwidth check for the streaming-pass variants (DSGD_STREAM_OPT, dsgd_stream_x.cuh).
-#   gpurun --timeout 2400 -- 'bash tools/r2_first_call.sh'
+#   gpurun --timeout 2400 -- 'bash tools/r2_first_call.sh'            # everything, ~35 GPU-minutes
+#   gpurun --timeout 900  -- 'bash tools/r2_first_call.sh micro persist'   # sections: tests micro persist stream
 # Everything lands in gpurun_out/r2_*.txt|json.  Nothing here is a bench value of record (bench.py alone is).
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
+SECTIONS="${*:-tests micro persist stream}"
+want() { case " $SECTIONS " in *" $1 "*) return 0;; *) return 1;; esac; }
 [ -x tools/microbench ] || (cd tools && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o microbench microbench.cu)
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_tests.txt 2>&1; echo "gpu tests rc=$?"; tail -3 gpurun_out/r2_tests.txt
-timeout 300 ./tools/microbench > gpurun_out/r2_microbench.txt 2>&1; echo "microbench rc=$?"
+if want tests; then timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_tests.txt 2>&1; echo "gpu tests rc=$?"; tail -3 gpurun_out/r2_tests.txt; fi
+if want micro; then timeout 300 ./tools/microbench > gpurun_out/r2_microbench.txt 2>&1; echo "microbench rc=$?"; tail -25 gpurun_out/r2_microbench.txt; fi
 for opt in 0 1 2 3; do
+  want persist || break
   export DSGD_PERSIST_OPT=$opt
   timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_zfullsize.py -q -m gpu -k "trajectory or epoch or golden or overflow" \
       > gpurun_out/r2_parity_opt$opt.txt 2>&1; echo "parity opt=$opt rc=$?"
@@ -29,6 +33,7 @@ done
 unset DSGD_PERSIST_OPT
 # streaming pass variants (dsgd_stream_x.cuh): 1 = fp32 fast path, 2 = hot-column accumulators (scatter), 3 = both
 for opt in 0 1 2 3; do
+  want stream || break
   export DSGD_STREAM_OPT=$opt
   timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_zfullsize.py -q -m gpu \
       -k "streaming or eval or gradient or zero_weights or additive or shards" > gpurun_out/r2_stream_parity_opt$opt.txt 2>&1
