@@ -848,13 +848,17 @@ static persist_kernel_t persist_variant(int opt) {
     case 1: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 0, 1>;
     case 2: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 0, 2>;
     case 3: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 0, 3>;
+    case 4: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 0, 4>;
+    case 5: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 0, 5>;
+    case 6: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 0, 6>;
+    case 7: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 0, 7>;
     default: return DSGD_PERSIST_KERNEL;
   }
 }
 static int persist_opt() {
   const char *e = getenv("DSGD_PERSIST_OPT");
   const int v = e ? atoi(e) : 0;
-  return (v >= 0 && v <= 3) ? v : 0;
+  return (v >= 0 && v <= 7) ? v : 0;
 }
 
 static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
@@ -872,7 +876,7 @@ static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
     CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL_MULTI2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
     CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL_MULTI3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
     CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL_MULTI4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
-    for (int opt = 1; opt <= 3; ++opt)
+    for (int opt = 1; opt <= 7; ++opt)
       CU(cudaFuncSetAttribute((const void *)persist_variant(opt), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
     CU(cudaMalloc(&ctx->p_bar_flags, sizeof(unsigned) * kBarFlagStride * (size_t)(ctx->sm_count / kBarGroup + 1)));
     CU(cudaMalloc(&ctx->p_push, sizeof(double) * 2 * 2 * (size_t)ctx->sm_count * (size_t)ctx->sm_count));

@@ -322,7 +322,8 @@ struct PersistSmem {
     if (p.tl && blockIdx.x == 0 && lane == 0 && t < 256) p.tl[t * 16 + (slot_)] = clock64(); \
   } while (0)
 
-// kOpt (mode 0 only): bit 0 = grid_barrier_flags instead of grid_barrier; bit 1 = per-CTA partials of c / ||w||^2 are
+// kOpt (mode 0 only): bit 2 = single-chunk rows are gated and scattered inside pass 1 (no partial, no second pass);
+// bit 0 = grid_barrier_flags instead of grid_barrier; bit 1 = per-CTA partials of c / ||w||^2 are
 // PUSHED to a private area of every CTA instead of 148 CTAs reading the same 2.4 KB (measured: c is handed over 1 880
 // cycles after the barrier).  Same values summed in the same order: results are bit-identical to kOpt == 0.
 template <int kCons, int kUpd, int kStages, int kStagePairs, int kMaxChunks, int kMode, int kOpt = 0>
@@ -1579,6 +1580,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
           }
         };
         // ---- pass 1: partial dots of this warp's chunks ----
+        [[maybe_unused]] unsigned hinge_early = 0;
         for (int c = warp; c < n_ch; c += kCons) {
           const uint32_t off = mt.ch_off[c];
           const int n = mt.ch_n[c];
@@ -1609,15 +1611,40 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
             acc += filt(xv * wt);  // (x * w).sum  (math/Vec.scala:58)
           }
           acc = warp_sum(acc);
+          if constexpr (kOpt & 4) {
+            // a row that is ONE chunk (<= 128 pairs: ~85 % of the rows) is complete in this warp: gate and scatter from
+            // the registers that still hold its pairs, no partial, no second pass (same dot: 0.0 + acc == acc)
+            const int row1 = mt.ch_row[c];
+            if (mt.row_nch[row1] == 1) {
+              const int yi = mt.row_y[row1];
+              const double y = (double)yi;
+              if (lane == 0) {
+                const int pred = (acc > 0.0) ? -1 : ((acc < 0.0) ? 1 : 0);
+                hinge_early += (unsigned)(1 - yi * pred);
+              }
+              if (!(y * acc < 0.0)) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const double gvv = filt(filt((double)__uint_as_float(pr[u].y)) * y);   // lanes past the chunk hold val 0
+                  if (gvv != 0.0) atomicAdd(&Gcur[pr[u].x], gvv);
+                }
+              }
+              continue;
+            }
+          }
           if (lane == 0) mt.part[c] = acc;
         }
         if (warp == 0) DSGD_TL(2);
         named_bar_sync(2, kCons * 32);
         // ---- pass 2: row dot (chunk partials in order), prediction, gate, scatter ----
         unsigned hinge = 0;
+        if constexpr (kOpt & 4) hinge = hinge_early;
         for (int c = warp; c < n_ch; c += kCons) {
           const int row = mt.ch_row[c];
           const int first = mt.row_first[row], nch = mt.row_nch[row];
+          if constexpr (kOpt & 4) {
+            if (nch == 1) continue;   // done in pass 1
+          }
           double dot = 0.0;
           for (int i = 0; i < nch; ++i) dot += mt.part[first + i];
           const int yi = mt.row_y[row];

@@ -14,7 +14,7 @@ want() { case " $SECTIONS " in *" $1 "*) return 0;; *) return 1;; esac; }
 [ -x tools/microbench ] || (cd tools && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o microbench microbench.cu)
 if want tests; then timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_tests.txt 2>&1; echo "gpu tests rc=$?"; tail -3 gpurun_out/r2_tests.txt; fi
 if want micro; then timeout 300 ./tools/microbench > gpurun_out/r2_microbench.txt 2>&1; echo "microbench rc=$?"; tail -25 gpurun_out/r2_microbench.txt; fi
-for opt in 0 1 2 3; do
+for opt in 0 1 2 4 7; do   # bit 0 flag barrier, bit 1 pushed partials, bit 2 one-pass single-chunk rows; 7 = all
   want persist || break
   export DSGD_PERSIST_OPT=$opt
   timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_zfullsize.py -q -m gpu -k "trajectory or epoch or golden or overflow" \
