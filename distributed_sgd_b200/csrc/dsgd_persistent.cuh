@@ -1345,7 +1345,6 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
     // columns per CTA, plus ONE counter slot [dim] = hinge total + 2^32 * sample count (exact in fp64)
     const int slice = (p.dim + 1 + G - 1) / G;
     const int j_lo = min(blockIdx.x * slice, p.dim + 1), j_hi = min(j_lo + slice, p.dim + 1);
-    const int cnt_owner = p.dim / slice;                          // the CTA whose slice holds slot [dim]
     const int n_all = G * kSyncThreads;
     const int a0 = blockIdx.x * kSyncThreads + threadIdx.x;
     const int par_stride = p.xstride, snd_stride = 2 * p.xstride;
