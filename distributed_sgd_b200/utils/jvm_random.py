@@ -45,3 +45,13 @@ class JvmRandom:
             raise RuntimeError(f"dsgd_jvm_sync_epoch failed ({got})")
         out = out.reshape(steps, n_groups, batch_size)
         return [[out[s, k][out[s, k] >= 0].copy() for k in range(n_groups)] for s in range(steps)]
+
+    def async_draws(self, assigned, n_updates: int, batch_size: int = 1) -> np.ndarray:
+        """The row ids n_updates iterations of Slave.asyncTask draw (core/Slave.scala:83-88): batch 1 is
+        `assignedSamples(Random.nextInt(size))`; batch > 1 is `Random.shuffle(assignedSamples.indices) take batchSize`, i.e.
+        POSITIONS used as row ids (quirk Q6).  Feed the result to `NativeCtx.async_replay` (one lane, deterministic)."""
+        assigned = np.ascontiguousarray(assigned, dtype=np.int32)
+        if batch_size == 1:
+            return np.array([assigned[self.next_int(assigned.size)] for _ in range(n_updates)], dtype=np.int32)
+        pos = np.arange(assigned.size, dtype=np.int32)
+        return np.concatenate([self.shuffle(pos)[:batch_size] for _ in range(n_updates)]).astype(np.int32)

@@ -199,3 +199,14 @@ def test_master_sync_jvm_exact_draws():
     ref = JvmRandom(0).sync_epoch(12, 2, 3)
     got = np.concatenate([s.reshape(-1) for s in steps]).tolist()
     assert got == [int(i) for st in ref for g in st for i in g]
+
+
+def test_jvm_async_draws():
+    from distributed_sgd_b200.utils.jvm_random import JvmRandom
+    assigned = np.arange(100, 200, dtype=np.int32)
+    a, b = JvmRandom(0), JvmRandom(0)
+    assert a.async_draws(assigned, 5).tolist() == [100 + b.next_int(100) for _ in range(5)] == [160, 148, 129, 147, 115]
+    a, b = JvmRandom(3), JvmRandom(3)
+    d = a.async_draws(assigned, 4, batch_size=7)                       # positions, not ids (quirk Q6)
+    assert d.shape == (28,) and d.max() < 100
+    assert d[:7].tolist() == b.shuffle(np.arange(100))[:7].tolist()
