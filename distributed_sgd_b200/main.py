@@ -22,7 +22,7 @@ import numpy as np
 
 
 def scenario(cfg, data, *, rank: int = 0, world: int = 1, device: Optional[int] = None, seed: int = 0, log=print,
-             async_concurrency: int = 64) -> dict:
+             async_concurrency: int = 64, jvm_exact: bool = False) -> dict:
     from . import EarlyStopping, Master, Slave, SparseSVM
     from .core import Group
 
@@ -30,7 +30,7 @@ def scenario(cfg, data, *, rank: int = 0, world: int = 1, device: Optional[int] 
     model = SparseSVM(cfg.lam)                                                 # dimSparsity: computed by the Slave on the device
     slave = Slave(rank, 0, train, model, cfg.is_async, world=world, device=device, test_data=test)
     master = Master.create(rank, train, test, model, cfg.is_async, cfg.node_count, slave=slave, group=Group(), seed=seed,
-                           log=(log if rank == 0 else None))
+                           log=(log if rank == 0 else None), jvm_exact=jvm_exact)
     w0 = np.zeros(data.dim)                                                    # data(0)._1.zerosLike (Main.scala:74)
     report = {"config": {k: getattr(cfg, k) for k in ("batch_size", "learning_rate", "lam", "node_count", "is_async",
                                                       "max_epochs", "check_every", "leaky_loss", "patience", "conv_delta")},
@@ -62,6 +62,8 @@ def main(argv=None) -> int:
     ap.add_argument("--conf", default=None, help="application.conf (HOCON `dsgd { }` block); DSGD_* variables override")
     ap.add_argument("--synthetic-rows", type=int, default=0, help="use RCV1-shaped synthetic rows instead of data-path")
     ap.add_argument("--seed", type=int, default=0)                            # Random.setSeed(0) (Main.scala:32)
+    ap.add_argument("--jvm-exact", action="store_true",
+                    help="sync mode: draw the batches from java.util.Random(seed) + Scala's Random.shuffle like the reference")
     args = ap.parse_args(argv)
     from .utils import load_config, rcv1, synthetic_rcv1
 
@@ -74,7 +76,7 @@ def main(argv=None) -> int:
     cfg = load_config(args.conf)
     data = synthetic_rcv1(n_rows=args.synthetic_rows, seed=args.seed) if args.synthetic_rows else rcv1(cfg.data_path, full=cfg.full)
     report = scenario(cfg, data, rank=rank, world=world, device=local_rank, seed=args.seed,
-                      log=lambda s: print(s, flush=True))
+                      log=lambda s: print(s, flush=True), jvm_exact=args.jvm_exact)
     if rank == 0:
         print(json.dumps(report))
     if world > 1:
