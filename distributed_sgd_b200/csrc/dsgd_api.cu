@@ -539,6 +539,7 @@ extern "C" int dsgd_stage_samples(dsgd_ctx *ctx, const int32_t *samples, int64_t
 // weights to use for a request: NULL -> resident; else copy into w_req and compute its scalars
 static int request_weights(dsgd_ctx *ctx, const double *w, const double **w_dev, const double **c_dev,
                            const double **nrm_dev, const float **w32_dev = nullptr) {
+  CU(cudaSetDevice(ctx->device));  // every request path passes here: a caller thread may have another device current
   if (!w) {
     *w_dev = ctx->w; *c_dev = ctx->scal + kScalC; *nrm_dev = ctx->scal + kScalNrm2;
     if (w32_dev) *w32_dev = ctx->w32;
