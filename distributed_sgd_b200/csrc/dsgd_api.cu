@@ -1356,7 +1356,9 @@ static int async_launch(dsgd_ctx *ctx, const double *w0, const int32_t *assigned
   CU(cudaStreamSynchronize(ctx->stream));  // inputs in place before the loop's own stream starts
   if (!ctx->a_ev0) { CU(cudaEventCreate(&ctx->a_ev0)); CU(cudaEventCreate(&ctx->a_ev1)); }
   CU(cudaEventRecord(ctx->a_ev0, st));
-  k_async_worker<<<cdiv(lanes, 4), 128, 0, st>>>(ap);
+  static const bool b1_fast = getenv("DSGD_ASYNC_OPT") && atoi(getenv("DSGD_ASYNC_OPT")) == 1;   // experimental, see dsgd_async.cuh
+  if (b1_fast && batch == 1) k_async_worker_b1<<<cdiv(lanes, 4), 128, 0, st>>>(ap);
+  else k_async_worker<<<cdiv(lanes, 4), 128, 0, st>>>(ap);
   CU(cudaEventRecord(ctx->a_ev1, st));
   LAUNCHED();
   CU(cudaGetLastError());

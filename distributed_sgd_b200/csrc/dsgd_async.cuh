@@ -162,6 +162,74 @@ __global__ void __launch_bounds__(128) k_async_worker(const AsyncParams p) {
   }
 }
 
+// EXPERIMENTAL (DSGD_ASYNC_OPT=1, batch 1 only; written after the round's GPU budget ran out, never run): the same loop
+// body without the per-lane scratch vector.  With one sample per iteration the batch sum IS the row's backward, so the
+// delta of every non-zero is formed straight from the pair: two dependent L2 round trips (scratch write + read-back and
+// claim) leave the per-update latency chain, and throughput here is lanes / latency.  Same arithmetic as the general
+// path for B = 1 (sum = 0 + y*x, mean = sum / 1.0); requires unique columns within a row, like the reference's Map rows.
+__global__ void __launch_bounds__(128) k_async_worker_b1(const AsyncParams p) {
+  const int lane = threadIdx.x & 31;
+  const int lane_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (lane_id >= p.n_lanes) return;
+  double *w = p.replica[0];
+  unsigned long long rng = p.seed * 0xD1342543DE82EF95ull + 0x632BE59BD9B4E019ull * (unsigned long long)(lane_id + 1);
+
+  for (;;) {
+    if (*p.stop) break;
+    unsigned long long it = 0;
+    if (lane == 0) it = atomicAdd(p.claimed, 1ull);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    if (p.max_updates > 0 && it >= (unsigned long long)p.max_updates) break;
+
+    // ---- 1. the sample: data(assignedSamples(Random.nextInt(size)))  (core/Slave.scala:84) ----
+    int32_t r = 0;
+    if (lane == 0) r = p.replay ? p.replay[it] : p.assigned[mix64(rng) % (unsigned long long)p.n_assigned];
+    r = __shfl_sync(0xffffffffu, r, 0);
+    const int64_t s0 = (int64_t)p.rp16[r] * 2, s1 = (int64_t)p.rp16[r + 1] * 2;
+    const double y = (double)p.label[r];
+
+    // ---- 2. c from the replica's running S = w . d ----
+    const double S = *(volatile double *)&w[p.dim + kCtlS];
+    const double c = p.lambda * 2.0 * S;
+    const bool add_c = (c != 0.0) && (fabs(c) > kEps);
+
+    // ---- 3. backward against the current replica ----
+    double dot = 0.0;
+    for (int64_t k = s0 + lane; k < s1; k += 32) {
+      const uint2 pr = p.pairs[k];
+      dot += filt(filt((double)__uint_as_float(pr.y)) * __ldcg(&w[pr.x]));
+    }
+    dot = warp_sum(dot);
+
+    // ---- 4. delta = lr * regularize(y * x / 1, w); apply to every replica ----
+    double sd = 0.0;
+    if (!(y * dot < 0.0)) {  // SparseSVM.scala:28
+      for (int64_t k = s0 + lane; k < s1; k += 32) {
+        const uint2 pr = p.pairs[k];
+        const double xv = filt((double)__uint_as_float(pr.y));
+        if (xv == 0.0) continue;                        // padding pair (or an explicit zero): no key
+        double m = filt(filt(xv * y) / 1.0);            // Vec.sum of one vector, Vec.mean = sum / size
+        if (m != 0.0 && add_c) m = filt(m + c);
+        const double delta = filt(m * p.lr);
+        if (delta != 0.0) {
+          for (int q = 0; q < p.n_replicas; ++q) atomicAdd_system(&p.replica[q][pr.x], -delta);
+          sd += delta * p.d[pr.x];
+        }
+      }
+    }
+    sd = warp_sum(sd);
+    if (lane == 0) {
+      if (sd != 0.0)
+        for (int q = 0; q < p.n_replicas; ++q) atomicAdd_system(&p.replica[q][p.dim + kCtlS], -sd);
+      if (p.master_slot >= 0)
+        atomicAdd_system(reinterpret_cast<unsigned long long *>(&p.replica[p.master_slot][p.dim + kCtlUpdates]), 1ull);
+      __threadfence_system();
+      atomicAdd(p.done, 1ull);
+    }
+    __syncwarp();
+  }
+}
+
 // weights -= delta for a sparse delta, keeping S in step (core/Slave.scala:177-185; core/ml/GradState.scala:8)
 __global__ void __launch_bounds__(256) k_async_apply_delta(double *__restrict__ w, int dim, const double *__restrict__ d,
                                                            const int32_t *__restrict__ idx,

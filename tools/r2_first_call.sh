@@ -4,12 +4,12 @@
 # persistent kernel (DSGD_PERSIST_OPT, dsgd_persistent.cuh kOpt), (4) prints CTA 0's step timeline for each and (5) does
 # the same parity + bandwidth check for the streaming-pass variants (DSGD_STREAM_OPT, dsgd_stream_x.cuh).
 #   gpurun --timeout 2400 -- 'bash tools/r2_first_call.sh'            # everything, ~35 GPU-minutes
-#   gpurun --timeout 900  -- 'bash tools/r2_first_call.sh micro persist'   # sections: tests micro persist stream
+#   gpurun --timeout 900  -- 'bash tools/r2_first_call.sh micro persist'   # sections: tests micro persist stream async
 # Everything lands in gpurun_out/r2_*.txt|json.  Nothing here is a bench value of record (bench.py alone is).
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-SECTIONS="${*:-tests micro persist stream}"
+SECTIONS="${*:-tests micro persist stream async}"
 want() { case " $SECTIONS " in *" $1 "*) return 0;; *) return 1;; esac; }
 [ -x tools/microbench ] || (cd tools && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o microbench microbench.cu)
 if want tests; then timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_tests.txt 2>&1; echo "gpu tests rc=$?"; tail -3 gpurun_out/r2_tests.txt; fi
@@ -41,3 +41,19 @@ for opt in 0 1 2 3; do
   timeout 300 python tools/stream_bw.py > gpurun_out/r2_stream_bw_opt$opt.txt 2>&1; echo "--- DSGD_STREAM_OPT=$opt"; cat gpurun_out/r2_stream_bw_opt$opt.txt
 done
 unset DSGD_STREAM_OPT
+# async batch-1 fast path (k_async_worker_b1, DSGD_ASYNC_OPT=1)
+for opt in 0 1; do
+  want async || break
+  export DSGD_ASYNC_OPT=$opt
+  timeout 300 python -m pytest tests/test_gpu_async.py -q -m gpu > gpurun_out/r2_async_parity_opt$opt.txt 2>&1; echo "async parity opt=$opt rc=$?"
+  timeout 300 python bench.py --mode async --steps 5 --warmup 3 > gpurun_out/r2_bench_async_opt$opt.json 2> gpurun_out/r2_bench_async_opt$opt.err
+  python - <<PY
+import json
+try:
+    j = json.loads(open("gpurun_out/r2_bench_async_opt$opt.json").read().strip().splitlines()[-1])
+    print("async opt=$opt value=%.4g e2e=%.4g" % (j["value"], j["e2e"]["value"]))
+except Exception as e:
+    print("async opt=$opt bench line unreadable:", e)
+PY
+done
+unset DSGD_ASYNC_OPT
