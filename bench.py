@@ -10,13 +10,23 @@ slice of the reference's fit loop (core/Master.scala:179): SGD_STEPS consecutive
 (gradient -> aggregate -> update), every one on weights produced by the previous one.  samples/sec counts
 the samples all GPUs consumed.
 
-Numbers on the JSON line:
+Keys of the JSON line (one line on stdout, rank 0):
   value        device-resident: sample ids staged in HBM before the timed region; CUDA events on the
                launch stream; max over ranks.
   e2e          the same work through the public C-ABI call with HOST buffers (dsgd_sync_steps): per bench
                step the sample ids go host->device from pinned memory and the per-batch losses come back.
-  roofline     the gradient kernel: algorithmic bytes (8*nnz + 16 per sample) per launch /
-               its mean duration (CUDA events around sampled launches), against MEASURED_PEAKS.json.
+  e2e_fit      the same metric through the reference-shaped driver MasterSync.fit (core/Master.scala:120-218):
+               per-epoch batch draws on the host, the step loop, the four per-epoch evaluations, the weight read-back.
+  roofline     the dominant kernel: algorithmic bytes (8*nnz + 16 per sample) per launch /
+               its mean duration (CUDA events around its launches), against MEASURED_PEAKS.json.
+  roofline_streaming  the bandwidth-bound forms of the same row kernels (full-shard evaluation, large-batch gradient).
+  sweep        BASELINE.json configs[4] at this GPU count: sync batch {64, 256, 1024} (device-resident).
+  async        BASELINE.json configs[3] at this GPU count: Hogwild, batch 1, one worker per GPU (lanes = 1, the
+               reference's sequential loop) and the many-lanes extension, with the master replica's test accuracy.
+  parity       a fresh 300-step trajectory at this GPU count checked against the CPU oracle IN THIS RUN.
+  rpc_seam     the literal per-request seam of SlaveImpl.gradient / forward (host weights in, dense result out).
+  nvlink       N > 1: bytes this rank stored into its peers per SGD step (counted by the kernel) and, where NVML
+               exposes them, the hardware NVLink tx/rx counters over the timed region.
   cpu_baseline the fp64 CPU oracle (array restatement of the Scala path -- the reference itself needs a
                JVM, which this image lacks) timed on this host on a bounded sample of the same workload.
 --impl reference times that CPU restatement as the reference arm.
@@ -24,6 +34,7 @@ Numbers on the JSON line:
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -60,6 +71,7 @@ def parse():
     ap.add_argument("--sgd-steps", type=int, default=0, help="SGD steps per bench step (0: one epoch at 1 worker)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip sweep / async / parity / rpc_seam / e2e_fit sub-records")
     a = ap.parse_args()
     if a.batch is None:
         a.batch = 256 if a.mode == "sync" else 1        # BASELINE.json configs[1]/[2] and configs[3]
@@ -72,6 +84,20 @@ def peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel_key: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per SGD step of the persistent kernel from this round's `ncu --set full`
+    capture (profiles/ncu_traffic.json), valid only while the kernel source is the one that was captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            rec = json.load(f)[kernel_key]
+        src = os.path.join(ROOT, "distributed_sgd_b200", "csrc", rec["source"])
+        if hashlib.sha256(open(src, "rb").read()).hexdigest()[:16] != rec["source_sha16"]:
+            return None, "profiles/ncu_traffic.json is from an older kernel source: not reported"
+        return rec, rec.get("capture", "profiles/ncu_traffic.json")
+    except Exception:
+        return None, "no ncu capture recorded for this kernel source"
 
 
 class ClockSampler:
@@ -117,6 +143,24 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def nvlink_counters(device: int):
+    """(tx_bytes, rx_bytes) summed over the GPU's NVLinks from NVML's throughput counters (KiB), or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        ids = [pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX]
+        out = []
+        for fid in ids:
+            fv = pynvml.nvmlDeviceGetFieldValues(h, [(fid, 0xFFFFFFFF)])[0]     # scope UINT_MAX: all links
+            if fv.nvmlReturn != 0:
+                return None
+            out.append(int(fv.value.ullVal) * 1024)
+        return tuple(out)
+    except Exception:
+        return None
+
+
 def sync_config(args, world, n_train, B, S):
     """The `config` object of a sync line -- shared by the GPU arm and the reference arm so that they name the same
     workload."""
@@ -143,11 +187,16 @@ def draw_batches(rng, lo: int, hi: int, batch: int, n_steps: int) -> np.ndarray:
     return out
 
 
-def cpu_leg(data, n_train, d, batch, workers, budget_s, threads, seed):
-    """Times the oracle's sync steps (K logical workers) on a bounded sample; returns (samples/s, description)."""
+def make_oracle(data, d):
     from oracle.oracle import Oracle
     orc = Oracle(data.row_ptr, data.col, data.val, data.label, data.dim, LAMBDA)
     orc.set_dim_sparsity(d)
+    return orc
+
+
+def cpu_leg(data, n_train, d, batch, workers, budget_s, threads, seed):
+    """Times the oracle's sync steps (K logical workers) on a bounded sample; returns (samples/s, description)."""
+    orc = make_oracle(data, d)
     rng = np.random.default_rng(seed + 17)
     per = n_train // workers
     probe = 40
@@ -164,10 +213,192 @@ def cpu_leg(data, n_train, d, batch, workers, budget_s, threads, seed):
     return n_steps * batch * workers / dt, f"{n_steps} sync SGD steps x {workers} worker(s) x batch {batch}, {dt:.1f} s"
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# sub-records
+# ---------------------------------------------------------------------------------------------------------------------
+
+def parity_record(ctx, group, data, n_train, d, B, rank, world, steps=300):
+    """A fresh trajectory from w = 0 (recorded batch draws, K = world workers) on the GPUs, replayed by the fp64 CPU oracle
+    on rank 0: per-step losses and final weights must agree; replicas must be bit-identical."""
+    per = n_train // world
+    rng = np.random.default_rng(4242)                              # same stream on every rank
+    idx = np.stack([np.concatenate([k * per + rng.choice(per, size=B, replace=False) for k in range(world)])
+                    for _ in range(steps)]).astype(np.int32)       # [steps, world * B]
+    mine = idx.reshape(steps, world, B)[:, rank, :].reshape(-1)
+    ctx.set_weights(np.zeros(data.dim))
+    group.barrier()
+    losses = ctx.sync_steps(mine, B, steps, LR, want_losses=True)
+    w = ctx.get_weights()
+    digests = group.all_gather_bytes(hashlib.sha256(w.tobytes()).digest())
+    rec = None
+    if rank == 0:
+        orc = make_oracle(data, d)
+        w_ref, l_ref = orc.sync_steps(np.zeros(data.dim), idx.reshape(-1), [B] * world, LR, n_steps=steps)
+        nz = w_ref != 0
+        rec = {"steps": steps, "workers": world, "batch_per_worker": B,
+               "max_rel_err_loss": float(np.max(np.abs(losses - l_ref) / np.abs(l_ref))),
+               "max_rel_err_weights": float(np.max(np.abs(w[nz] - w_ref[nz]) / np.abs(w_ref[nz]))) if nz.any() else 0.0,
+               "support_equal": bool(np.array_equal(w != 0, nz)),
+               "replicas_identical": all(b == digests[0] for b in digests),
+               "checker": "oracle/dsgd_oracle.c (fp64 CPU restatement of core/Master.scala:184-197), same batch draws"}
+    group.barrier()
+    return rec
+
+
+def sweep_record(ctx, group, data, n_train, rank, world, hbm_peak, batches=(64, 256, 1024), s_steps=600, reps=3):
+    """configs[4], sync side: device-resident samples/s for batch 64 / 256 / 1024 per GPU at this GPU count."""
+    per = n_train // world
+    out = []
+    for B in batches:
+        rng = np.random.default_rng(900 + rank)
+        idx = draw_batches(rng, rank * per, (rank + 1) * per, B, s_steps)
+        ctx.set_weights(np.zeros(data.dim))
+        ctx.stage_samples(idx.reshape(-1))
+        group.barrier()
+        ctx.sync_steps_staged(0, B, s_steps, LR, want_losses=False)        # warm-up
+        ctx.synchronize()
+        group.barrier()
+        ctx.timer_start()
+        for _ in range(reps):
+            ctx.sync_steps_staged(0, B, s_steps, LR, want_losses=False)
+        ms = group.all_reduce_max(ctx.timer_stop())
+        by = data.algorithmic_bytes(idx.reshape(-1)) * reps
+        out.append({"mode": "sync", "batch_per_gpu": B, "n_gpus": world, "value": reps * s_steps * B * world / (ms * 1e-3),
+                    "unit": UNIT, "us_per_step": ms * 1e3 / (reps * s_steps),
+                    "roofline_frac": by / (ms * 1e-3) / 1e9 / hbm_peak, "sgd_steps_timed": reps * s_steps})
+    return out
+
+
+def async_record(args, group, data, n_train, rank, local_rank, world, hbm_peak):
+    """configs[3]: async Hogwild, batch 1, one worker per GPU, lock-free peer replica writes over NVLink.  lanes = 1 is the
+    reference's loop (one sequential asyncTask per slave, core/Slave.scala:79-111); lanes = 256 is this build's extension
+    (256 Hogwild lanes share the GPU's replica).  lr from application.conf."""
+    from distributed_sgd_b200.native import REPLICA_MASTER, REPLICA_SELF, NativeCtx
+    actx = NativeCtx(local_rank, data.dim, LAMBDA, rank=rank, world=world, is_async=True)
+    actx.load_csr(data.row_ptr, data.col, data.val, data.label)
+    actx.compute_dim_sparsity(n_train)
+    w0 = np.zeros(data.dim)
+    per = n_train // world
+    assigned = np.arange(rank * per, (rank + 1) * per, dtype=np.int32)
+    actx.set_weights(w0)
+    if rank == 0:
+        actx.async_host_master(w0)
+    if world > 1:
+        handles = group.all_gather_bytes(actx.ipc_export(REPLICA_SELF))
+        master = group.broadcast_bytes(actx.ipc_export(REPLICA_MASTER) if rank == 0 else b"", 0)
+        for k, h in enumerate(handles):
+            if k != rank:
+                actx.ipc_import(k, h)
+        if rank != 0:
+            actx.ipc_import(world, master)
+    group.barrier()
+    mean_bytes = data.algorithmic_bytes() / data.n_rows
+    out = []
+    for lanes, U in ((1, 60000), (256, 1500000)):
+        actx.set_weights(w0)
+        if rank == 0:
+            actx.async_host_master(w0)
+        group.barrier()
+
+        def run(seed, n_upd):
+            actx.start_async(None, assigned, 1, LR, concurrency=lanes, max_updates=n_upd, seed=seed)
+            while actx.async_running():
+                time.sleep(0.0002)
+            actx.stop_async()
+            return actx.async_elapsed_ms()
+
+        run(7, U // 10)
+        group.barrier()
+        t0 = time.perf_counter()
+        ms = run(11, U)
+        wall = group.all_reduce_max(time.perf_counter() - t0)
+        ms = group.all_reduce_max(ms)
+        group.barrier()
+        w_self = actx.get_weights()
+        blobs = group.all_gather_bytes(w_self.tobytes())
+        rec = {"mode": "async", "batch": 1, "lanes_per_gpu": lanes, "n_gpus": world, "updates_per_gpu": U, "lr": LR,
+               "value": U * world / (ms * 1e-3), "e2e_value": U * world / wall, "unit": UNIT,
+               "us_per_update_per_lane": ms * 1e3 * lanes / U,
+               "roofline_frac": U * mean_bytes / (ms * 1e-3) / 1e9 / hbm_peak,
+               "label": ("one worker per GPU, sequential loop: the reference's Slave.asyncTask" if lanes == 1 else
+                         "EXTENSION: 256 Hogwild lanes per GPU on the GPU's replica (the reference runs one loop per slave)")}
+        if rank == 0:
+            ws = [np.frombuffer(b, dtype=np.float64) for b in blobs]
+            w_master = actx.async_master_weights()
+            loss, acc = actx.eval(n_train, data.n_rows, w_master)
+            rec.update({"master_test_loss": loss, "master_test_acc": acc, "master_updates": int(actx.async_updates()),
+                        "replica_max_abs_diff": float(max(np.max(np.abs(w - ws[0])) for w in ws)),
+                        "replica_vs_master_max_abs_diff": float(np.max(np.abs(ws[0] - w_master)))})
+        out.append(rec)
+    actx.close()
+    return out
+
+
+def rpc_seam_record(ctx, data, n_train, d, B=256, reps=200):
+    """The literal drop-in seam of SlaveImpl.gradient / SlaveImpl.forward (core/Slave.scala:129-157): weights arrive with the
+    request (host buffer, 378 KB), the dense gradient / the predictions go back to the host, one blocking C-ABI call each;
+    next to it the CPU port's time for the same request."""
+    rng = np.random.default_rng(77)
+    w = rng.standard_normal(data.dim) * 0.05
+    idx = [rng.choice(n_train, size=B, replace=False).astype(np.int32) for _ in range(reps)]
+    for i in range(10):
+        ctx.gradient(idx[i], w); ctx.forward(idx[i], w)
+    t = time.perf_counter()
+    for i in range(reps):
+        ctx.gradient(idx[i], w)
+    g_us = (time.perf_counter() - t) / reps * 1e6
+    t = time.perf_counter()
+    for i in range(reps):
+        ctx.forward(idx[i], w)
+    f_us = (time.perf_counter() - t) / reps * 1e6
+    t = time.perf_counter()
+    for i in range(reps):
+        ctx.gradient(idx[i], None)
+    gr_us = (time.perf_counter() - t) / reps * 1e6
+    orc = make_oracle(data, d)
+    n_cpu = 50
+    t = time.perf_counter()
+    for i in range(n_cpu):
+        orc.gradient(w, idx[i])
+    cg_us = (time.perf_counter() - t) / n_cpu * 1e6
+    t = time.perf_counter()
+    for i in range(n_cpu):
+        orc.forward(w, idx[i])
+    cf_us = (time.perf_counter() - t) / n_cpu * 1e6
+    return {"batch": B, "requests_timed": reps, "gradient_us_per_request": g_us, "forward_us_per_request": f_us,
+            "gradient_resident_weights_us_per_request": gr_us,
+            "h2d_bytes_per_request": data.dim * 8 + B * 4, "d2h_bytes_gradient": data.dim * 8, "d2h_bytes_forward": B * 8,
+            "cpu_port_gradient_us_per_request": cg_us, "cpu_port_forward_us_per_request": cf_us,
+            "samples_per_s_gradient": B / (g_us * 1e-6), "cpu_port_samples_per_s_gradient": B / (cg_us * 1e-6),
+            "api": "dsgd_gradient / dsgd_forward (C ABI), weights passed with the request like GradientRequest.weights"}
+
+
+def fit_record(ctx, group, data, n_train, rank, world, B, epochs=3):
+    """samples/s through MasterSync.fit (the reference's public API for this path, core/Master.scala:120-218), everything
+    inside the timed region: per-epoch batch draws on the host, H2D of the ids, the step loop, train/test loss and accuracy
+    after every epoch, the weight read-back."""
+    from distributed_sgd_b200 import MasterSync, Slave, SparseSVM
+    train, test = data.split_at(n_train)
+    model = SparseSVM(LAMBDA)
+    slave = Slave(rank, 0, train, model, world=world, test_data=test, ctx=ctx)
+    # the ctx already carries its peer exchange: build the master around it without re-initialising it
+    master = MasterSync(rank, train, test, model, world, slave=slave, group=group, seed=5, attach=False)
+    never = lambda losses: False
+    master.fit(np.zeros(data.dim), 1, B, LR, never)                 # warm-up epoch
+    group.barrier()
+    t0 = time.perf_counter()
+    state = master.fit(np.zeros(data.dim), epochs, B, LR, never)
+    dt = group.all_reduce_max(time.perf_counter() - t0)
+    steps_per_epoch = -(-(n_train // world) // B)
+    samples = sum(int(min(B, n_train // world - s * B)) for s in range(steps_per_epoch)) * world * epochs
+    return {"value": samples / dt, "unit": UNIT, "epochs": epochs, "sgd_steps_per_epoch": steps_per_epoch,
+            "seconds": dt, "final_train_loss": float(state.loss), "final_test_acc": float(master.history["test_accs"][-1]),
+            "api": "MasterSync.fit (Python mirror of core/Master.scala:120-218 over the C ABI), epoch evaluations included"}
+
+
 def bench_async(args, ctx, data, n_train, d, group, rank, local_rank, world):
-    """BASELINE.json configs[3]: async Hogwild, one worker per GPU, lock-free peer replica writes over NVLink,
-    batch 1 by default.  A bench step = `--async-updates` worker iterations per GPU (device-side sampling)."""
-    import torch
+    """`--mode async`: BASELINE.json configs[3] as the headline line.  A bench step = `--async-updates` worker iterations per
+    GPU (device-side sampling), lr from application.conf."""
     from distributed_sgd_b200.native import REPLICA_MASTER, REPLICA_SELF
     B = args.batch
     U = args.async_updates
@@ -188,9 +419,9 @@ def bench_async(args, ctx, data, n_train, d, group, rank, local_rank, world):
     group.barrier()
 
     def run(seed):
-        ctx.start_async(None, assigned, B, 0.1, concurrency=args.lanes, max_updates=U, seed=seed)
+        ctx.start_async(None, assigned, B, LR, concurrency=args.lanes, max_updates=U, seed=seed)
         while ctx.async_running():
-            time.sleep(0.0005)
+            time.sleep(0.0002)
         ctx.stop_async()
         return ctx.async_elapsed_ms()
 
@@ -211,20 +442,16 @@ def bench_async(args, ctx, data, n_train, d, group, rank, local_rank, world):
     wall = group.all_reduce_max(wall)
     samples_total = args.steps * U * B * world
     value = samples_total / (ms_dev * 1e-3)
-    # e2e: the public call with host buffers (assigned ids H2D, final master weights D2H), wall clock
     e2e_value = samples_total / wall
     w_master = ctx.async_master_weights() if rank == 0 else None
     hbm_peak, peak_src = peaks()
     mean_bytes = data.algorithmic_bytes() / data.n_rows
     achieved = (args.steps * U * B * mean_bytes) / (ms_dev * 1e-3) / 1e9     # per GPU
-    cpu = None
     if rank == 0:
-        from oracle.oracle import Oracle
-        orc = Oracle(data.row_ptr, data.col, data.val, data.label, data.dim, LAMBDA)
-        orc.set_dim_sparsity(d)
+        orc = make_oracle(data, d)
         n_cpu = 20000
         idx = np.random.default_rng(3).integers(0, n_train, size=n_cpu * B).astype(np.int32)
-        t = time.perf_counter(); orc.async_run(w0, idx, B, 0.1); dt = time.perf_counter() - t
+        t = time.perf_counter(); orc.async_run(w0, idx, B, LR); dt = time.perf_counter() - t
         cpu = {"value": n_cpu * B / dt, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"{n_cpu} sequential async iterations of batch {B} (one worker), {dt:.1f} s; the reference recomputes "
                          "w.dimSparsity (47 236 products) every iteration (core/ml/SparseSVM.scala:31) and so does this port"}
@@ -235,8 +462,8 @@ def bench_async(args, ctx, data, n_train, d, group, rank, local_rank, world):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"async Hogwild (configs[3]): RCV1-shaped synthetic, {DIM} feats, {args.rows} rows, batch {B}, "
                                    f"one worker per GPU, {args.lanes} Hogwild lanes per GPU, peer replica writes over NVLink",
-                       "mode": "async", "batch": B, "updates_per_gpu_per_step": U, "lanes": args.lanes, "parallelism": f"dp{world}",
-                       "l2": "rows drawn at random from 0.43 GB of CSR (larger than the 126 MB L2)"},
+                       "mode": "async", "batch": B, "lr": LR, "updates_per_gpu_per_step": U, "lanes": args.lanes,
+                       "parallelism": f"dp{world}", "l2": "rows drawn at random from 0.43 GB of CSR (larger than the 126 MB L2)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(assigned.nbytes), "d2h_bytes_per_step": 0,
                     "api": "dsgd_start_async ... dsgd_stop_async (C ABI)"},
             "gpu_launches": int(launches),
@@ -305,8 +532,9 @@ def main():
     ctx = NativeCtx(local_rank, data.dim, LAMBDA, rank=rank, world=world, is_async=(args.mode == "async"))
     ctx.load_csr(data.row_ptr, data.col, data.val, data.label)   # every slave holds every row (quirk Q13)
     d = ctx.compute_dim_sparsity(n_train)
+    use_nccl = bool(os.environ.get("BENCH_NCCL_PATH"))           # A/B: NCCL allreduce between the kernels of a step
     if world > 1 and args.mode == "sync":
-        if os.environ.get("DSGD_NO_P2P"):    # general path: NCCL allreduce between the kernels of a step
+        if use_nccl:
             uid = NativeCtx.comm_unique_id() if rank == 0 else b""
             ctx.comm_init(group.broadcast_bytes(uid, 0))
         else:
@@ -325,6 +553,7 @@ def main():
     pinned = torch.empty((total_steps, S * B), dtype=torch.int32).pin_memory()
     pinned.numpy()[:] = samples_np
     alg_bytes_per_step = [data.algorithmic_bytes(samples_np[i]) for i in range(total_steps)]
+    hbm_peak, peak_src = peaks()
 
     def barrier():
         ctx.synchronize()
@@ -342,6 +571,8 @@ def main():
     for i in range(args.warmup):
         ctx.sync_steps_staged(i * S * B, B, S, LR, want_losses=True)
     barrier()
+    nvl0 = nvlink_counters(local_rank) if (rank == 0 and world > 1) else None
+    xs0 = ctx.xchg_stats() if world > 1 else None
     launches0 = ctx.launch_count()
     ctx.timer_start()
     for i in range(args.warmup, total_steps):
@@ -349,6 +580,8 @@ def main():
     ms = ctx.timer_stop()
     launches = ctx.launch_count() - launches0
     barrier()
+    nvl1 = nvlink_counters(local_rank) if (rank == 0 and world > 1) else None
+    xs1 = ctx.xchg_stats() if world > 1 else None
     clock_info = clocks.stop() if rank == 0 else None
     ms = group.all_reduce_max(ms)
     samples_total = args.steps * S * B * world
@@ -371,7 +604,7 @@ def main():
     # both legs walked the same batches from the same start: identical results expected
     same = bool(np.array_equal(ctx.get_weights(), w_after)) if world == 1 else None
 
-    # ---- leg 3: mean duration of the dominant kernel (gradient) over the same work -----------------------
+    # ---- leg 3: mean duration of the dominant kernel over the same work -----------------------
     ctx.set_weights(np.zeros(data.dim))
     ctx.stage_samples(samples_np.reshape(-1))   # leg 2 re-staged one bench step at a time
     ctx.profile_begin(sample_every=1)
@@ -379,13 +612,15 @@ def main():
         ctx.sync_steps_staged(i * S * B, B, S, LR, want_losses=False)
     k_ms, k_n = ctx.profile_end()
     barrier()
-    hbm_peak, peak_src = peaks()
     # every launch of the dominant kernel was bracketed: algorithmic bytes of the region / launches
     alg_per_launch = float(np.sum(alg_bytes_per_step[args.warmup:])) / max(k_n, 1)
     achieved = alg_per_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    kernel_name = ("k_sync_persistent (whole run of %d SGD steps per launch)" % S) if k_n == args.steps \
+    persistent = (k_n == args.steps)
+    kernel_name = ("k_sync_persistent (whole run of %d SGD steps per launch)" % S) if persistent \
         else "k_rows<scatter> (gradient, one launch per SGD step)"
     step_frac = (float(np.mean(alg_bytes_per_step[args.warmup:])) * args.steps / (ms * 1e-3) / 1e9) / hbm_peak
+    traffic_rec, traffic_src = ncu_traffic("k_sync_persistent_multi" if world > 1 else "k_sync_persistent") if persistent else (None, "n/a")
+    traffic = float(traffic_rec["dram_bytes_per_sgd_step_batch256"]) * (B / 256.0) * S if traffic_rec else None
 
     # ---- leg 3b: the same row kernels where they are bandwidth- rather than latency-bound -----------------------
     # (batch 256 moves 197 KB per step; the HBM roofline of the path shows on the full-shard evaluation pass,
@@ -403,17 +638,50 @@ def main():
         big = np.random.default_rng(1).choice(n_train, size=min(262144, n_train), replace=False).astype(np.int32)
         gr_bytes = data.algorithmic_bytes(big)
         gr_ms = best_ms(lambda: ctx.gradient(big))
+        w_trained = ctx.get_weights()
+        gr0_ms = best_ms(lambda: ctx.gradient(big, np.zeros(data.dim)))
+        tr_e, tr_e_src = ncu_traffic("k_stream_rows_eval")
+        tr_g, _ = ncu_traffic("k_stream_rows_scatter")
         streaming = {
             "eval_full_train_pass": {"kernel": "k_stream_rows<eval>", "rows": int(n_train), "ms": ev_ms,
-                                     "achieved": ev_bytes / ev_ms / 1e6, "unit": "GB/s", "frac": ev_bytes / ev_ms / 1e6 / hbm_peak},
+                                     "achieved": ev_bytes / ev_ms / 1e6, "unit": "GB/s", "frac": ev_bytes / ev_ms / 1e6 / hbm_peak,
+                                     "algorithmic_bytes": ev_bytes, "traffic": tr_e["dram_bytes"] if tr_e else None},
             "gradient_batch_%d" % len(big): {"kernel": "k_stream_rows<scatter>", "rows": int(len(big)), "ms": gr_ms,
                                              "achieved": gr_bytes / gr_ms / 1e6, "unit": "GB/s",
-                                             "frac": gr_bytes / gr_ms / 1e6 / hbm_peak,
-                                             "note": "bounded by fp64 RED issue rate at L2 (0.48 per SM-cycle measured), not HBM"},
+                                             "frac": gr_bytes / gr_ms / 1e6 / hbm_peak, "algorithmic_bytes": gr_bytes,
+                                             "traffic": tr_g["dram_bytes"] if tr_g else None,
+                                             "weights": "trained (the resident weights after the timed legs): the rows that pass "
+                                                        "the gate are the misclassified ones"},
+            "gradient_batch_%d_untrained" % len(big): {
+                "kernel": "k_stream_rows<scatter>", "rows": int(len(big)), "ms": gr0_ms, "achieved": gr_bytes / gr0_ms / 1e6,
+                "unit": "GB/s", "frac": gr_bytes / gr0_ms / 1e6 / hbm_peak,
+                "weights": "w = 0: EVERY row passes the gate (SparseSVM.scala:28), the scatter is bound by the fp64 RED rate at "
+                           "L2, not by HBM"},
         }
+        ctx.set_weights(w_trained)
     barrier()
 
-    # ---- leg 4: CPU baseline on this host (rank 0, N = 1 only) -------------------------------------------
+    extras = {}
+    if not args.no_extras:
+        # ---- configs[4] sweep, sync side ----
+        extras["sweep"] = sweep_record(ctx, group, data, n_train, rank, world, hbm_peak)
+        # ---- parity of a fresh trajectory against the oracle, in this run ----
+        extras["parity"] = parity_record(ctx, group, data, n_train, d, B, rank, world)
+        # ---- e2e through MasterSync.fit ----
+        try:
+            extras["e2e_fit"] = fit_record(ctx, group, data, n_train, rank, world, B)
+        except Exception as e:  # the headline line must not die on a sub-record
+            extras["e2e_fit"] = {"error": repr(e)}
+        # ---- configs[3] async Hogwild ----
+        try:
+            extras["async"] = async_record(args, group, data, n_train, rank, local_rank, world, hbm_peak)
+        except Exception as e:
+            extras["async"] = {"error": repr(e)}
+        if rank == 0 and world == 1:
+            extras["rpc_seam"] = rpc_seam_record(ctx, data, n_train, d)
+    barrier()
+
+    # ---- CPU baseline on this host (rank 0, N = 1 only) -------------------------------------------
     cpu = None
     if rank == 0 and world == 1:
         v, desc = cpu_leg(data, n_train, d, B, 1, args.cpu_seconds, 1, args.seed)
@@ -422,29 +690,40 @@ def main():
                                 "(core/Slave.scala:142); host has %d cores" % (os.cpu_count() or 0)}
 
     if rank == 0:
+        nvlink = None
+        if world > 1 and xs0 and xs1:
+            dv, db, dn = (xs1[0] - xs0[0]), (xs1[1] - xs0[1]), max(xs1[2] - xs0[2], 1)
+            nvlink = {"stored_bytes_per_sgd_step_rank0": (16 * dv + 8 * db) * (world - 1) / dn,
+                      "value_words_per_peer_per_step": dv / dn, "bitmap_words_per_peer_per_step": db / dn,
+                      "dense_exchange_bytes_per_sgd_step": (world - 1) * (data.dim + 1) * 16,
+                      "source": "counted by the kernel (dsgd_xchg_stats): 16-byte value words + 8-byte bitmap words x (N - 1) peers"}
+            if nvl0 and nvl1:
+                nvlink["nvml_tx_bytes_per_sgd_step_rank0"] = (nvl1[0] - nvl0[0]) / (args.steps * S)
+                nvlink["nvml_rx_bytes_per_sgd_step_rank0"] = (nvl1[1] - nvl0[1]) / (args.steps * S)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": sync_config(args, world, n_train, B, S),
+            "us_per_sgd_step": ms * 1e3 / (args.steps * S),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(S * B * 4), "d2h_bytes_per_step": int(S * 8),
                     "api": "dsgd_sync_steps (C ABI, pinned host buffers)", "matches_device_leg": same},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the ncu --set full capture in
-                         # profiles/r1c_summary.md: 67.21 MB for a 300-step launch at batch 256 = 224 KB per SGD step
-                         "traffic": (float(S) * 67.21e6 / 300.0 * (B / 256.0)) if k_n == args.steps else None,
-                         "traffic_source": "ncu capture of a 300-step launch (profiles/r1c_summary.md), scaled to this launch",
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_per_launch, "kernel_ms": k_ms, "launches_sampled": int(k_n),
-                         "whole_step_frac": step_frac},
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_per_launch, "kernel_ms": k_ms,
+                         "launches_sampled": int(k_n), "whole_step_frac": step_frac},
             "roofline_streaming": streaming,
             "cpu_baseline": cpu,
             "clocks": clock_info,
+            "exchange": ("nccl allreduce between kernels" if use_nccl else "fused: sparse LL words over peer memory") if world > 1 else None,
+            "nvlink": nvlink,
             "final_batch_loss": float(last_losses[-1]),
             # fingerprints of the device-resident leg, for tools/verify_bench_loss.py (oracle replay of the same run)
             "final_weights_l1": float(np.abs(w_after).sum()), "final_weights_nnz": int(np.count_nonzero(w_after)),
         }
+        out.update(extras)
         print(json.dumps(out))
     ctx.close()
     if world > 1:

@@ -25,12 +25,57 @@ EarlyStopping = Callable[[Sequence[float]], bool]
 Split = Callable[[int, int], List[range]]
 
 
+class EpochDraw(list):
+    """The batch draws of one epoch: `self[s][k]` = row ids of worker k at step s (a list of lists of int32 arrays, the
+    shape the tests and the oracle replay), backed by ONE array `ids[steps, K, batch]` (-1 beyond a short slice) and
+    `counts[steps, K]` so that `fit` can hand whole runs of steps to the device without per-step Python work."""
+
+    ids: np.ndarray
+    counts: np.ndarray
+
+    @classmethod
+    def _wrap(cls, ids: np.ndarray, counts: np.ndarray) -> "EpochDraw":
+        self = cls([[ids[s, k, :counts[s, k]] for k in range(ids.shape[1])] for s in range(ids.shape[0])])
+        self.ids, self.counts = ids, counts
+        return self
+
+    @classmethod
+    def draw(cls, seed: int, epoch: int, groups: List[range], batch_size: int) -> "EpochDraw":
+        import ctypes as C
+        from .. import native
+        K = len(groups)
+        g_start = np.array([g.start for g in groups], dtype=np.int64)
+        g_len = np.array([len(g) for g in groups], dtype=np.int64)
+        steps = -(-int(g_len.max()) // batch_size) if K else 0
+        ids = np.empty((steps, K, batch_size), dtype=np.int32)
+        counts = np.empty((steps, K), dtype=np.int32)
+        h = native.host_lib()
+        rc = h.dsgd_draw_epoch(C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), epoch, K, g_start.ctypes.data_as(C.c_void_p),
+                               g_len.ctypes.data_as(C.c_void_p), batch_size, ids.ctypes.data_as(C.c_void_p),
+                               counts.ctypes.data_as(C.c_void_p), ids.size)
+        if rc != steps:
+            raise ValueError(f"draw_epoch failed ({rc})")
+        return cls._wrap(ids, counts)
+
+    @classmethod
+    def from_steps(cls, steps_list) -> "EpochDraw":
+        steps, K = len(steps_list), len(steps_list[0]) if steps_list else 0
+        B = max((len(b) for st in steps_list for b in st), default=0)
+        ids = np.full((steps, K, B), -1, dtype=np.int32)
+        counts = np.zeros((steps, K), dtype=np.int32)
+        for s, st in enumerate(steps_list):
+            for k, b in enumerate(st):
+                ids[s, k, :len(b)] = b
+                counts[s, k] = len(b)
+        return cls._wrap(ids, counts)
+
+
 class Master:
     """core/Master.scala:19-255 (abstract).  `Master.apply` (Master.scala:259-271) is `Master.create`."""
 
     def __init__(self, node: int, data: Data, test_data: Data, model: SparseSVM, expected_node_count: int, *,
                  slave: Slave, group: Optional[Group] = None, seed: int = 0, log: Optional[Callable[[str], None]] = None,
-                 jvm_exact: bool = False):
+                 jvm_exact: bool = False, attach: bool = True):
         self.node, self.model, self.expected_node_count = node, model, expected_node_count
         self.n_train, self.n_test = data.n_rows, test_data.n_rows
         self.dim = data.dim
@@ -42,7 +87,9 @@ class Master:
         if slave.n_test != self.n_test or slave.n_train != self.n_train:
             raise ValueError("the Slave must hold the same train/test rows as the Master")
         # Random.setSeed(0) (Main.scala:32): one stream, identical on every rank
+        self.seed = int(seed)
         self.rng = np.random.default_rng(seed)
+        self._epochs_drawn = 0
         # jvm_exact: draw the batches with java.util.Random(seed) + Scala 2.12's Random.shuffle, the stream a reference
         # run consumes; default: numpy's generator (statistically the same draws, much faster)
         self.jvm = None
@@ -50,7 +97,8 @@ class Master:
             from ..utils.jvm_random import JvmRandom
             self.jvm = JvmRandom(seed)
         self.log = log or (lambda s: None)
-        if self.group.world > 1 and not slave.is_async:
+        # attach=False: the Slave's device context already carries its communicator / peer exchange
+        if attach and self.group.world > 1 and not slave.is_async:
             # NCCL communicator (general path: several logical workers per GPU) ...
             uid = NativeCtx.comm_unique_id() if self.group.rank == 0 else b""
             self.ctx.comm_init(self.group.broadcast_bytes(uid, 0))
@@ -133,25 +181,22 @@ class MasterSync(Master):
     def update_grad(self, grad_update):  # MasterSync.scala:16-17
         raise NotImplementedError("Synchronous master cannot perform async operation update grad")
 
-    def draw_epoch(self, groups: List[range], batch_size: int, virtual_workers: int = 1):
+    def draw_epoch(self, groups: List[range], batch_size: int, epoch: Optional[int] = None):
         """Sample ids of one epoch: for every step (`0 until maxSamples by batchSize`, Master.scala:179) and
         every worker a fresh shuffle of its range, sliced at [batch, batch + batchSize) (Master.scala:
         184-187, quirk Q5).  A slice of a fresh permutation is a uniform draw without replacement of
-        min(batchSize, len - batch) elements.  Returns a list of steps, each a list of per-worker arrays."""
+        min(batchSize, len - batch) elements -- drawn directly (csrc/dsgd_host.c: dsgd_draw_epoch) from a counter-based
+        generator keyed by (seed, epoch, step, worker), identical on every rank.  Returns an EpochDraw: a list of steps,
+        each a list of per-worker arrays (what the oracle replays), plus the same ids as one array for the device."""
+        if epoch is None:
+            epoch = self._epochs_drawn
+        self._epochs_drawn = epoch + 1
         if self.jvm is not None:
             n, size = groups[-1].stop, len(groups[0])
             if [(g.start, g.stop) for g in groups] != [(a, min(a + size, n)) for a in range(0, n, size)]:
                 raise ValueError("jvm_exact draws are defined for SplitStrategy.vanilla groups")
-            return self.jvm.sync_epoch(n, len(groups), batch_size, group_size=size)
-        max_samples = max(len(g) for g in groups)
-        steps = []
-        for batch in range(0, max_samples, batch_size):
-            per_worker = []
-            for g in groups:
-                m = max(0, min(batch_size, len(g) - batch))
-                per_worker.append((g.start + self.rng.choice(len(g), size=m, replace=False)).astype(np.int32))
-            steps.append(per_worker)
-        return steps
+            return EpochDraw.from_steps(self.jvm.sync_epoch(n, len(groups), batch_size, group_size=size))
+        return EpochDraw.draw(self.seed, epoch, groups, batch_size)
 
     def fit(self, initial_weights: np.ndarray, max_epochs: int, batch_size: int, learning_rate: float,
             stopping_criterion: EarlyStopping, split_strategy: Split = SplitStrategy.vanilla, *,
@@ -174,6 +219,11 @@ class MasterSync(Master):
         test_accs: List[float] = []
         self.step_losses: List[np.ndarray] = []
         epoch = 0
+        # a one-thread pool overlaps the next epoch's draw with the current epoch's kernel (not with jvm_exact: that
+        # stream is sequential and must not run ahead of an early stop)
+        from concurrent.futures import ThreadPoolExecutor
+        prefetch = ThreadPoolExecutor(1) if self.jvm is None else None
+        pending = None
         while True:
             if losses:
                 self.log(f"loss after epoch {epoch}: {losses[0]}")
@@ -183,24 +233,41 @@ class MasterSync(Master):
                          else "Converged to target: stopping computation")
                 self.history = {"losses": losses[::-1], "test_losses": test_losses[::-1], "accs": accs[::-1],
                                 "test_accs": test_accs[::-1]}
+                if prefetch is not None:
+                    prefetch.shutdown(wait=True)
                 # `losses.head` throws on an empty list in the reference (max_epochs == 0)
                 return state.finish(losses[0])
-            steps = self.draw_epoch(groups, batch_size)
-            # consecutive steps with identical per-worker counts go to the device in one call
-            i = 0
-            while i < len(steps):
-                shape = [len(steps[i][k]) for k in my_groups]
-                j = i
-                while j < len(steps) and [len(steps[j][k]) for k in my_groups] == shape:
-                    j += 1
-                if any(len(steps[i][k]) == 0 for k in range(k_total)):
-                    raise ValueError("Cannot sum an empty list of vectors")  # Vec.scala:129 via Master.scala:187 (Q7)
-                flat = (np.concatenate([np.concatenate([steps[s][k] for k in my_groups]) for s in range(i, j)])
-                        if my_groups else np.zeros(0, dtype=np.int32))
+            steps = pending.result() if pending is not None else self.draw_epoch(groups, batch_size)
+            pending = None
+            if not isinstance(steps, EpochDraw):
+                steps = EpochDraw.from_steps(steps)
+            if prefetch is not None and epoch + 1 < max_epochs:
+                # the draws of epoch e + 1 do not depend on epoch e: make them while the GPU runs epoch e
+                pending = prefetch.submit(self.draw_epoch, groups, batch_size, self._epochs_drawn)
+            counts = steps.counts                                                 # [steps, k_total]
+            if counts.size and (counts[:, :k_total] == 0).any():
+                raise ValueError("Cannot sum an empty list of vectors")  # Vec.scala:129 via Master.scala:187 (Q7)
+            # consecutive steps with identical counts for ALL workers go to the device in one call; the boundaries come
+            # from the global shape so that every rank issues the same sequence of calls (the fused multi-GPU kernel
+            # numbers its exchange tags by call)
+            n_steps = counts.shape[0]
+            change = np.flatnonzero((counts[1:] != counts[:-1]).any(axis=1)) + 1 if n_steps > 1 else np.zeros(0, dtype=np.int64)
+            bounds = [0, *change.tolist(), n_steps]
+            for i, j in zip(bounds[:-1], bounds[1:]):
+                if j == i:
+                    continue
+                shape = [int(counts[i, k]) for k in my_groups]
+                if my_groups:
+                    g0, g1 = my_groups[0], my_groups[-1] + 1
+                    if all(c == steps.ids.shape[2] for c in shape):
+                        flat = np.ascontiguousarray(steps.ids[i:j, g0:g1, :]).reshape(-1)
+                    else:
+                        flat = np.concatenate([steps.ids[s, k, :counts[s, k]] for s in range(i, j) for k in my_groups])
+                else:
+                    flat = np.zeros(0, dtype=np.int32)
                 self.ctx.set_workers(shape, k_total)
                 ls = self.ctx.sync_steps(flat, int(sum(shape)), j - i, learning_rate, want_losses=True)
                 self.step_losses.append(ls)
-                i = j
             w = None  # evaluate the resident weights
             tl, ta = self.local_loss_accuracy(w, test_data=False)        # Master.scala:206-207
             vl, va = self.local_loss_accuracy(w, test_data=True)         # Master.scala:208-209
@@ -272,7 +339,9 @@ class MasterAsync(Master):
                 if updates - last_step < check_every:                             # latest computation was too close
                     time.sleep(poll_seconds)                                      # (the reference waits 2.5 s)
                     continue
-                w = self.ctx.async_master_weights()                               # innerGradState.grad
+                # innerGradState.grad: ONE snapshot (rank 0 hosts the master replica), evaluated row-sharded by everybody
+                blob = self.ctx.async_master_weights().tobytes() if r == 0 else b""
+                w = np.frombuffer(self.group.broadcast_bytes(blob, 0), dtype=np.float64).copy()
                 loss, acc = self.local_loss_accuracy(w, test_data=True)           # MasterAsync.scala:118-120
                 loss_s = leak_loss_coef * loss + (1 - leak_loss_coef) * (test_losses[0] if test_losses else loss)
                 acc_s = leak_loss_coef * acc + (1 - leak_loss_coef) * (test_accs[0] if test_accs else acc)
@@ -294,6 +363,7 @@ class MasterAsync(Master):
             self.group.barrier()
         if best_w is None:
             # the reference would hand back its initial bestGrad (Vec.zeros(1)) here; we return what the master holds
-            best_w = self.ctx.async_master_weights()
+            blob = self.ctx.async_master_weights().tobytes() if r == 0 else b""
+            best_w = np.frombuffer(self.group.broadcast_bytes(blob, 0), dtype=np.float64).copy()
             best_loss = self.local_loss_accuracy(best_w, test_data=True)[0]
         return state.replace_grad(best_w).finish(best_loss)                       # MasterAsync.scala:91

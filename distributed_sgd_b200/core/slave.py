@@ -18,18 +18,27 @@ from ..utils.dataset import Data
 
 class Slave:
     def __init__(self, node: int, master: int, data: Data, model: SparseSVM, is_async: bool = False, *,
-                 world: int = 1, device: Optional[int] = None, test_data: Optional[Data] = None):
+                 world: int = 1, device: Optional[int] = None, test_data: Optional[Data] = None,
+                 ctx: Optional[NativeCtx] = None):
         """`new Slave(node, master, data, model, async)` (core/Slave.scala:20; Main.scala:138,149).
 
         node = this worker's rank; master = the master's rank (kept for recognisability; the master logic
         runs SPMD on every rank).  `data` is the FULL training array, addressed by global row id (quirk
         Q13).  test_data (extension): rows appended after the training rows so the same device context can
-        serve Master.localLoss(testData) -- they are never sampled.
+        serve Master.localLoss(testData) -- they are never sampled.  ctx (extension): a device context that already
+        holds exactly these rows (train rows followed by the test rows) and its dimSparsity.
         """
         self.node, self.master, self.model, self.is_async, self.world = node, master, model, is_async, world
         self.n_train = data.n_rows
         self.n_test = test_data.n_rows if test_data is not None else 0
         self.dim = data.dim
+        if ctx is not None:
+            if ctx.n_rows != self.n_train + self.n_test or ctx.dim != data.dim:
+                raise ValueError("Slave: the given device context does not hold these rows")
+            self.ctx = ctx
+            if model.dim_sparsity is None:
+                model.dim_sparsity = ctx.compute_dim_sparsity(self.n_train)
+            return
         self.ctx = NativeCtx(node if device is None else device, data.dim, model.lam, rank=node, world=world,
                              is_async=is_async)
         if test_data is not None:

@@ -16,7 +16,7 @@
 #include "dsgd_kernels.cuh"
 #include "dsgd_persistent.cuh"
 #include "dsgd_stream.cuh"
-#include "dsgd_stream_x.cuh"
+#include "dsgd_stream_v1.cuh"
 #include "dsgd_async.cuh"
 #include <cstdlib>
 
@@ -38,6 +38,7 @@ struct dsgd_ctx {
 
   // rows
   int64_t n_rows = 0, nnz = 0, n_pairs = 0;
+  bool rows_unique = false;   // every row's columns are strictly increasing (no duplicate keys: the reference's rows are Maps)
   uint32_t *rp16 = nullptr;
   uint2 *pairs = nullptr;
   int8_t *label = nullptr;
@@ -73,13 +74,11 @@ struct dsgd_ctx {
   unsigned *p_hinge = nullptr;
   int64_t p_hinge_cap = 0;
   unsigned *p_bar = nullptr;   // [0]: barrier counter, [1]: abort flag
-  unsigned *p_bar_flags = nullptr;  // DSGD_PERSIST_OPT & 1: release flag lines of the flag barrier
-  double *p_push = nullptr;         // DSGD_PERSIST_OPT & 2: pushed partials [2][G][G][2]
-  uint32_t *hot_bits = nullptr;     // DSGD_STREAM_OPT & 2: hot-column bitmap / slot prefix / slot -> column (dsgd_stream.cuh)
+  unsigned *p_bar_flags = nullptr;  // release flag lines of the flag barrier
+  uint32_t *hot_bits = nullptr;     // hot-column bitmap / slot prefix / slot -> column of the streaming scatter (dsgd_stream.cuh)
   uint16_t *hot_prefix = nullptr;
   int32_t *hot_cols = nullptr;
   int n_hot = 0;
-  bool stream_opt_ready = false;
   bool p_ready = false;
   long long *p_tl = nullptr;   // debug timeline (DSGD_PERSIST_TIMELINE)
 
@@ -99,12 +98,16 @@ struct dsgd_ctx {
   bool a_running = false;
   cudaEvent_t a_ev0 = nullptr, a_ev1 = nullptr;
 
-  // sync-mode exchange block shared with peers over NVLink: 3 gradient buffers (dim + 8 doubles each) + flag words
+  // sync-mode receive area shared with peers over NVLink: value words [sender][parity][dim + 8] x 16 B, then bitmap
+  // words [sender][parity][ceil((dim + 1) / 32)] x 8 B (dsgd_persistent.cuh)
   double *xblk = nullptr;
   double *peer_x[kMaxWorld] = {};
   bool peer_x_ipc[kMaxWorld] = {};
+  int grid_limit = 0;   // dsgd_set_grid_limit: CTAs of the persistent sync kernel (0: one per SM)
   int64_t x_step = 0;   // global step counter of the fused multi-GPU kernel (identical on every rank)
-  unsigned long long *x_llw = nullptr;  // weights in LL form, two parities (mode 3)
+  int64_t x_steps_run = 0;  // SGD steps run by the fused kernel so far (dsgd_xchg_stats)
+  unsigned long long *x_llw = nullptr;  // this rank's weights in LL form, two parities
+  unsigned long long *x_stats = nullptr;  // [0] value words, [1] bitmap words pushed to each peer so far; [2] SGD steps of those launches
 
   // sampled per-launch timing of the gradient kernel
   int32_t prof_every = 0;
@@ -282,7 +285,7 @@ extern "C" int dsgd_destroy(dsgd_ctx *ctx) {
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   void *ptrs[] = {ctx->rp16, ctx->pairs, ctx->label, ctx->w, ctx->g, ctx->d, ctx->w_req, ctx->w32, ctx->w32_req, ctx->n_exact, ctx->scal,
                   ctx->cnt, ctx->partial, ctx->out2, ctx->gsum, ctx->p_wbuf[0], ctx->p_wbuf[1], ctx->p_gbuf[0],
-                  ctx->p_gbuf[1], ctx->p_gbuf[2], ctx->p_partial, ctx->p_hinge, ctx->p_bar, ctx->p_bar_flags, ctx->p_push, ctx->hot_bits, ctx->hot_prefix, ctx->hot_cols, ctx->samples,
+                  ctx->p_gbuf[1], ctx->p_gbuf[2], ctx->p_partial, ctx->p_hinge, ctx->p_bar, ctx->p_bar_flags, ctx->x_stats, ctx->hot_bits, ctx->hot_prefix, ctx->hot_cols, ctx->samples,
                   ctx->losses, ctx->preds};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -395,6 +398,10 @@ extern "C" int dsgd_load_csr(dsgd_ctx *ctx, int64_t n_rows, int64_t nnz, const i
   for (int64_t k = 0; k < nnz; ++k)
     NEED(col[k] >= 0 && col[k] < ctx->dim, DSGD_ERR_RANGE, "dsgd_load_csr: column %d at position %lld outside [0,%d)",
          col[k], (long long)k, ctx->dim);
+  bool unique = true;
+  for (int64_t r = 0; r < n_rows && unique; ++r)
+    for (int64_t k = row_ptr[r] + 1; k < row_ptr[r + 1]; ++k)
+      if (col[k] <= col[k - 1]) { unique = false; break; }
   CU(cudaSetDevice(ctx->device));
   for (void *p : {(void *)ctx->rp16, (void *)ctx->pairs, (void *)ctx->label}) if (p) CU(cudaFree(p));
   ctx->rp16 = nullptr; ctx->pairs = nullptr; ctx->label = nullptr;
@@ -419,7 +426,7 @@ extern "C" int dsgd_load_csr(dsgd_ctx *ctx, int64_t n_rows, int64_t nnz, const i
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaFree(d_rp)); CU(cudaFree(d_col)); CU(cudaFree(d_val));
-  ctx->n_rows = n_rows; ctx->nnz = nnz; ctx->n_pairs = n_pairs;
+  ctx->n_rows = n_rows; ctx->nnz = nnz; ctx->n_pairs = n_pairs; ctx->rows_unique = unique;
   return DSGD_OK;
 }
 
@@ -561,34 +568,18 @@ static inline int rows_grid(const dsgd_ctx *ctx, int64_t n) {
   return (int)std::min<int64_t>(std::max<int64_t>(cdiv(n, 8), 1), (int64_t)ctx->sm_count * 8);
 }
 
-// ---- streaming pass (large n): fp32 weights staged in shared memory, one persistent CTA per SM -----------------
+// ---- streaming pass (large n): fp32 weights staged in shared memory, one persistent CTA per SM (dsgd_stream.cuh) ----
 constexpr int64_t kStreamMinRows = 2048;
 
 static bool stream_eligible(const dsgd_ctx *ctx, int64_t n) {
-  static const bool off = getenv("DSGD_NO_STREAM") != nullptr;
-  return !off && n >= kStreamMinRows && (size_t)ctx->dim * sizeof(float) + 1024 <= 227u * 1024u;
+  return n >= kStreamMinRows && stream_smem_bytes(ctx->dim, false) + 1024 <= 227u * 1024u;
 }
 
-// experimental variants of the streaming kernel (DSGD_STREAM_OPT: 1 = fp32 fast path, 2 = hot-column accumulators for
-// the scatter, 3 = both; dsgd_stream.cuh, kOpt): not the default until measured
-static int stream_opt() {
-  const char *e = getenv("DSGD_STREAM_OPT");
-  const int v = e ? atoi(e) : 0;
-  return (v >= 0 && v <= 3) ? v : 0;
-}
-typedef void (*stream_kernel_t)(const StreamParamsX);
-template <bool kScatter, bool kPreds>
-static stream_kernel_t stream_variant(int opt) {
-  if constexpr (!kScatter) {
-    return k_stream_rows_x<kScatter, kPreds, 1>;
-  } else {
-    switch (opt) {
-      case 2: return k_stream_rows_x<kScatter, kPreds, 2>;
-      case 3: return k_stream_rows_x<kScatter, kPreds, 3>;
-      default: return k_stream_rows_x<kScatter, kPreds, 1>;
-    }
-  }
-}
+// TEMPORARY A/B switches of round 2's first GPU session (removed once measured): DSGD_STREAM_V1=1 runs round 1's kernel,
+// DSGD_STREAM_HOT=1 turns the hot-column accumulators of the scatter on.
+static bool stream_use_v1() { static const bool v = getenv("DSGD_STREAM_V1") != nullptr; return v; }
+static bool stream_use_hot() { static const bool v = getenv("DSGD_STREAM_HOT") && atoi(getenv("DSGD_STREAM_HOT")) != 0; return v; }
+
 // the kHotSlots most frequent columns (over all loaded rows) get a shared-memory slot: bitmap, per-word slot prefix and
 // slot -> column list, built once on the host from the column histogram
 static int stream_hot_prepare(dsgd_ctx *ctx) {
@@ -621,6 +612,7 @@ static int stream_hot_prepare(dsgd_ctx *ctx) {
     for (int b = 0; b < 32; ++b)
       if (bits[wd] >> b & 1u) cols.push_back((int32_t)(wd * 32 + (size_t)b));   // slot order = column order
   }
+  const int n = (int)cols.size();
   if (cols.empty()) cols.push_back(0);
   CU(cudaMalloc(&ctx->hot_bits, sizeof(uint32_t) * words));
   CU(cudaMalloc(&ctx->hot_prefix, sizeof(uint16_t) * words));
@@ -628,75 +620,70 @@ static int stream_hot_prepare(dsgd_ctx *ctx) {
   CU(cudaMemcpy(ctx->hot_bits, bits.data(), sizeof(uint32_t) * words, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(ctx->hot_prefix, prefix.data(), sizeof(uint16_t) * words, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(ctx->hot_cols, cols.data(), sizeof(int32_t) * cols.size(), cudaMemcpyHostToDevice));
-  int n = 0;
-  for (size_t wd = 0; wd < words; ++wd) n += __builtin_popcount(bits[wd]);
   ctx->n_hot = n;
+  return DSGD_OK;
+}
+
+template <bool kScatter, bool kPreds>
+static int stream_launch_v1(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t row_begin, int64_t n, const double *w_dev,
+                            const float *w32_dev, double *g, double *preds) {
+  const size_t smem = (size_t)ctx->dim * sizeof(float);
+  CU(cudaFuncSetAttribute(k_stream_rows_v1<kScatter, kPreds>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  StreamParamsV1 sp;
+  sp.rp16 = ctx->rp16; sp.units = reinterpret_cast<const uint4 *>(ctx->pairs); sp.label = ctx->label;
+  sp.samples = samples_dev; sp.row_begin = row_begin; sp.n = n; sp.w = w_dev; sp.w32 = w32_dev; sp.dim = ctx->dim;
+  sp.g = g; sp.preds = preds; sp.cnt = ctx->cnt; sp.n_exact = ctx->n_exact; sp.next_block = ctx->n_exact + 1;
+  CU(cudaMemsetAsync(ctx->n_exact + 1, 0, sizeof(unsigned long long), ctx->stream));
+  const int64_t blocks32 = (n + 31) / 32;
+  const int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, cdiv(blocks32, kStreamThreadsV1 / 32)));
+  auto *pe = prof_slot(ctx);
+  if (pe) cudaEventRecord(pe->first, ctx->stream);
+  k_stream_rows_v1<kScatter, kPreds><<<grid, kStreamThreadsV1, smem, ctx->stream>>>(sp);
+  if (pe) cudaEventRecord(pe->second, ctx->stream);
+  LAUNCHED();
+  CU(cudaGetLastError());
   return DSGD_OK;
 }
 
 template <bool kScatter, bool kPreds>
 static int stream_launch(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t row_begin, int64_t n, const double *w_dev,
                          const float *w32_dev, double *g, double *preds) {
-  int opt = stream_opt();
-  if (!kScatter) opt &= 1;
-  if ((opt & 2) && stream_smem_bytes(ctx->dim, 2) + 256 > 227u * 1024u) opt &= 1;   // no room for the slots beside the weights
-  if (opt) {
-    if (!ctx->stream_opt_ready) {
-      for (int o = 1; o <= 3; ++o) {
-        CU(cudaFuncSetAttribute((const void *)stream_variant<false, false>(o), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem_bytes(ctx->dim, 0)));
-        CU(cudaFuncSetAttribute((const void *)stream_variant<false, true>(o), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem_bytes(ctx->dim, 0)));
-        const size_t sm = (o & 2) && stream_smem_bytes(ctx->dim, 2) + 256 <= 227u * 1024u ? stream_smem_bytes(ctx->dim, 2) : stream_smem_bytes(ctx->dim, 0);
-        CU(cudaFuncSetAttribute((const void *)stream_variant<true, false>(o), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      }
-      ctx->stream_opt_ready = true;
-    }
-    if (opt & 2) {
-      int rc = stream_hot_prepare(ctx);
-      if (rc) return rc;
-    }
-    // a launch of the hot-column variant covers at most kHotMaxRows rows (limb headroom)
-    const int64_t max_rows = (opt & 2) ? kHotMaxRows : n;
-    for (int64_t off = 0; off < n; off += max_rows) {
-      const int64_t m = std::min<int64_t>(max_rows, n - off);
-      StreamParamsX sp;
-      memset(&sp, 0, sizeof sp);
-      sp.rp16 = ctx->rp16; sp.units = reinterpret_cast<const uint4 *>(ctx->pairs); sp.label = ctx->label;
-      sp.samples = samples_dev ? samples_dev + off : nullptr; sp.row_begin = row_begin + off; sp.n = m;
-      sp.w = w_dev; sp.w32 = w32_dev; sp.dim = ctx->dim;
-      sp.g = g; sp.preds = preds ? preds + off : nullptr; sp.cnt = ctx->cnt; sp.n_exact = ctx->n_exact; sp.next_block = ctx->n_exact + 1;
-      sp.hot_bits = ctx->hot_bits; sp.hot_prefix = ctx->hot_prefix; sp.hot_cols = ctx->hot_cols; sp.n_hot = ctx->n_hot;
-      CU(cudaMemsetAsync(ctx->n_exact + 1, 0, sizeof(unsigned long long), ctx->stream));
-      const int64_t blocks32 = (m + 31) / 32;
-      const int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, cdiv(blocks32, kStreamThreads / 32)));
-      auto *pe = prof_slot(ctx);
-      if (pe) cudaEventRecord(pe->first, ctx->stream);
-      stream_variant<kScatter, kPreds>(opt)<<<grid, kStreamThreads, stream_smem_bytes(ctx->dim, opt), ctx->stream>>>(sp);
-      if (pe) cudaEventRecord(pe->second, ctx->stream);
-      LAUNCHED();
-      CU(cudaGetLastError());
-    }
-    return DSGD_OK;
-  }
-  const size_t smem = (size_t)ctx->dim * sizeof(float);
+  if (stream_use_v1()) return stream_launch_v1<kScatter, kPreds>(ctx, samples_dev, row_begin, n, w_dev, w32_dev, g, preds);
+  const bool hot = kScatter && stream_use_hot() && stream_smem_bytes(ctx->dim, true) + 256 <= 227u * 1024u;
   if (!ctx->stream_ready) {
-    CU(cudaFuncSetAttribute(k_stream_rows<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaFuncSetAttribute(k_stream_rows<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaFuncSetAttribute(k_stream_rows<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k_stream_rows<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem_bytes(ctx->dim, false)));
+    CU(cudaFuncSetAttribute(k_stream_rows<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem_bytes(ctx->dim, false)));
+    CU(cudaFuncSetAttribute(k_stream_rows<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem_bytes(ctx->dim, false)));
+    if (stream_smem_bytes(ctx->dim, true) + 256 <= 227u * 1024u)
+      CU(cudaFuncSetAttribute(k_stream_rows<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem_bytes(ctx->dim, true)));
     ctx->stream_ready = true;
   }
-  StreamParams sp;
-  sp.rp16 = ctx->rp16; sp.units = reinterpret_cast<const uint4 *>(ctx->pairs); sp.label = ctx->label;
-  sp.samples = samples_dev; sp.row_begin = row_begin; sp.n = n; sp.w = w_dev; sp.w32 = w32_dev; sp.dim = ctx->dim;
-  sp.g = g; sp.preds = preds; sp.cnt = ctx->cnt; sp.n_exact = ctx->n_exact; sp.next_block = ctx->n_exact + 1;
-  CU(cudaMemsetAsync(ctx->n_exact + 1, 0, sizeof(unsigned long long), ctx->stream));
-  const int64_t blocks32 = (n + 31) / 32;
-  const int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, cdiv(blocks32, kStreamThreads / 32)));
-  auto *pe = prof_slot(ctx);
-  if (pe) cudaEventRecord(pe->first, ctx->stream);
-  k_stream_rows<kScatter, kPreds><<<grid, kStreamThreads, smem, ctx->stream>>>(sp);
-  if (pe) cudaEventRecord(pe->second, ctx->stream);
-  LAUNCHED();
-  CU(cudaGetLastError());
+  if (hot) {
+    int rc = stream_hot_prepare(ctx);
+    if (rc) return rc;
+  }
+  // a launch of the hot-column variant covers at most kHotMaxRows rows (limb headroom of the fixed-point slots)
+  const int64_t max_rows = hot ? kHotMaxRows : n;
+  for (int64_t off = 0; off < n; off += max_rows) {
+    const int64_t m = std::min<int64_t>(max_rows, n - off);
+    StreamParams sp;
+    memset(&sp, 0, sizeof sp);
+    sp.rp16 = ctx->rp16; sp.units = reinterpret_cast<const uint4 *>(ctx->pairs); sp.label = ctx->label;
+    sp.samples = samples_dev ? samples_dev + off : nullptr; sp.row_begin = row_begin + off; sp.n = m;
+    sp.w = w_dev; sp.w32 = w32_dev; sp.dim = ctx->dim;
+    sp.g = g; sp.preds = preds ? preds + off : nullptr; sp.cnt = ctx->cnt; sp.n_exact = ctx->n_exact; sp.next_block = ctx->n_exact + 1;
+    sp.hot_bits = ctx->hot_bits; sp.hot_prefix = ctx->hot_prefix; sp.hot_cols = ctx->hot_cols; sp.n_hot = ctx->n_hot;
+    CU(cudaMemsetAsync(ctx->n_exact + 1, 0, sizeof(unsigned long long), ctx->stream));
+    const int64_t blocks32 = (m + 31) / 32;
+    const int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, cdiv(blocks32, kStreamThreads / 32)));
+    auto *pe = prof_slot(ctx);
+    if (pe) cudaEventRecord(pe->first, ctx->stream);
+    if (kScatter && hot) k_stream_rows<kScatter, kPreds, kScatter><<<grid, kStreamThreads, stream_smem_bytes(ctx->dim, true), ctx->stream>>>(sp);
+    else k_stream_rows<kScatter, kPreds, false><<<grid, kStreamThreads, stream_smem_bytes(ctx->dim, false), ctx->stream>>>(sp);
+    if (pe) cudaEventRecord(pe->second, ctx->stream);
+    LAUNCHED();
+    CU(cudaGetLastError());
+  }
   return DSGD_OK;
 }
 
@@ -834,33 +821,27 @@ extern "C" int dsgd_comm_init(dsgd_ctx *ctx, const uint8_t id[DSGD_UNIQUE_ID_BYT
   return DSGD_OK;
 }
 
-// ---- persistent single-worker loop ------------------------------------------------------------------------
+// ---- persistent sync loop (dsgd_persistent.cuh) ----------------------------------------------------------------
 constexpr int kPCons = 8, kPUpd = 6, kPStages = 8, kPStagePairs = 2560, kPMaxChunks = 128;
 using PSmem = PersistSmem<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks>;
-#define DSGD_PERSIST_KERNEL k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 0>
-#define DSGD_PERSIST_KERNEL_MULTI2 k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 1>
-#define DSGD_PERSIST_KERNEL_MULTI k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 2>
-#define DSGD_PERSIST_KERNEL_MULTI3 k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 3>
-#define DSGD_PERSIST_KERNEL_MULTI4 k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 4>  // experimental
-// experimental single-GPU variants (DSGD_PERSIST_OPT=1..3; dsgd_persistent.cuh, kOpt): not the default until measured
 typedef void (*persist_kernel_t)(const PersistParams);
+template <bool kMulti>
 static persist_kernel_t persist_variant(int opt) {
-  switch (opt) {
-    case 1: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 0, 1>;
-    case 2: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 0, 2>;
-    case 3: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 0, 3>;
-    case 4: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 0, 4>;
-    case 5: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 0, 5>;
-    case 6: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 0, 6>;
-    case 7: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, 0, 7>;
-    default: return DSGD_PERSIST_KERNEL;
+  switch (opt & 3) {
+    case 0: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, kMulti, 0>;
+    case 1: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, kMulti, 1>;
+    case 2: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, kMulti, 2>;
+    default: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, kMulti, 3>;
   }
 }
+// TEMPORARY A/B switch of round 2's first GPU session (removed once measured): bit 0 = flag barrier, bit 1 = one-pass
+// single-chunk rows
 static int persist_opt() {
-  const char *e = getenv("DSGD_PERSIST_OPT");
-  const int v = e ? atoi(e) : 0;
-  return (v >= 0 && v <= 7) ? v : 0;
+  static const int v = getenv("DSGD_PERSIST_OPT") ? atoi(getenv("DSGD_PERSIST_OPT")) & 3 : 2;
+  return v;
 }
+static bool persist_timeline() { static const bool v = getenv("DSGD_PERSIST_TIMELINE") != nullptr; return v; }
+static size_t bar_flag_words(const dsgd_ctx *ctx) { return (size_t)kBarFlagStride * (size_t)(ctx->sm_count / kBarGroup + 1); }
 
 static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
   if (!ctx->p_ready) {
@@ -872,15 +853,11 @@ static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
     }
     CU(cudaMalloc(&ctx->p_partial, sizeof(double) * 2 * 2 * (size_t)ctx->sm_count));
     CU(cudaMalloc(&ctx->p_bar, sizeof(unsigned) * 4));
-    CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
-    CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL_MULTI, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
-    CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL_MULTI2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
-    CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL_MULTI3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
-    CU(cudaFuncSetAttribute(DSGD_PERSIST_KERNEL_MULTI4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
-    for (int opt = 1; opt <= 7; ++opt)
-      CU(cudaFuncSetAttribute((const void *)persist_variant(opt), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
-    CU(cudaMalloc(&ctx->p_bar_flags, sizeof(unsigned) * kBarFlagStride * (size_t)(ctx->sm_count / kBarGroup + 1)));
-    CU(cudaMalloc(&ctx->p_push, sizeof(double) * 2 * 2 * (size_t)ctx->sm_count * (size_t)ctx->sm_count));
+    for (int opt = 0; opt < 4; ++opt) {
+      CU(cudaFuncSetAttribute((const void *)persist_variant<false>(opt), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
+      CU(cudaFuncSetAttribute((const void *)persist_variant<true>(opt), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
+    }
+    CU(cudaMalloc(&ctx->p_bar_flags, sizeof(unsigned) * bar_flag_words(ctx)));
     ctx->p_ready = true;
   }
   if (ctx->p_hinge_cap < n_steps) {
@@ -893,16 +870,41 @@ static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
   return DSGD_OK;
 }
 
-// CTAs of the persistent kernel: every CTA owns at most kMaxRowsPerCta rows of a step.  0: batch too large.
+// CTAs of the persistent kernel: one per SM (measured in round 1 with tools/sweep_persist.py: fastest at batch 64, 256
+// and 1024); every CTA owns at most kMaxRowsPerCta rows of a step.  0: the batch is too large for this kernel.
 static int persist_grid(const dsgd_ctx *ctx, int64_t batch) {
-  const int g_min = cdiv(batch, kMaxRowsPerCta);
-  if (g_min > ctx->sm_count) return 0;
+  const int g = ctx->grid_limit > 0 ? std::min(ctx->grid_limit, ctx->sm_count) : ctx->sm_count;
+  if (cdiv(batch, kMaxRowsPerCta) > g) return 0;
   if (ctx->n_pairs >= (1ll << 31)) return 0;  // chunk descriptors carry a 31-bit global pair index
-  if (const char *e = getenv("DSGD_PERSIST_CTAS")) {
-    const int g = atoi(e);
-    if (g > 0) return std::max(g_min, std::min(g, ctx->sm_count));
+  return g;
+}
+// K GPUs: one column of the CTA's slice per barrier-synchronised thread
+static bool persist_multi_fits(const dsgd_ctx *ctx, int G) {
+  const int slice = (cdiv(ctx->dim + 1, G) + 31) & ~31;
+  return slice <= (kPCons + kPUpd) * 32;
+}
+
+// fields shared by the one-GPU and the K-GPU launch
+static int persist_params(dsgd_ctx *ctx, PersistParams &pp, const int32_t *samples_dev, int64_t n_per_step, int64_t n_steps,
+                          double lr, double *losses_dev, int opt) {
+  memset(&pp, 0, sizeof pp);
+  pp.rp16 = ctx->rp16; pp.pairs = ctx->pairs; pp.label = ctx->label; pp.samples = samples_dev;
+  pp.n_steps = n_steps; pp.batch = (int32_t)n_per_step; pp.dim = ctx->dim;
+  pp.wbuf[0] = ctx->p_wbuf[0]; pp.wbuf[1] = ctx->p_wbuf[1];
+  for (int i = 0; i < 3; ++i) pp.gbuf[i] = ctx->p_gbuf[i];
+  pp.d = ctx->d; pp.partial = ctx->p_partial; pp.hinge = ctx->p_hinge; pp.losses = losses_dev;
+  pp.w_out = ctx->w; pp.w32_out = ctx->w32; pp.scal = ctx->scal;
+  pp.bar = ctx->p_bar; pp.abort_flag = reinterpret_cast<int *>(ctx->p_bar + 1); pp.bar_flags = ctx->p_bar_flags;
+  pp.lambda = ctx->lambda; pp.lr = lr; pp.world = 1;
+  CU(cudaMemsetAsync(ctx->p_hinge, 0, sizeof(unsigned) * (size_t)n_steps, ctx->stream));
+  CU(cudaMemsetAsync(ctx->p_bar, 0, sizeof(unsigned) * 4, ctx->stream));
+  if (opt & 1) CU(cudaMemsetAsync(ctx->p_bar_flags, 0, sizeof(unsigned) * bar_flag_words(ctx), ctx->stream));
+  if (persist_timeline()) {
+    if (!ctx->p_tl) CU(cudaMalloc(&ctx->p_tl, sizeof(long long) * kTlWords));
+    CU(cudaMemsetAsync(ctx->p_tl, 0, sizeof(long long) * kTlWords, ctx->stream));
+    pp.tl = ctx->p_tl;
   }
-  return ctx->sm_count;  // measured (tools/sweep_persist.py): one CTA per SM is fastest at batch 64, 256 and 1024
+  return DSGD_OK;
 }
 
 static int persist_run(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t n_per_step, int64_t n_steps, double lr,
@@ -911,55 +913,37 @@ static int persist_run(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t n_per_
   if (rc) return rc;
   const int G = persist_grid(ctx, n_per_step);
   NEED((uint64_t)G * (uint64_t)(n_steps + 2) < (1ull << 32), DSGD_ERR_INVALID, "dsgd_sync_steps: too many steps for one launch");
-  const size_t vd = sizeof(double) * (size_t)ctx->dim;
-  CU(cudaMemcpyAsync(ctx->p_wbuf[1], ctx->w, vd, cudaMemcpyDeviceToDevice, ctx->stream));
-  CU(cudaMemsetAsync(ctx->p_hinge, 0, sizeof(unsigned) * (size_t)n_steps, ctx->stream));
-  CU(cudaMemsetAsync(ctx->p_bar, 0, sizeof(unsigned) * 4, ctx->stream));
-  PersistParams pp;
-  memset(&pp, 0, sizeof pp);
-  pp.world = 1;
-  pp.rp16 = ctx->rp16; pp.pairs = ctx->pairs; pp.label = ctx->label; pp.samples = samples_dev;
-  pp.n_steps = n_steps; pp.batch = (int32_t)n_per_step; pp.dim = ctx->dim;
-  pp.wbuf[0] = ctx->p_wbuf[0]; pp.wbuf[1] = ctx->p_wbuf[1];
-  for (int i = 0; i < 3; ++i) pp.gbuf[i] = ctx->p_gbuf[i];
-  pp.d = ctx->d; pp.partial = ctx->p_partial; pp.hinge = ctx->p_hinge; pp.losses = losses_dev;
-  pp.w_out = ctx->w; pp.w32_out = ctx->w32; pp.scal = ctx->scal;
-  pp.bar = ctx->p_bar; pp.abort_flag = reinterpret_cast<int *>(ctx->p_bar + 1);
-  pp.lambda = ctx->lambda; pp.lr = lr; pp.k_den = 1.0;
   const int opt = persist_opt();
-  if (opt & 1) CU(cudaMemsetAsync(ctx->p_bar_flags, 0, sizeof(unsigned) * kBarFlagStride * (size_t)(ctx->sm_count / kBarGroup + 1), ctx->stream));
-  pp.bar_flags = ctx->p_bar_flags; pp.push = ctx->p_push;
-  pp.tl = nullptr;
-  if (getenv("DSGD_PERSIST_TIMELINE")) {
-    if (!ctx->p_tl) CU(cudaMalloc(&ctx->p_tl, sizeof(long long) * (256 * 16 + 4 * 160 * 2)));
-    CU(cudaMemsetAsync(ctx->p_tl, 0, sizeof(long long) * (256 * 16 + 4 * 160 * 2), ctx->stream));
-    pp.tl = ctx->p_tl;
-  }
+  PersistParams pp;
+  if ((rc = persist_params(ctx, pp, samples_dev, n_per_step, n_steps, lr, losses_dev, opt))) return rc;
+  CU(cudaMemcpyAsync(ctx->p_wbuf[1], ctx->w, sizeof(double) * (size_t)ctx->dim, cudaMemcpyDeviceToDevice, ctx->stream));
+  pp.k_den = 1.0;
   pp.timeout_cycles = 4000000000ll;  // ~2 s at 1.9 GHz: a healthy barrier takes well under a microsecond
   void *args[] = {&pp};
   auto *pe = prof_slot(ctx);
   if (pe) cudaEventRecord(pe->first, ctx->stream);
-  CU(cudaLaunchCooperativeKernel((void *)persist_variant(opt), dim3(G), dim3((kPCons + kPUpd + 1) * 32), args, sizeof(PSmem),
+  CU(cudaLaunchCooperativeKernel((void *)persist_variant<false>(opt), dim3(G), dim3((kPCons + kPUpd + 1) * 32), args, sizeof(PSmem),
                                  ctx->stream));
   if (pe) cudaEventRecord(pe->second, ctx->stream);
   LAUNCHED();
   return DSGD_OK;
 }
 
-// ---- fused multi-GPU loop: all ranks run the persistent kernel and exchange gradients through peer memory ----
-// exported block of a rank: receive area [sender][parity][dim + 8] doubles, then flag words [sender][cta] (u64)
-constexpr int kXFlagCtas = 192;
-static size_t xblk_llw_offset(const dsgd_ctx *ctx) {  // an LL element is 16 bytes = 2 doubles' worth
-  return 2 * (size_t)kMaxWorld * 2 * (size_t)(ctx->dim + kReplicaPad) + (size_t)kMaxWorld * kXFlagCtas;
-}
-// ... followed (DSGD_P2P_MODE=4) by the rank's two LL weight buffers, which the column owners on the peers store into
-static size_t xblk_doubles(const dsgd_ctx *ctx) { return xblk_llw_offset(ctx) + 2 * 2 * (size_t)(ctx->dim + kReplicaPad); }
+// ---- fused K-GPU loop: all ranks run the persistent kernel and exchange gradients through peer memory ----
+// exported block of a rank (in 8-byte words): value words [sender][parity][dim + 8] x 2, then bitmap words
+// [sender][parity][ceil((dim + 1) / 32)]
+static size_t xblk_stride(const dsgd_ctx *ctx) { return (size_t)(ctx->dim + kReplicaPad); }
+static size_t xblk_words(const dsgd_ctx *ctx) { return ((size_t)ctx->dim + 1 + 31) / 32; }
+static size_t xblk_bm_offset(const dsgd_ctx *ctx) { return 2 * (size_t)kMaxWorld * 2 * xblk_stride(ctx); }
+static size_t xblk_doubles(const dsgd_ctx *ctx) { return xblk_bm_offset(ctx) + (size_t)kMaxWorld * 2 * xblk_words(ctx); }
 
 static int xblk_ensure(dsgd_ctx *ctx) {
   if (ctx->xblk) return DSGD_OK;
   CU(cudaSetDevice(ctx->device));
   CU(cudaMalloc(&ctx->xblk, sizeof(double) * xblk_doubles(ctx)));
   CU(cudaMemset(ctx->xblk, 0, sizeof(double) * xblk_doubles(ctx)));
+  CU(cudaMalloc(&ctx->x_stats, sizeof(unsigned long long) * 4));
+  CU(cudaMemset(ctx->x_stats, 0, sizeof(unsigned long long) * 4));
   return DSGD_OK;
 }
 
@@ -974,75 +958,66 @@ static int persist_run_multi(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t 
                              double *losses_dev) {
   int rc = persist_prepare(ctx, n_steps);
   if (rc) return rc;
-  const int G = ctx->sm_count;  // the same on every rank
-  NEED((uint64_t)G * (uint64_t)(2 * n_steps + 2) < (1ull << 32), DSGD_ERR_INVALID, "dsgd_sync_steps: too many steps for one launch");
-  const size_t vd = sizeof(double) * (size_t)ctx->dim;
-  CU(cudaMemcpyAsync(ctx->p_wbuf[ctx->x_step & 1], ctx->w, vd, cudaMemcpyDeviceToDevice, ctx->stream));
-  CU(cudaMemsetAsync(ctx->p_hinge, 0, sizeof(unsigned) * (size_t)n_steps, ctx->stream));
-  CU(cudaMemsetAsync(ctx->p_bar, 0, sizeof(unsigned) * 4, ctx->stream));
+  const int G = persist_grid(ctx, n_per_step);
+  NEED((uint64_t)G * (uint64_t)(n_steps + 2) < (1ull << 32), DSGD_ERR_INVALID, "dsgd_sync_steps: too many steps for one launch");
+  const int opt = persist_opt();
   PersistParams pp;
-  memset(&pp, 0, sizeof pp);
-  pp.rp16 = ctx->rp16; pp.pairs = ctx->pairs; pp.label = ctx->label; pp.samples = samples_dev;
-  pp.n_steps = n_steps; pp.batch = (int32_t)n_per_step; pp.dim = ctx->dim;
-  pp.wbuf[0] = ctx->p_wbuf[0]; pp.wbuf[1] = ctx->p_wbuf[1];
-  for (int i = 0; i < 3; ++i) pp.gbuf[i] = ctx->p_gbuf[i];
-  pp.d = ctx->d; pp.partial = ctx->p_partial; pp.hinge = ctx->p_hinge; pp.losses = losses_dev;
-  pp.w_out = ctx->w; pp.w32_out = ctx->w32; pp.scal = ctx->scal;
-  pp.bar = ctx->p_bar; pp.abort_flag = reinterpret_cast<int *>(ctx->p_bar + 1);
-  pp.lambda = ctx->lambda; pp.lr = lr; pp.k_den = (double)ctx->world;
+  if ((rc = persist_params(ctx, pp, samples_dev, n_per_step, n_steps, lr, losses_dev, opt))) return rc;
+  // the kernel's first interval reads the host-provided weights from wbuf[0] and publishes them in LL form
+  CU(cudaMemcpyAsync(ctx->p_wbuf[0], ctx->w, sizeof(double) * (size_t)ctx->dim, cudaMemcpyDeviceToDevice, ctx->stream));
+  pp.k_den = (double)ctx->world;
   pp.timeout_cycles = 20000000000ll;  // ~10 s: covers a peer that launches late
-  pp.tl = nullptr;
-  if (getenv("DSGD_PERSIST_TIMELINE")) {
-    if (!ctx->p_tl) CU(cudaMalloc(&ctx->p_tl, sizeof(long long) * (256 * 16 + 4 * 160 * 2)));
-    CU(cudaMemsetAsync(ctx->p_tl, 0, sizeof(long long) * (256 * 16 + 4 * 160 * 2), ctx->stream));
-    pp.tl = ctx->p_tl;
-  }
   pp.world = ctx->world; pp.rank = ctx->rank; pp.step_base = ctx->x_step;
-  const size_t stride = (size_t)(ctx->dim + kReplicaPad);
-  NEED(G <= kXFlagCtas, DSGD_ERR_INVALID, "more SMs than flag words");
-  pp.xstride = (int)stride;
-  for (int b = 0; b < 3; ++b) pp.xg[b] = ctx->p_gbuf[b];   // local: peers never read them, they receive pushed copies
+  pp.xstride = (int)xblk_stride(ctx);
+  pp.xwords = (int)xblk_words(ctx);
   for (int r = 0; r < ctx->world; ++r) {
-    double *base = (r == ctx->rank) ? ctx->xblk : ctx->peer_x[r];
-    pp.xrecv[r] = base;
-    pp.xflag[r] = reinterpret_cast<unsigned long long *>(base + 2 * (size_t)kMaxWorld * 2 * stride);
+    unsigned long long *blk = reinterpret_cast<unsigned long long *>((r == ctx->rank) ? ctx->xblk : ctx->peer_x[r]);
+    pp.xval[r] = blk;
+    pp.xbm[r] = blk + xblk_bm_offset(ctx);
   }
+  if (!ctx->x_llw) {
+    CU(cudaMalloc(&ctx->x_llw, 2 * 2 * sizeof(unsigned long long) * xblk_stride(ctx)));
+    CU(cudaMemsetAsync(ctx->x_llw, 0, 2 * 2 * sizeof(unsigned long long) * xblk_stride(ctx), ctx->stream));
+  }
+  pp.llw[0] = ctx->x_llw;
+  pp.llw[1] = ctx->x_llw + 2 * xblk_stride(ctx);
+  pp.xstats = ctx->x_stats;
   void *args[] = {&pp};
   auto *pe = prof_slot(ctx);
   if (pe) cudaEventRecord(pe->first, ctx->stream);
-  // variants kept for A/B measurements: DSGD_P2P_MODE=1 two grid barriers per step, 2 one barrier with the K-way
-  // reduction done by the consumers per gathered non-zero, 3 (default) one barrier with LL-word weights
-  static const int mode_env = getenv("DSGD_P2P_MODE") ? atoi(getenv("DSGD_P2P_MODE")) : 3;
-  // mode 3 updates one column per thread: the CTA's column slice must fit the barrier-synchronised threads
-  const int mode = ((mode_env == 3 || mode_env == 4) && cdiv(ctx->dim + 1, G) > (kPCons + kPUpd) * 32) ? 2 : mode_env;
-  void *fn = mode == 1 ? (void *)DSGD_PERSIST_KERNEL_MULTI2 : mode == 2 ? (void *)DSGD_PERSIST_KERNEL_MULTI
-           : mode == 4 ? (void *)DSGD_PERSIST_KERNEL_MULTI4 : (void *)DSGD_PERSIST_KERNEL_MULTI3;
-  if (mode == 4) {
-    // LL weight buffers live in the exported block so that the column owners on the peers can store into them
-    for (int r = 0; r < ctx->world; ++r) {
-      double *blk = (r == ctx->rank) ? ctx->xblk : ctx->peer_x[r];
-      unsigned long long *llw = reinterpret_cast<unsigned long long *>(blk + xblk_llw_offset(ctx));
-      pp.xllw[r][0] = llw;
-      pp.xllw[r][1] = llw + 2 * (size_t)(ctx->dim + kReplicaPad);
-    }
-    CU(cudaMemcpyAsync(ctx->p_wbuf[0], ctx->w, vd, cudaMemcpyDeviceToDevice, ctx->stream));
-  }
-  if (mode == 3) {
-    if (!ctx->x_llw) {
-      CU(cudaMalloc(&ctx->x_llw, 2 * 2 * sizeof(unsigned long long) * (size_t)(ctx->dim + kReplicaPad)));
-      CU(cudaMemsetAsync(ctx->x_llw, 0, 2 * 2 * sizeof(unsigned long long) * (size_t)(ctx->dim + kReplicaPad), ctx->stream));
-    }
-    pp.llw[0] = ctx->x_llw;
-    pp.llw[1] = ctx->x_llw + 2 * (size_t)(ctx->dim + kReplicaPad);
-    // the kernel's first interval reads the host-provided weights from wbuf[0]
-    CU(cudaMemcpyAsync(ctx->p_wbuf[0], ctx->w, vd, cudaMemcpyDeviceToDevice, ctx->stream));
-  }
-  CU(cudaLaunchCooperativeKernel(fn, dim3(G), dim3((kPCons + kPUpd + 1) * 32), args, sizeof(PSmem), ctx->stream));
+  CU(cudaLaunchCooperativeKernel((void *)persist_variant<true>(opt), dim3(G), dim3((kPCons + kPUpd + 1) * 32), args, sizeof(PSmem),
+                                 ctx->stream));
   if (pe) cudaEventRecord(pe->second, ctx->stream);
   LAUNCHED();
-  // +3: the next launch must not meet LL words carrying tags this one used (the host may install new weights in
-  // between), and a multiple of 3 keeps the rotation of the three gradient buffers (the dirty one is re-zeroed before use)
-  ctx->x_step += n_steps + 3;
+  // The next launch must not meet LL words carrying tags this one used (the host may install new weights in between): the
+  // step counter jumps.  By 6: a multiple of 3 keeps the rotation of the three gradient buffers (the dirty one is re-zeroed
+  // before use), and an EVEN jump makes the first push of launch n+1 (its second interval) land in the receive parity that
+  // a slow peer is NOT reading in launch n's last interval (+3 put them on the same one: ADVICE.md round 1).
+  ctx->x_step += n_steps + 6;
+  ctx->x_steps_run += n_steps;
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_set_grid_limit(dsgd_ctx *ctx, int32_t n_ctas) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(n_ctas >= 0, DSGD_ERR_INVALID, "dsgd_set_grid_limit: negative");
+  ctx->grid_limit = n_ctas;
+  return DSGD_OK;
+}
+
+// Diagnostic for the bandwidth figures of the fused K-GPU step: words this rank has pushed to EACH peer so far (a value word
+// is 16 bytes on the wire, a bitmap word 8) and the SGD steps of those launches.
+extern "C" int dsgd_xchg_stats(dsgd_ctx *ctx, int64_t *value_words, int64_t *bitmap_words, int64_t *steps) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  unsigned long long host[2] = {0, 0};
+  if (ctx->x_stats) {
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(host, ctx->x_stats, sizeof host, cudaMemcpyDeviceToHost));
+  }
+  if (value_words) *value_words = (int64_t)host[0];
+  if (bitmap_words) *bitmap_words = (int64_t)host[1];
+  if (steps) *steps = ctx->x_steps_run;
   return DSGD_OK;
 }
 
@@ -1103,12 +1078,13 @@ static int persist_check(dsgd_ctx *ctx) {  // after a stream sync: did a device-
   return DSGD_OK;
 }
 
-// Debug: copies the last persistent run's clock64 timeline (256 steps x 16 stamps) out; needs DSGD_PERSIST_TIMELINE.
+// Debug: copies the last persistent run's timeline out (include/dsgd.h); needs DSGD_PERSIST_TIMELINE.
+static_assert(kTlWords == DSGD_TIMELINE_WORDS, "timeline layout");
 extern "C" int dsgd_debug_timeline(dsgd_ctx *ctx, long long *out) {
   if (!ctx || !out) return DSGD_ERR_INVALID;
   NEED(ctx->p_tl, DSGD_ERR_STATE, "no timeline recorded (set DSGD_PERSIST_TIMELINE=1)");
   CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaMemcpy(out, ctx->p_tl, sizeof(long long) * (256 * 16 + 4 * 160 * 2), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(out, ctx->p_tl, sizeof(long long) * kTlWords, cudaMemcpyDeviceToHost));
   return DSGD_OK;
 }
 
@@ -1158,14 +1134,12 @@ extern "C" int dsgd_sync_steps_staged(dsgd_ctx *ctx, int64_t first, int64_t n_pe
   const int fin_blocks = cdiv(ctx->dim + 1, 256);
   const int32_t k_total = ctx->k_total > 0 ? ctx->k_total : ctx->world;
   const bool single = (ctx->world == 1 && ctx->n_local == 1 && k_total == 1);
-  static const bool no_persist = getenv("DSGD_NO_PERSIST") != nullptr;
-  if (single && !no_persist && n_steps > 0 && persist_grid(ctx, n_per_step) > 0) {
+  if (single && n_steps > 0 && persist_grid(ctx, n_per_step) > 0) {
     // one worker on one GPU: the whole run of steps is one persistent cooperative kernel
     return persist_run(ctx, ctx->samples + first, n_per_step, n_steps, lr, want_losses ? ctx->losses : nullptr);
   }
-  static const bool no_p2p = getenv("DSGD_NO_P2P") != nullptr;
-  if (!no_p2p && !no_persist && ctx->world > 1 && ctx->n_local == 1 && k_total == ctx->world && n_steps > 0 &&
-      xchg_complete(ctx) && persist_grid(ctx, n_per_step) > 0) {
+  if (ctx->world > 1 && ctx->n_local == 1 && k_total == ctx->world && n_steps > 0 && xchg_complete(ctx) &&
+      persist_grid(ctx, n_per_step) > 0 && persist_multi_fits(ctx, persist_grid(ctx, n_per_step))) {
     // one worker per GPU, every peer's exchange block mapped: aggregate inside the persistent kernel over NVLink
     return persist_run_multi(ctx, ctx->samples + first, n_per_step, n_steps, lr, want_losses ? ctx->losses : nullptr);
   }
@@ -1356,8 +1330,9 @@ static int async_launch(dsgd_ctx *ctx, const double *w0, const int32_t *assigned
   CU(cudaStreamSynchronize(ctx->stream));  // inputs in place before the loop's own stream starts
   if (!ctx->a_ev0) { CU(cudaEventCreate(&ctx->a_ev0)); CU(cudaEventCreate(&ctx->a_ev1)); }
   CU(cudaEventRecord(ctx->a_ev0, st));
-  static const bool b1_fast = getenv("DSGD_ASYNC_OPT") && atoi(getenv("DSGD_ASYNC_OPT")) == 1;   // experimental, see dsgd_async.cuh
-  if (b1_fast && batch == 1) k_async_worker_b1<<<cdiv(lanes, 4), 128, 0, st>>>(ap);
+  // batch 1 on rows with unique columns (what the reference's Map rows are): the delta of every non-zero is formed straight
+  // from the pair, without the per-lane scratch vector
+  if (batch == 1 && ctx->rows_unique) k_async_worker_b1<<<cdiv(lanes, 4), 128, 0, st>>>(ap);
   else k_async_worker<<<cdiv(lanes, 4), 128, 0, st>>>(ap);
   CU(cudaEventRecord(ctx->a_ev1, st));
   LAUNCHED();

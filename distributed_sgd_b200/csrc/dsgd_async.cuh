@@ -162,8 +162,8 @@ __global__ void __launch_bounds__(128) k_async_worker(const AsyncParams p) {
   }
 }
 
-// EXPERIMENTAL (DSGD_ASYNC_OPT=1, batch 1 only; written after the round's GPU budget ran out, never run): the same loop
-// body without the per-lane scratch vector.  With one sample per iteration the batch sum IS the row's backward, so the
+// Batch 1 on rows with unique columns (dsgd_load_csr checks; the reference's rows are Maps): the same loop body without the
+// per-lane scratch vector.  With one sample per iteration the batch sum IS the row's backward, so the
 // delta of every non-zero is formed straight from the pair: two dependent L2 round trips (scratch write + read-back and
 // claim) leave the per-update latency chain, and throughput here is lanes / latency.  Same arithmetic as the general
 // path for B = 1 (sum = 0 + y*x, mean = sum / 1.0); requires unique columns within a row, like the reference's Map rows.

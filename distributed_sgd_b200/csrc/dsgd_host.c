@@ -298,3 +298,79 @@ int64_t dsgd_jvm_sync_epoch(uint64_t *state, int64_t n_rows, int64_t group_size,
   free(buf);
   return steps;
 }
+
+/* ---- batch draws of one epoch of Master.fit (core/Master.scala:179-187), fast form ----------------------------------
+ * The reference shuffles every worker's whole index range afresh for every step and takes the slice
+ * [batch, batch + B) of it (quirk Q5): a slice of a fresh uniform permutation is a uniform draw WITHOUT replacement of
+ * min(B, len - batch) rows of the range.  This draws exactly that, for all steps and groups of one epoch, with Floyd's
+ * subset sampling (O(B) per draw instead of the O(len) shuffle) from a counter-based generator keyed by
+ * (seed, epoch, step, group): every rank draws the same batches, steps are independent (parallel), and the draw of
+ * epoch e + 1 can be made while epoch e runs on the GPU.
+ *   groups: n_groups ranges [g_start[k], g_start[k] + g_len[k]);  steps = ceil(max_k g_len[k] / B)
+ *   out[(step * n_groups + k) * B + i] = row id, -1 where the slice is shorter than B; counts[step * n_groups + k] =
+ *   rows drawn.  Returns the number of steps, or < 0. */
+int64_t dsgd_draw_epoch(uint64_t seed, int64_t epoch, int32_t n_groups, const int64_t *g_start, const int64_t *g_len,
+                        int32_t batch_size, int32_t *out, int32_t *counts, int64_t out_capacity) {
+  if (n_groups <= 0 || batch_size <= 0 || !g_start || !g_len || !out || !counts) return -1;
+  int64_t max_len = 0;
+  for (int32_t k = 0; k < n_groups; ++k) {
+    if (g_len[k] < 0 || g_start[k] < 0 || g_start[k] + g_len[k] > (int64_t)INT32_MAX) return -1;
+    if (g_len[k] > max_len) max_len = g_len[k];
+  }
+  const int64_t steps = (max_len + batch_size - 1) / batch_size;
+  if (steps * n_groups * (int64_t)batch_size > out_capacity) return -2;
+  int hbits = 4;
+  while ((1 << hbits) < 4 * batch_size) ++hbits;       /* open addressing, load <= 1/4 */
+  const uint32_t hmask = (1u << hbits) - 1u;
+  int failed = 0;
+#pragma omp parallel
+  {
+    int64_t *table = (int64_t *)malloc(sizeof(int64_t) * ((size_t)hmask + 1));
+    if (!table) {
+#pragma omp atomic write
+      failed = 1;
+    } else {
+#pragma omp for schedule(static)
+      for (int64_t s = 0; s < steps; ++s) {
+        for (int32_t k = 0; k < n_groups; ++k) {
+          const int64_t len = g_len[k], batch = s * (int64_t)batch_size;
+          int64_t m = len - batch;
+          if (m > batch_size) m = batch_size;
+          if (m < 0) m = 0;
+          int32_t *dst = out + (s * n_groups + k) * (int64_t)batch_size;
+          counts[s * n_groups + k] = (int32_t)m;
+          for (int64_t i = m; i < batch_size; ++i) dst[i] = -1;
+          if (m == 0) continue;
+          rng_t g = rng_for(seed ^ 0x5EEDBA7C4ull ^ ((uint64_t)epoch << 20), (uint64_t)(s * n_groups + k));
+          for (uint32_t i = 0; i <= hmask; ++i) table[i] = -1;
+          /* Floyd: for j = len - m .. len - 1: t = uniform[0, j]; take t unless already taken, then take j */
+          int64_t n_out = 0;
+          for (int64_t j = len - m; j < len; ++j) {
+            /* unbiased bounded draw: 64-bit multiply-shift with rejection (Lemire) */
+            const uint64_t range = (uint64_t)j + 1;
+            uint64_t x = splitmix64(&g.s);
+            __uint128_t mm = (__uint128_t)x * range;
+            uint64_t lo = (uint64_t)mm;
+            if (lo < range) {
+              const uint64_t thr = (0 - range) % range;
+              while (lo < thr) { x = splitmix64(&g.s); mm = (__uint128_t)x * range; lo = (uint64_t)mm; }
+            }
+            int64_t t = (int64_t)(mm >> 64);
+            uint32_t h = (uint32_t)((uint64_t)t * 0x9E3779B97F4A7C15ull >> 40) & hmask;
+            int taken = 0;
+            while (table[h] >= 0) { if (table[h] == t) { taken = 1; break; } h = (h + 1) & hmask; }
+            if (taken) {
+              t = j;
+              h = (uint32_t)((uint64_t)t * 0x9E3779B97F4A7C15ull >> 40) & hmask;
+              while (table[h] >= 0) h = (h + 1) & hmask;
+            }
+            table[h] = t;
+            dst[n_out++] = (int32_t)(g_start[k] + t);
+          }
+        }
+      }
+      free(table);
+    }
+  }
+  return failed ? -3 : steps;
+}

@@ -35,6 +35,9 @@ enum Cnt : int {
 
 __device__ __forceinline__ double filt(double v) { return fabs(v) > kEps ? v : 0.0; }  // Sparse.scala:108-118
 
+// prediction = -signum(x . w)  (core/ml/SparseSVM.scala:14)
+__device__ __forceinline__ int pred_of(double dot) { return (dot > 0.0) ? -1 : ((dot < 0.0) ? 1 : 0); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

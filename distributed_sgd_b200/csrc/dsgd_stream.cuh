@@ -1,18 +1,28 @@
 // dsgd_stream.cuh -- streaming pass over many row windows: Master.localLoss/localAccuracy (core/Master.scala:
 // 100-107), SlaveImpl.forward (core/Slave.scala:129-140) and large-batch SlaveImpl.gradient (142-157).
 //
-// This is the HBM-bound form of the hot path (roofline: 8*nnz + 16 bytes per sample).  What the
-// kernel does to stay on the HBM roof instead of the L2 one:
-//   * the weight vector is staged ONCE per CTA into shared memory as fp32 (47 236 x 4 B = 189 KB of the 227 KB),
-//     so the ~94 gathers per row hit shared-memory banks, not L2 sectors (a 4-byte gather costs a 32-byte
-//     sector at L2: 4x the row stream itself);
-//   * one persistent CTA per SM, 32 warps; a warp owns blocks of 32 consecutive rows (~24 KB contiguous), loads
-//     their bounds and labels with one coalesced access, and two 16-lane groups walk rows with 128-bit loads
-//     (2 pairs per lane); the next block's bounds are fetched while the current block is processed;
-//   * products are exact in fp64 ((double)x * (double)w32) and accumulated in fp64.
-// Exactness against the fp64 weights the reference uses: rounding w to fp32 perturbs x.w by at most
-// 2^-24 * max|w| * sum|x_j|.  Rows whose |x.w| is inside that band (about one in a million) are recomputed with
-// the fp64 weights from L2, so predictions and gate decisions are those of the fp64 arithmetic.
+// This is the HBM-bound form of the hot path (roofline: 8*nnz + 16 bytes per sample).
+//   * The weight vector is staged ONCE per CTA into shared memory as fp32 (47 236 x 4 B = 189 KB of the 227 KB),
+//     so the ~94 gathers per row hit shared-memory banks, not 32-byte L2 sectors.  One persistent CTA per SM.
+//   * FLAT STREAM.  A warp owns blocks of 32 rows and walks their 16-byte units (2 pairs) as ONE virtual
+//     stream: unit v of the block belongs to the row whose prefix-sum interval contains v, found with one ballot
+//     and one or-reduction per 32 units -- every lane loads a useful unit whatever the row lengths are (round 1
+//     walked a row per 16-lane group: 47 of 64 load slots used on the mean row, long rows serialised), kUnroll
+//     128-bit loads per lane are in flight before the first is used (64 KB per SM), and consecutive rows of an
+//     evaluation pass make every warp load one contiguous 512-byte request.
+//   * The dot is needed for its SIGN only (prediction, gate: SparseSVM.scala:14,28), so it is accumulated with fp32
+//     FMAs against the fp32 weights -- no fp32->fp64 conversions (ncu, round 1: the XU pipe they run on was 46 %
+//     busy).  A lane accumulates its units of the open row; the warp reduces once per ROW END, not per load.
+//   * Exactness against the fp64 arithmetic of the reference: the fp32 result differs from x.w by at most
+//       (D + 1) * 2^-24 * max|w| * sum|x|,   D = units/32 + 9 roundings on the longest add chain, + 1 for rounding w
+//     (first-order bound, 1.5x slack).  Rows whose |dot| is inside that band are recomputed with the fp64 weights
+//     from L2 after the block's stream, so every prediction and gate decision is that of the fp64 arithmetic
+//     (tests/test_gpu_parity.py::test_streaming_exact_fallback_decides_like_fp64).
+//   * Scatter (gradient): rows that pass the gate are re-walked after the block's stream (their units are in
+//     L1/L2) and y*x goes to g with fp64 REDs.  kHot: the kHotSlots most frequent columns get a per-CTA exact
+//     fixed-point accumulator in the shared memory left beside the weights (three 32-bit limbs of g * 2^40; shared
+//     memory has native 32-bit atomics only), flushed with one RED per touched slot: the RED rate at L2
+//     (0.48 per SM-cycle, tools/microbench.cu) is what bounds a large-batch gradient on untrained weights.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -22,6 +32,9 @@
 namespace dsgd {
 
 constexpr int kStreamThreads = 1024;
+constexpr int kStreamUnroll = 4;
+constexpr int kHotSlots = 2688;
+constexpr int64_t kHotMaxRows = 1 << 18;   // limb headroom: 2^18 adds of < 2^14 (resp. <= 2^12 in magnitude)
 
 struct StreamParams {
   const uint32_t *rp16;
@@ -35,11 +48,21 @@ struct StreamParams {
   double *g;               // scatter target (fp64, L2) or nullptr
   double *preds;           // per-sample predictions or nullptr
   unsigned long long *cnt; // kCntHinge / kCntCorrect
-  unsigned long long *n_exact;  // how many rows took the exact fallback (diagnostic), may be nullptr
+  unsigned long long *n_exact;     // rows that took the exact fallback (diagnostic)
   unsigned long long *next_block;  // work counter (zero on entry): blocks beyond the first wave are claimed dynamically
+  const uint32_t *hot_bits;    // kHot: bit c set = column c has a shared-memory accumulator slot
+  const uint16_t *hot_prefix;  //       slots before word c >> 5 (slot = prefix + popc of the lower bits of the word)
+  const int32_t *hot_cols;     //       slot -> column
+  int n_hot;                   //       slots in use (<= kHotSlots)
 };
 
-template <bool kScatter, bool kPreds>
+__host__ __device__ constexpr size_t stream_smem_bytes(int dim, bool hot) {
+  const size_t ws = (((size_t)dim + 3) & ~(size_t)3) * sizeof(float);
+  const size_t words = ((size_t)dim + 31) / 32;
+  return hot ? ws + (size_t)kHotSlots * 12 + words * 4 + ((words * 2 + 15) & ~(size_t)15) : ws;
+}
+
+template <bool kScatter, bool kPreds, bool kHot>
 __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *ws = reinterpret_cast<float *>(smem_raw);
@@ -47,6 +70,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
   __shared__ unsigned long long s_cnt[2];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
   // ---- stage the fp32 weights, find max|w| ----
   float wmax = 0.f;
   {
@@ -67,118 +91,203 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
     for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
     if (lane == 0) s_wmax[warp] = wmax;
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0ull;
+    if constexpr (kHot) {
+      const int words = (p.dim + 31) >> 5;
+      uint32_t *acc = reinterpret_cast<uint32_t *>(ws + ((p.dim + 3) & ~3));
+      uint32_t *hb = acc + 3 * kHotSlots;
+      uint16_t *hp = reinterpret_cast<uint16_t *>(hb + words);
+      for (int i = threadIdx.x; i < 3 * kHotSlots; i += kStreamThreads) acc[i] = 0u;
+      for (int i = threadIdx.x; i < words; i += kStreamThreads) { hb[i] = __ldg(&p.hot_bits[i]); hp[i] = __ldg(&p.hot_prefix[i]); }
+    }
     __syncthreads();
     wmax = 0.f;
 #pragma unroll
     for (int i = 0; i < kStreamThreads / 32; ++i) wmax = fmaxf(wmax, s_wmax[i]);
   }
-  // |x.w - x.w32| <= 2^-24 * max|w| * sum|x| (+ fp32 underflow slack); 1.5x covers fp32 rounding of the bound itself
-  const float band_scale = 1.5f * 5.9604645e-8f * wmax;
+  const float band_scale = 1.5f * 5.9604645e-8f * wmax;   // 1.5 * 2^-24 * max|w|
+  uint32_t *hot_acc = nullptr;
+  const uint32_t *hot_bits = nullptr;
+  const uint16_t *hot_prefix = nullptr;
+  if constexpr (kHot) {
+    hot_acc = reinterpret_cast<uint32_t *>(ws + ((p.dim + 3) & ~3));
+    hot_bits = hot_acc + 3 * kHotSlots;
+    hot_prefix = reinterpret_cast<const uint16_t *>(hot_bits + ((p.dim + 31) >> 5));
+  }
+  // one gradient entry: into the CTA's fixed-point slot if the column has one and the value is exactly representable
+  auto scatter_one = [&](uint32_t col, double gv) {
+    if (gv == 0.0) return;
+    if constexpr (kHot) {
+      const uint32_t bits = hot_bits[col >> 5], bit = 1u << (col & 31);
+      if (bits & bit) {
+        const double sv = gv * 1099511627776.0;  // 2^40: exact scaling
+        if (fabs(sv) <= 1099511627776.0) {
+          const long long iv = __double2ll_rn(sv);
+          if ((double)iv == sv) {
+            const uint32_t slot = (uint32_t)hot_prefix[col >> 5] + (uint32_t)__popc(bits & (bit - 1u));
+            const int l2 = (int)(iv >> 28);                                  // signed rest, |l2| <= 2^12
+            const uint32_t rem = (uint32_t)(iv - ((long long)l2 << 28));     // in [0, 2^28)
+            atomicAdd(&hot_acc[3 * slot], rem & 0x3fffu);
+            atomicAdd(&hot_acc[3 * slot + 1], rem >> 14);
+            atomicAdd(&hot_acc[3 * slot + 2], (uint32_t)l2);
+            return;
+          }
+        }
+      }
+    }
+    atomicAdd(&p.g[col], gv);
+  };
 
-  const int half = lane >> 4, hl = lane & 15;
   const int64_t n_blocks = (p.n + 31) >> 5;
   const int64_t warp_global = (int64_t)blockIdx.x * (kStreamThreads / 32) + warp;
   const int64_t n_warps = (int64_t)gridDim.x * (kStreamThreads / 32);
   unsigned hinge = 0, correct = 0, n_exact = 0;
 
   // bounds of the block being processed / the next one: lane l holds row l of the block
-  auto load_block = [&](int64_t blk, uint32_t &b, uint32_t &e, int &y, int64_t &rid) {
+  auto load_block = [&](int64_t blk, uint32_t &b, uint32_t &e, int &y) {
     const int64_t i = (blk << 5) + lane;
-    b = 0u; e = 0u; y = 0; rid = -1;
+    b = 0u; e = 0u; y = 0;   // y == 0: no such row
     if (blk < n_blocks && i < p.n) {
-      rid = p.samples ? (int64_t)__ldg(&p.samples[i]) : p.row_begin + i;
+      const int64_t rid = p.samples ? (int64_t)__ldg(&p.samples[i]) : p.row_begin + i;
       b = __ldg(&p.rp16[rid]);
       e = __ldg(&p.rp16[rid + 1]);
       y = (int)__ldg(&p.label[rid]);
     }
   };
   // Work distribution: the first wave is static (block = warp id), later blocks are claimed from a global counter
-  // one step ahead (so the next block's bounds are prefetched while the current one is processed).  Rows are
-  // heavy-tailed (1..2000 non-zeros): dynamic claiming keeps the tail of the pass short.
+  // one step ahead (so the next block's bounds are prefetched while the current one is processed).
   auto claim = [&]() -> int64_t {
     unsigned long long v = 0;
     if (lane == 0) v = atomicAdd(p.next_block, 1ull);
     return (int64_t)__shfl_sync(0xffffffffu, v, 0) + n_warps;
   };
-  uint32_t nb, ne; int ny; int64_t nrid;
+  uint32_t nb, ne; int ny;
   int64_t blk = warp_global;
   int64_t blk_next = (blk < n_blocks) ? claim() : n_blocks;
-  load_block(blk, nb, ne, ny, nrid);
+  load_block(blk, nb, ne, ny);
   for (; blk < n_blocks;) {
-    const uint32_t cb = nb, ce = ne; const int cy = ny; const int64_t crid = nrid;
-    load_block(blk_next, nb, ne, ny, nrid);
-    // 16 iterations: in iteration j the two halves take rows 2j and 2j+1 of the block.  A row is walked in
-    // super-steps of kUnroll 128-bit loads per lane (kUnroll * 32 pairs per 16-lane group), all issued before the
-    // first use: the bytes in flight per SM, not the instruction count, decide how close to the HBM roof this
-    // runs, and long rows (a third of the non-zeros sit beyond a row's first 96 pairs) must not serialise.
-    constexpr int kUnroll = 4;
-#pragma unroll 1
-    for (int j = 0; j < 16; ++j) {
-      const int row_l = 2 * j + half;
-      const uint32_t b = __shfl_sync(0xffffffffu, cb, row_l), e = __shfl_sync(0xffffffffu, ce, row_l);
-      const int yi = __shfl_sync(0xffffffffu, cy, row_l);
-      const int64_t rid = __shfl_sync(0xffffffffu, crid, row_l);
-      double acc = 0.0;
-      float asum = 0.f;
-      for (uint32_t u0 = b + hl; u0 < e; u0 += 16u * kUnroll) {
-        uint4 q[kUnroll];
+    uint32_t b = nb;
+    int len = (int)(ne - nb);   // units
+    int y = ny;
+    load_block(blk_next, nb, ne, ny);
+    int opos = lane;            // position of this lane's row inside the block (before compaction)
+    // empty rows: dot 0 -> prediction 0, hinge 1, never correct, nothing to scatter (SparseSVM.scala:14-16)
+    if (y != 0 && len == 0) {
+      hinge += 1u;
+      if (kPreds) p.preds[(blk << 5) + lane] = 0.0;
+    }
+    const unsigned ne_mask = __ballot_sync(0xffffffffu, y != 0 && len > 0);
+    if (ne_mask != 0xffffffffu) {   // compact the non-empty rows to lanes 0 .. n-1 (order kept)
+      const unsigned src = __fns(ne_mask, 0, lane + 1);
+      const bool has = src < 32u;
+      const int sl = has ? (int)src : 0;
+      b = __shfl_sync(0xffffffffu, b, sl);
+      len = __shfl_sync(0xffffffffu, len, sl);
+      y = __shfl_sync(0xffffffffu, y, sl);
+      opos = sl;
+      if (!has) { len = 0; y = 0; }
+    }
+    // P = inclusive prefix sum of the row lengths: row l covers virtual units [P - len, P)
+    int P = len;
 #pragma unroll
-        for (int i = 0; i < kUnroll; ++i) {
-          q[i] = make_uint4(0u, 0u, 0u, 0u);  // col 0, val +0.0f: inert
-          if (u0 + 16u * i < e) q[i] = __ldg(&p.units[u0 + 16u * i]);
-        }
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, P, o);
+      if (lane >= o) P += a;
+    }
+    const int total = __shfl_sync(0xffffffffu, P, 31);
+    const uint32_t base = b - (uint32_t)(P - len);   // unit address of virtual unit v of this row = base + v (mod 2^32)
+    float acc_p = 0.f, acc_a = 0.f;                   // this lane's share of the OPEN row: sum x*w, sum |x|
+    bool need_exact = false, do_scatter = false;
+    int pred_mine = 0;
+    // prediction known for this lane's row: counters and the gate (y * dot < 0  <=>  pred == y)
+    auto finalize = [&](int pr) {
+      pred_mine = pr;
+      hinge += (unsigned)(1 - y * pr);
+      correct += (unsigned)(pr == y);
+      do_scatter = kScatter && (pr != y);
+    };
+
+    for (int v0 = 0; v0 < total; v0 += 32 * kStreamUnroll) {
+      uint4 q[kStreamUnroll];
+      unsigned ends[kStreamUnroll];   // bit j: a row's LAST unit sits at lane j of this slot
+      int rlo[kStreamUnroll];         // row of the slot's first unit
+      int rmy[kStreamUnroll];         // row of this lane's unit
 #pragma unroll
-        for (int i = 0; i < kUnroll; ++i) {
-          const float x0 = __uint_as_float(q[i].y), x1 = __uint_as_float(q[i].w);
-          const float w0 = ws[q[i].x], w1 = ws[q[i].z];
-          // fp32 x fp32 products are exact in fp64 (24 + 24 significant bits), so a fused multiply-add rounds
-          // exactly like multiply-then-add: same bits as the unfused form, one instruction less
-          acc = fma((double)x0, (double)w0, acc);
-          acc = fma((double)x1, (double)w1, acc);
-          asum += fabsf(x0) + fabsf(x1);
-        }
+      for (int i = 0; i < kStreamUnroll; ++i) {
+        const int vs = v0 + 32 * i;
+        rlo[i] = __popc(__ballot_sync(0xffffffffu, P <= vs));
+        const unsigned d = (unsigned)(P - vs - 1);
+        ends[i] = __reduce_or_sync(0xffffffffu, (len > 0 && d < 32u) ? (1u << d) : 0u);
+        rmy[i] = rlo[i] + __popc(ends[i] & lt_mask);
+        const uint32_t bs = __shfl_sync(0xffffffffu, base, rmy[i] & 31);
+        q[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (vs + lane < total) q[i] = __ldg(&p.units[bs + (uint32_t)(vs + lane)]);
       }
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) {
-        acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        asum += __shfl_xor_sync(0xffffffffu, asum, o);
-      }
-      double dot = acc;
-      const bool valid = rid >= 0;
-      // exact fallback: the fp32-rounded weights cannot decide the sign (includes dot == 0 with non-empty rows)
-      const bool ambiguous = valid && (e > b) && (fabs(dot) <= (double)(band_scale * asum) + 1e-300);
-      if (ambiguous) {
-        double ex = 0.0;
-        for (uint32_t u = b + hl; u < e; u += 16) {
-          const uint4 q = __ldg(&p.units[u]);
-          ex += filt(filt((double)__uint_as_float(q.y)) * __ldcg(&p.w[q.x]));
-          ex += filt(filt((double)__uint_as_float(q.w)) * __ldcg(&p.w[q.z]));
-        }
-        // only this 16-lane group is here (the other group's row may not be ambiguous): group-local mask
-        const unsigned gmask = half ? 0xffff0000u : 0x0000ffffu;
+      for (int i = 0; i < kStreamUnroll; ++i) {
+        const float x0 = __uint_as_float(q[i].y), x1 = __uint_as_float(q[i].w);
+        float pp = 0.f;
+        if (v0 + 32 * i + lane < total) pp = __fmaf_rn(x1, ws[q[i].z], x0 * ws[q[i].x]);
+        const float aa = fabsf(x0) + fabsf(x1);
+        unsigned m = ends[i];
+        int k = rlo[i];
+        while (m) {   // warp-uniform: close the rows that end inside this slot, in order
+          m &= m - 1u;
+          const bool sel = (rmy[i] == k);
+          float sp = acc_p + (sel ? pp : 0.f), sa = acc_a + (sel ? aa : 0.f);
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) ex += __shfl_xor_sync(gmask, ex, o);
-        dot = ex;
-        if (hl == 0) ++n_exact;
-      }
-      if (valid) {
-        const int pred = (dot > 0.0) ? -1 : ((dot < 0.0) ? 1 : 0);
-        if (hl == 0) {
-          hinge += (unsigned)(1 - yi * pred);
-          correct += (unsigned)(pred == yi);
-          if (kPreds) p.preds[((blk << 5) + row_l)] = (double)pred;
-        }
-        if (kScatter) {
-          const double y = (double)yi;
-          if (!(y * dot < 0.0)) {  // SparseSVM.scala:28
-            for (uint32_t u = b + hl; u < e; u += 16) {
-              const uint4 q = __ldg(&p.units[u]);
-              const double g0 = filt(filt((double)__uint_as_float(q.y)) * y);
-              const double g1 = filt(filt((double)__uint_as_float(q.w)) * y);
-              if (g0 != 0.0) atomicAdd(&p.g[q.x], g0);
-              if (g1 != 0.0) atomicAdd(&p.g[q.z], g1);
-            }
+          for (int o = 16; o > 0; o >>= 1) {
+            sp += __shfl_xor_sync(0xffffffffu, sp, o);
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
           }
+          if (lane == k) {
+            const float thresh = band_scale * sa * (float)((len >> 5) + 10) + 1e-30f;
+            if (!(fabsf(sp) > thresh)) need_exact = true;   // also catches NaN
+            else finalize(sp > 0.f ? -1 : 1);
+          }
+          acc_p = 0.f;
+          acc_a = 0.f;
+          ++k;
+        }
+        const bool sel = (rmy[i] == k);
+        acc_p += sel ? pp : 0.f;
+        acc_a += sel ? aa : 0.f;
+      }
+    }
+    // ---- exact recomputation of the rows the fp32 sign could not decide ----
+    unsigned ex = __ballot_sync(0xffffffffu, need_exact);
+    while (ex) {
+      const int r = __ffs(ex) - 1;
+      ex &= ex - 1u;
+      const uint32_t rb = __shfl_sync(0xffffffffu, b, r);
+      const int rl = __shfl_sync(0xffffffffu, len, r);
+      double acc = 0.0;
+      for (int u = lane; u < rl; u += 32) {
+        const uint4 qq = __ldg(&p.units[rb + (uint32_t)u]);
+        acc += filt(filt((double)__uint_as_float(qq.y)) * __ldcg(&p.w[qq.x]));
+        acc += filt(filt((double)__uint_as_float(qq.w)) * __ldcg(&p.w[qq.z]));
+      }
+      const double dot = warp_sum(acc);
+      if (lane == r) {
+        finalize(pred_of(dot));
+        ++n_exact;
+      }
+    }
+    if (kPreds) {
+      if (y != 0) p.preds[(blk << 5) + opos] = (double)pred_mine;
+    }
+    // ---- scatter y*x of the rows that passed the gate (SparseSVM.scala:28) ----
+    if (kScatter) {
+      unsigned sc = __ballot_sync(0xffffffffu, do_scatter);
+      while (sc) {
+        const int r = __ffs(sc) - 1;
+        sc &= sc - 1u;
+        const uint32_t rb = __shfl_sync(0xffffffffu, b, r);
+        const int rl = __shfl_sync(0xffffffffu, len, r);
+        const double yy = (double)__shfl_sync(0xffffffffu, y, r);
+        for (int u = lane; u < rl; u += 32) {
+          const uint4 qq = __ldg(&p.units[rb + (uint32_t)u]);
+          scatter_one(qq.x, filt(filt((double)__uint_as_float(qq.y)) * yy));
+          scatter_one(qq.z, filt(filt((double)__uint_as_float(qq.w)) * yy));
         }
       }
     }
@@ -198,6 +307,23 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
   if (threadIdx.x == 0) {
     if (s_cnt[0]) atomicAdd(&p.cnt[kCntHinge], s_cnt[0]);
     if (s_cnt[1]) atomicAdd(&p.cnt[kCntCorrect], s_cnt[1]);
+  }
+  if constexpr (kHot) {
+    // every warp is past its last scatter (the barrier above): flush the touched slots, one RED each
+    for (int slot = threadIdx.x; slot < p.n_hot; slot += kStreamThreads) {
+      const long long tot = (long long)hot_acc[3 * slot] + ((long long)hot_acc[3 * slot + 1] << 14) +
+                            ((long long)(int)hot_acc[3 * slot + 2] << 28);
+      if (tot != 0) {
+        double *dst = &p.g[__ldg(&p.hot_cols[slot])];
+        if (tot > -(1ll << 53) && tot < (1ll << 53)) {
+          atomicAdd(dst, (double)tot * 0x1p-40);             // the conversion is exact
+        } else {
+          const long long hi = tot >> 30, lo = tot - (hi << 30);             // both convert exactly
+          atomicAdd(dst, (double)hi * 0x1p-10);
+          atomicAdd(dst, (double)lo * 0x1p-40);
+        }
+      }
+    }
   }
 }
 

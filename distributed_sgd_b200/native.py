@@ -100,6 +100,9 @@ ABI = {
     "dsgd_xchg_export": [_vp, _vp],
     "dsgd_xchg_import": [_vp, C.c_int, _vp],
     "dsgd_xchg_attach": [_vp, C.c_int, _vp],
+    "dsgd_xchg_stats": [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)],
+    "dsgd_debug_timeline": [_vp, _vp],
+    "dsgd_set_grid_limit": [_vp, _i32],
     "dsgd_set_workers": [_vp, _i32, _vp, _i32],
     "dsgd_sync_step": [_vp, _vp, _i64, _f64, C.POINTER(_f64)],
     "dsgd_sync_steps": [_vp, _vp, _i64, _i64, _f64, _vp],
@@ -158,6 +161,8 @@ def host_lib():
         h.dsgd_rcv1_parse.argtypes = [C.c_char_p, _i32, _i64, _i64, _vp, _vp, _vp, _vp]
         h.dsgd_rcv1_labels.argtypes = [C.c_char_p, _vp, _i64, _vp]
         h.dsgd_rcv1_write.argtypes = [C.c_char_p, C.c_char_p, _i64, _vp, _vp, _vp, _vp, _i64]
+        h.dsgd_draw_epoch.restype = C.c_int64
+        h.dsgd_draw_epoch.argtypes = [C.c_uint64, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _i64]
         _host = h
     return _host
 
@@ -341,6 +346,24 @@ class NativeCtx:
             if r != self.rank:
                 self.xchg_import(r, h)
         group.barrier()
+
+    def xchg_stats(self) -> Tuple[int, int, int]:
+        """(value words, bitmap words) this rank stored into EACH peer so far, and the SGD steps of those launches."""
+        v, b, n = C.c_int64(), C.c_int64(), C.c_int64()
+        self._ck(self._l.dsgd_xchg_stats(self._h, C.byref(v), C.byref(b), C.byref(n)))
+        return v.value, b.value, n.value
+
+    def set_grid_limit(self, n_ctas: int):
+        """CTAs of the persistent sync kernel (0: one per SM) -- lets several ranks share one GPU in tests."""
+        self._ck(self._l.dsgd_set_grid_limit(self._h, n_ctas))
+
+    TIMELINE_WORDS = 256 * 16 + 4 * 160 * 4
+
+    def debug_timeline(self) -> np.ndarray:
+        """Phase stamps of the last persistent launch (needs DSGD_PERSIST_TIMELINE in the environment)."""
+        out = np.zeros(self.TIMELINE_WORDS, dtype=np.int64)
+        self._ck(self._l.dsgd_debug_timeline(self._h, _ptr(out)))
+        return out
 
     def sync_step(self, samples, lr: float, want_loss: bool = True):
         samples = _arr(samples, np.int32)

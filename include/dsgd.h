@@ -76,6 +76,15 @@ int dsgd_launch_count(const dsgd_ctx *ctx, int64_t *count);
  * returns their mean duration and how many launches were sampled. */
 int dsgd_profile_begin(dsgd_ctx *ctx, int32_t sample_every);
 int dsgd_profile_end(dsgd_ctx *ctx, float *mean_ms, int64_t *n_sampled);
+/* CTAs of the persistent sync kernel (0 = one per SM, the default and the fastest).  The kernel is cooperative and its
+ * ranks wait for each other, so K contexts that share ONE GPU (the K-rank tests on a single-GPU box: tests/
+ * test_gpu_fused_one_gpu.py) must each take at most 1/K of the SMs. */
+int dsgd_set_grid_limit(dsgd_ctx *ctx, int32_t n_ctas);
+/* Developer aid (tools/timeline.py): with the environment variable DSGD_PERSIST_TIMELINE set, the persistent sync kernel
+ * stamps clock64 per phase (CTA 0, 256 steps x 16 slots) and, for steps 100..103, {barrier arrival ns, barrier exit ns,
+ * pairs of the CTA's rows, spare} per CTA; this copies the last launch's DSGD_TIMELINE_WORDS int64 words out. */
+#define DSGD_TIMELINE_WORDS (256 * 16 + 4 * 160 * 4)
+int dsgd_debug_timeline(dsgd_ctx *ctx, long long *out);
 
 /* ---- data: the `data: Array[(Vec, Int)]` constructor argument (core/Slave.scala:20; Main.scala:138,149).
  *      Rows are repacked on the device into 16-byte aligned (col, val) windows.  label in {-1, +1}. ------ */
@@ -119,14 +128,18 @@ int dsgd_eval_counts(dsgd_ctx *ctx, const double *w, int64_t row_begin, int64_t 
 int dsgd_comm_unique_id(uint8_t id[DSGD_UNIQUE_ID_BYTES]);
 int dsgd_comm_init(dsgd_ctx *ctx, const uint8_t id[DSGD_UNIQUE_ID_BYTES]);
 
-/* Peer exchange for the FUSED multi-GPU step: each rank exports its exchange block (three gradient buffers and
- * flag words), the host transports the handles, every rank imports every other rank's.  Once all world-1 peers
+/* Peer exchange for the FUSED multi-GPU step: each rank exports its receive area, the host transports the handles, every rank imports every other rank's.  Once all world-1 peers
  * are attached, sync steps with one worker per GPU run as one persistent kernel per call that sums the workers'
- * replies directly out of peer memory over NVLink (no NCCL call, no launch per step); otherwise the NCCL
- * allreduce path is used.  dsgd_xchg_attach is the same-process form. */
+ * replies directly out of peer memory over NVLink (no NCCL call, no launch per step; only the non-zero entries of a
+ * reply travel); otherwise the NCCL allreduce path is used.  Up to 8 ranks (one NVSwitch box).  dsgd_xchg_attach is
+ * the same-process form. */
 int dsgd_xchg_export(dsgd_ctx *ctx, uint8_t handle[DSGD_IPC_HANDLE_BYTES]);
 int dsgd_xchg_import(dsgd_ctx *ctx, int peer_rank, const uint8_t handle[DSGD_IPC_HANDLE_BYTES]);
 int dsgd_xchg_attach(dsgd_ctx *ctx, int peer_rank, dsgd_ctx *peer);
+/* Traffic of the fused step so far, for the NVLink figures of the bench: words this rank has stored into EACH peer's
+ * receive area (a value word is 16 bytes on the wire -- one non-zero gradient entry --, a bitmap word 8 bytes -- which of
+ * 32 columns were sent) and the SGD steps of those launches.  Any pointer may be NULL. */
+int dsgd_xchg_stats(dsgd_ctx *ctx, int64_t *value_words, int64_t *bitmap_words, int64_t *steps);
 
 /* ---- logical workers of a sync step.  Default: this ctx is ONE worker (its whole slice is one
  *      GradientRequest) and the master averages over `world` results.  With n_local > 1 the slice of every

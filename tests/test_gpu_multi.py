@@ -28,8 +28,6 @@ def _worker(rank, world, port, q, mode):
     from distributed_sgd_b200.utils import synthetic_rcv1
     from oracle.oracle import Oracle
 
-    if mode == "nccl":
-        os.environ["DSGD_NO_P2P"] = "1"
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     group = Group()

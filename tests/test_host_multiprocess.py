@@ -102,3 +102,54 @@ def test_spmd_master_two_ranks_gloo():
     assert r0["loss"] == r1["loss"] == [0.5 * 4.0 + 1.0] * 2
     assert r0["acc"] == r1["acc"] == [(50 // 2 + 51 // 2) / 101] * 2
     assert r0["updates"] == 2
+
+
+def test_ranks_issue_the_same_call_sequence_when_the_last_group_is_short():
+    """n_train = 41, 2 ranks, batch 7 -> groups of 21 and 20 rows; steps draw (7,7), (7,7), (7,6).
+    Rank 0's own counts never change, rank 1's do: cutting the epoch into device calls by a rank's OWN counts made the ranks
+    issue different call sequences (the fused multi-GPU kernel numbers its exchange by call and would spin into its
+    watchdog).  The boundaries must come from the global shape."""
+    sys.path.insert(0, ROOT)
+    from distributed_sgd_b200.core import master as master_mod
+    from distributed_sgd_b200.ml import EarlyStopping, SparseSVM
+    from distributed_sgd_b200.utils.dataset import Data
+
+    class OneRankOfTwo:           # a Group that claims rank r of 2 without a process group
+        def __init__(self, r):
+            self.rank, self.world, self.active = r, 2, False
+        def barrier(self): pass
+        def broadcast_bytes(self, b, src=0): return b
+        def all_gather_bytes(self, b): return [b, b]
+        def all_reduce_sum(self, v): return list(v)
+        def all_reduce_max(self, v): return v
+
+    n_train, n_test, dim = 41, 10, 8
+    stub = lambda n: Data(np.arange(n + 1, dtype=np.int64), np.zeros(n, np.int32), np.ones(n, np.float32),
+                          np.ones(n, np.int8), dim)
+    shapes = []
+    for r in range(2):
+        slave = FakeSlave(r, 2, n_train, n_test, dim)
+        m = master_mod.MasterSync(r, stub(n_train), stub(n_test), SparseSVM(0.5), 2, slave=slave, group=OneRankOfTwo(r),
+                                  seed=0, attach=False)
+        m.fit(np.zeros(dim), max_epochs=1, batch_size=7, learning_rate=0.5,
+              stopping_criterion=EarlyStopping.no_improvement(patience=5, min_delta=0.01))
+        shapes.append([(c[2], c[3]) for c in slave.ctx.calls if c[0] == "steps"])
+    assert shapes[0] == [(7, 2), (7, 1)] and shapes[1] == [(7, 2), (6, 1)]      # same number of calls, same step counts
+
+
+def test_empty_slice_fails_the_fit_on_every_rank():
+    """Quirk Q7 (math/Vec.scala:129 via core/Master.scala:187): a worker whose slice is empty at some step makes Vec.sum
+    throw; every rank must notice at that step, whichever rank owns the empty slice."""
+    sys.path.insert(0, ROOT)
+    import pytest
+    from distributed_sgd_b200.core import master as master_mod
+    from distributed_sgd_b200.ml import EarlyStopping, SparseSVM
+    from distributed_sgd_b200.utils.dataset import Data
+    n_train, dim = 29, 8                          # 2 workers: groups of 15 and 14; batch 7 -> third step draws (1, 0)
+    stub = lambda n: Data(np.arange(n + 1, dtype=np.int64), np.zeros(n, np.int32), np.ones(n, np.float32),
+                          np.ones(n, np.int8), dim)
+    slave = FakeSlave(0, 1, n_train, 5, dim)
+    m = master_mod.MasterSync(0, stub(n_train), stub(5), SparseSVM(0.5), 1, slave=slave, seed=0)
+    with pytest.raises(ValueError, match="empty list"):
+        m.fit(np.zeros(dim), max_epochs=1, batch_size=7, learning_rate=0.5,
+              stopping_criterion=EarlyStopping.no_improvement(patience=5, min_delta=0.01), virtual_workers=2)
