@@ -328,15 +328,21 @@ class MasterAsync(Master):
         test_accs: List[float] = []
         best_loss, best_w = float("inf"), None
         last_step = -check_every                                                  # MasterAsync.scala:161
-        self.history = {"test_losses": test_losses, "test_accs": test_accs, "checks_at": []}
+        # polls: every look at the update counter (updates, computed?); raw_*: the unsmoothed numbers of the computed polls --
+        # what a replay of core/MasterAsync.scala:96-162 over the same stream needs (tests/test_host_logic.py)
+        self.history = {"test_losses": test_losses, "test_accs": test_accs, "checks_at": [], "polls": [],
+                        "raw_test_losses": [], "raw_test_accs": [], "best_check": None, "ended_by": None}
         try:
             while True:
                 updates = self.ctx.async_updates() if r == 0 else 0
                 updates = int(self.group.all_reduce_max(float(updates)))
                 if updates >= max_steps:                                          # MasterAsync.scala:171-174
                     self.log("max number of steps reached: stopping computation")
+                    self.history["polls"].append((updates, False))
+                    self.history["ended_by"] = "max_steps"
                     break
                 if updates - last_step < check_every:                             # latest computation was too close
+                    self.history["polls"].append((updates, False))
                     time.sleep(poll_seconds)                                      # (the reference waits 2.5 s)
                     continue
                 # innerGradState.grad: ONE snapshot (rank 0 hosts the master replica), evaluated row-sharded by everybody
@@ -347,13 +353,18 @@ class MasterAsync(Master):
                 acc_s = leak_loss_coef * acc + (1 - leak_loss_coef) * (test_accs[0] if test_accs else acc)
                 if best_loss > loss_s:                                            # MasterAsync.scala:130-139
                     best_loss, best_w = loss_s, w
+                    self.history["best_check"] = len(self.history["checks_at"])
                 test_losses.insert(0, loss_s)
                 test_accs.insert(0, acc_s)
                 self.history["checks_at"].append(updates)
+                self.history["polls"].append((updates, True))
+                self.history["raw_test_losses"].append(loss)
+                self.history["raw_test_accs"].append(acc)
                 if on_check:
-                    on_check(updates, {"test_loss": loss_s, "test_acc": acc_s})
+                    on_check(updates, {"test_loss": loss_s, "test_acc": acc_s, "weights": w})
                 if stopping_criterion(test_losses):                               # MasterAsync.scala:146-152
                     self.log("converged to target: stopping computation")
+                    self.history["ended_by"] = "converged"
                     break
                 last_step = updates
         finally:

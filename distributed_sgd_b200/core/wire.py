@@ -125,6 +125,8 @@ class SlaveServicer:
         self.concurrency, self.seed = concurrency, seed
         self.colleagues: Dict[Tuple[str, int], bool] = {}
         self.M = Messages()
+        import threading
+        self._ctx_lock = threading.Lock()
 
     # registration bookkeeping (core/Slave.scala:115-127)
     def RegisterSlave(self, node, context=None):
@@ -141,16 +143,21 @@ class SlaveServicer:
             raise IndexError("sample id outside the training rows")   # data(idx) on the reference's array
         return idx.astype(np.int32)
 
+    # Forward / Gradient / StartAsync share the context's request buffers (weights, gradient, counters): the C ABI wants
+    # them serialised by the caller (include/dsgd.h, "Threading"), and the handlers run on a thread pool -- hence the lock.
+    # UpdateGrad / StopAsync are the calls the ABI allows while the async loop runs and stay outside it.
     def Forward(self, request, context=None):             # core/Slave.scala:129-140
         idx = self._samples(request.samples)
         w = sparse_to_dense(request.weights, self.dim)
-        preds = self.ctx.forward(idx, w) if idx.size else np.zeros(0)
+        with self._ctx_lock:
+            preds = self.ctx.forward(idx, w) if idx.size else np.zeros(0)
         return self.M.ForwardReply(predictions=preds.tolist())
 
     def Gradient(self, request, context=None):            # core/Slave.scala:142-157
         idx = self._samples(request.samples)
         w = sparse_to_dense(request.weights, self.dim)
-        grad = self.ctx.gradient(idx, w)                  # empty batch -> DsgdEmpty (Vec.sum of an empty list throws)
+        with self._ctx_lock:
+            grad = self.ctx.gradient(idx, w)              # empty batch -> DsgdEmpty (Vec.sum of an empty list throws)
         return self.M.GradUpdate(gradUpdate=dense_to_sparse(self.M, grad, self.dim))
 
     def StartAsync(self, request, context=None):          # core/Slave.scala:159-175
@@ -158,8 +165,9 @@ class SlaveServicer:
             raise RuntimeError("Cannot initialize async computation: slave is in synchronous mode.")
         idx = self._samples(request.samples)
         w = sparse_to_dense(request.weights, self.dim)
-        self.ctx.start_async(w, idx, request.batchSize, request.learningRate, concurrency=self.concurrency,
-                             max_updates=0, seed=self.seed)
+        with self._ctx_lock:
+            self.ctx.start_async(w, idx, request.batchSize, request.learningRate, concurrency=self.concurrency,
+                                 max_updates=0, seed=self.seed)
         return self.M.Ack()
 
     def StopAsync(self, request, context=None):           # core/Slave.scala:187-195
@@ -205,8 +213,8 @@ def serve_slave(servicer: SlaveServicer, port: int, host: str = "127.0.0.1", max
             wrap(getattr(servicer, name)),
             request_deserializer=getattr(M, req).FromString,
             response_serializer=getattr(M, rep).SerializeToString)
-    # The reference serves on a fixed 8-thread pool (utils/Pool.scala:13); the device context serialises its calls,
-    # except the async service calls, which are safe while the loop runs.
+    # The reference serves on a fixed 8-thread pool (utils/Pool.scala:13); the servicer serialises the request calls on its
+    # device context with a lock, the async service calls (UpdateGrad, StopAsync) are safe while the loop runs.
     server = grpc.server(futures.ThreadPoolExecutor(max_workers=max_workers))
     server.add_generic_rpc_handlers((grpc.method_handlers_generic_handler(f"{PACKAGE}.Slave", handlers),))
     bound = server.add_insecure_port(f"{host}:{port}")    # usePlaintext (core/package.scala:20-21)

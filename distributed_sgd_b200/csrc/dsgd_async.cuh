@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(128) k_async_worker(const AsyncParams p) {
           if (m != 0.0 && add_c) m = filt(m + c);     // regularize on the surviving keys
           const double delta = filt(m * p.lr);        // learningRate * (...)
           if (delta != 0.0) {
-            for (int q = 0; q < p.n_replicas; ++q) atomicAdd_system(&p.replica[q][pr.x], -delta);
+            for (int q = 0; q < p.n_replicas; ++q) red_add_f64_sys(&p.replica[q][pr.x], -delta);
             sd += delta * p.d[pr.x];
           }
         }
@@ -152,9 +152,9 @@ __global__ void __launch_bounds__(128) k_async_worker(const AsyncParams p) {
     sd = warp_sum(sd);
     if (lane == 0) {
       if (sd != 0.0)
-        for (int q = 0; q < p.n_replicas; ++q) atomicAdd_system(&p.replica[q][p.dim + kCtlS], -sd);
+        for (int q = 0; q < p.n_replicas; ++q) red_add_f64_sys(&p.replica[q][p.dim + kCtlS], -sd);
       if (p.master_slot >= 0)
-        atomicAdd_system(reinterpret_cast<unsigned long long *>(&p.replica[p.master_slot][p.dim + kCtlUpdates]), 1ull);
+        red_add_u64_sys(reinterpret_cast<unsigned long long *>(&p.replica[p.master_slot][p.dim + kCtlUpdates]), 1ull);
       __threadfence_system();
       atomicAdd(p.done, 1ull);
     }
@@ -162,72 +162,125 @@ __global__ void __launch_bounds__(128) k_async_worker(const AsyncParams p) {
   }
 }
 
-// Batch 1 on rows with unique columns (dsgd_load_csr checks; the reference's rows are Maps): the same loop body without the
-// per-lane scratch vector.  With one sample per iteration the batch sum IS the row's backward, so the
-// delta of every non-zero is formed straight from the pair: two dependent L2 round trips (scratch write + read-back and
-// claim) leave the per-update latency chain, and throughput here is lanes / latency.  Same arithmetic as the general
-// path for B = 1 (sum = 0 + y*x, mean = sum / 1.0); requires unique columns within a row, like the reference's Map rows.
+// Batch 1 on rows with unique columns (dsgd_load_csr checks; the reference's rows are Maps): the loop body of
+// BASELINE.json configs[3] -- one sample per update -- without the per-lane scratch vector.  With one sample the batch sum IS
+// the row's backward (sum = 0 + y*x, mean = sum / 1.0), so the delta of every non-zero is formed straight from the pair.
+// An update is a chain of dependent latencies (sample id -> row pointers -> row window from HBM -> weight gathers from
+// L2 -> reduce -> REDs), and with `concurrency` = 1 (the reference's one sequential loop per slave, core/Slave.scala:79-111)
+// throughput is 1 / chain.  What does not depend on the weights leaves the chain: the NEXT iteration's sample id, row
+// pointers, label and the first 128 pairs of its window are fetched while the current iteration computes; the deltas go
+// out as fire-and-forget REDs (the reference's updateGrad futures are not awaited either, core/Slave.scala:104-105) and
+// are fenced once, when the loop ends; the stop flag is looked at every 32 iterations.
+constexpr int kAsyncPre = 4;   // pairs per lane held in registers for the next row
+struct AsyncRow {
+  int64_t s0, s1;
+  double y;
+  uint2 pre[kAsyncPre];
+  bool valid;
+};
+__device__ __forceinline__ AsyncRow async_fetch_row(const AsyncParams &p, bool have, unsigned long long it, unsigned long long &rng,
+                                                    int lane) {
+  AsyncRow row;
+  row.valid = have;
+  row.s0 = row.s1 = 0;
+  row.y = 0.0;
+#pragma unroll
+  for (int u = 0; u < kAsyncPre; ++u) row.pre[u] = make_uint2(0u, 0u);
+  if (!have) return row;
+  int32_t r = 0;
+  if (lane == 0)   // data(assignedSamples(Random.nextInt(size)))  (core/Slave.scala:84)
+    r = p.replay ? __ldg(&p.replay[it]) : __ldg(&p.assigned[mix64(rng) % (unsigned long long)p.n_assigned]);
+  r = __shfl_sync(0xffffffffu, r, 0);
+  row.s0 = (int64_t)__ldg(&p.rp16[r]) * 2;
+  row.s1 = (int64_t)__ldg(&p.rp16[r + 1]) * 2;
+  row.y = (double)__ldg(&p.label[r]);
+#pragma unroll
+  for (int u = 0; u < kAsyncPre; ++u) {
+    const int64_t k = row.s0 + lane + 32 * u;
+    if (k < row.s1) row.pre[u] = __ldg(&p.pairs[k]);
+  }
+  return row;
+}
+
 __global__ void __launch_bounds__(128) k_async_worker_b1(const AsyncParams p) {
   const int lane = threadIdx.x & 31;
   const int lane_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (lane_id >= p.n_lanes) return;
   double *w = p.replica[0];
   unsigned long long rng = p.seed * 0xD1342543DE82EF95ull + 0x632BE59BD9B4E019ull * (unsigned long long)(lane_id + 1);
+  // iterations are claimed from a shared counter (keeps the total bounded and deals a replay sequence in order); a
+  // single lane just counts
+  unsigned long long local_it = 0;
+  auto claim = [&](unsigned long long &it) -> bool {
+    if (p.n_lanes == 1) {
+      it = local_it++;
+    } else {
+      unsigned long long v = 0;
+      if (lane == 0) v = atomicAdd(p.claimed, 1ull);
+      it = __shfl_sync(0xffffffffu, v, 0);
+    }
+    return !(p.max_updates > 0 && it >= (unsigned long long)p.max_updates);
+  };
+  unsigned long long it = 0, it_next = 0;
+  bool have = claim(it);
+  AsyncRow cur = async_fetch_row(p, have, it, rng, lane);
+  unsigned n_done = 0;
+  while (cur.valid) {
+    bool stop = false;
+    if ((n_done & 31u) == 0u) stop = (*p.stop != 0);
+    const bool have_next = !stop && claim(it_next);
+    const AsyncRow nxt = async_fetch_row(p, have_next, it_next, rng, lane);   // in flight while this iteration computes
 
-  for (;;) {
-    if (*p.stop) break;
-    unsigned long long it = 0;
-    if (lane == 0) it = atomicAdd(p.claimed, 1ull);
-    it = __shfl_sync(0xffffffffu, it, 0);
-    if (p.max_updates > 0 && it >= (unsigned long long)p.max_updates) break;
-
-    // ---- 1. the sample: data(assignedSamples(Random.nextInt(size)))  (core/Slave.scala:84) ----
-    int32_t r = 0;
-    if (lane == 0) r = p.replay ? p.replay[it] : p.assigned[mix64(rng) % (unsigned long long)p.n_assigned];
-    r = __shfl_sync(0xffffffffu, r, 0);
-    const int64_t s0 = (int64_t)p.rp16[r] * 2, s1 = (int64_t)p.rp16[r + 1] * 2;
-    const double y = (double)p.label[r];
-
-    // ---- 2. c from the replica's running S = w . d ----
+    // ---- c from the replica's running S = w . d (SparseSVM.scala:31) ----
     const double S = *(volatile double *)&w[p.dim + kCtlS];
     const double c = p.lambda * 2.0 * S;
     const bool add_c = (c != 0.0) && (fabs(c) > kEps);
+    const double y = cur.y;
 
-    // ---- 3. backward against the current replica ----
+    // ---- backward against the current replica: x . w, gate (SparseSVM.scala:26-29) ----
+    double wv[kAsyncPre];
+#pragma unroll
+    for (int u = 0; u < kAsyncPre; ++u) wv[u] = (cur.pre[u].y << 1) ? __ldcg(&w[cur.pre[u].x]) : 0.0;
     double dot = 0.0;
-    for (int64_t k = s0 + lane; k < s1; k += 32) {
-      const uint2 pr = p.pairs[k];
+#pragma unroll
+    for (int u = 0; u < kAsyncPre; ++u) dot += filt(filt((double)__uint_as_float(cur.pre[u].y)) * wv[u]);
+    for (int64_t k = cur.s0 + lane + 32 * kAsyncPre; k < cur.s1; k += 32) {     // rows longer than 128 pairs
+      const uint2 pr = __ldg(&p.pairs[k]);
       dot += filt(filt((double)__uint_as_float(pr.y)) * __ldcg(&w[pr.x]));
     }
     dot = warp_sum(dot);
 
-    // ---- 4. delta = lr * regularize(y * x / 1, w); apply to every replica ----
+    // ---- delta = lr * regularize(y * x / 1, w); apply to every replica (core/Slave.scala:92-105) ----
     double sd = 0.0;
-    if (!(y * dot < 0.0)) {  // SparseSVM.scala:28
-      for (int64_t k = s0 + lane; k < s1; k += 32) {
-        const uint2 pr = p.pairs[k];
+    if (!(y * dot < 0.0)) {
+      auto push = [&](uint2 pr) {
         const double xv = filt((double)__uint_as_float(pr.y));
-        if (xv == 0.0) continue;                        // padding pair (or an explicit zero): no key
+        if (xv == 0.0) return;                          // padding pair (or an explicit zero): no key
         double m = filt(filt(xv * y) / 1.0);            // Vec.sum of one vector, Vec.mean = sum / size
         if (m != 0.0 && add_c) m = filt(m + c);
         const double delta = filt(m * p.lr);
         if (delta != 0.0) {
-          for (int q = 0; q < p.n_replicas; ++q) atomicAdd_system(&p.replica[q][pr.x], -delta);
-          sd += delta * p.d[pr.x];
+          for (int q = 0; q < p.n_replicas; ++q) red_add_f64_sys(&p.replica[q][pr.x], -delta);
+          sd += delta * __ldg(&p.d[pr.x]);
         }
-      }
+      };
+#pragma unroll
+      for (int u = 0; u < kAsyncPre; ++u) push(cur.pre[u]);
+      for (int64_t k = cur.s0 + lane + 32 * kAsyncPre; k < cur.s1; k += 32) push(__ldg(&p.pairs[k]));
     }
     sd = warp_sum(sd);
     if (lane == 0) {
       if (sd != 0.0)
-        for (int q = 0; q < p.n_replicas; ++q) atomicAdd_system(&p.replica[q][p.dim + kCtlS], -sd);
+        for (int q = 0; q < p.n_replicas; ++q) red_add_f64_sys(&p.replica[q][p.dim + kCtlS], -sd);
       if (p.master_slot >= 0)
-        atomicAdd_system(reinterpret_cast<unsigned long long *>(&p.replica[p.master_slot][p.dim + kCtlUpdates]), 1ull);
-      __threadfence_system();
+        red_add_u64_sys(reinterpret_cast<unsigned long long *>(&p.replica[p.master_slot][p.dim + kCtlUpdates]), 1ull);
       atomicAdd(p.done, 1ull);
     }
     __syncwarp();
+    ++n_done;
+    cur = nxt;
   }
+  __threadfence_system();   // every delta of this lane is visible in every replica before the kernel reports completion
 }
 
 // weights -= delta for a sparse delta, keeping S in step (core/Slave.scala:177-185; core/ml/GradState.scala:8)

@@ -35,6 +35,19 @@ enum Cnt : int {
 
 __device__ __forceinline__ double filt(double v) { return fabs(v) > kEps ? v : 0.0; }  // Sparse.scala:108-118
 
+// Gradient scatter: a reduction WITHOUT a return value.  Written as PTX `red` because nvcc 12.9 compiles atomicAdd(double *)
+// with an unused result to ATOMG (result discarded, but the response still travels back: ncu counted 1.9 M returned sectors
+// per 300 steps) inside the large persistent kernels, and to REDG only in small ones.
+__device__ __forceinline__ void red_add_f64(double *p, double v) {
+  asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_f64_sys(double *p, double v) {   // peer replicas over NVLink
+  asm volatile("red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_u64_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 // prediction = -signum(x . w)  (core/ml/SparseSVM.scala:14)
 __device__ __forceinline__ int pred_of(double dot) { return (dot > 0.0) ? -1 : ((dot < 0.0) ? 1 : 0); }
 

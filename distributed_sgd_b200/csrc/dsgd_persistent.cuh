@@ -422,7 +422,7 @@ __device__ __forceinline__ unsigned consume_stage(StageMeta<kMaxChunks> &mt, con
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const double gvv = filt(filt((double)__uint_as_float(pr[u].y)) * y);
-            if (gvv != 0.0) atomicAdd(&Gcur[pr[u].x], gvv);
+            if (gvv != 0.0) red_add_f64(&Gcur[pr[u].x], gvv);
           }
         }
         continue;
@@ -449,7 +449,7 @@ __device__ __forceinline__ unsigned consume_stage(StageMeta<kMaxChunks> &mt, con
         for (int k = lane; k < n; k += 32) {
           const uint2 pr = src[k];
           const double gvv = filt(filt((double)__uint_as_float(pr.y)) * y);
-          if (gvv != 0.0) atomicAdd(&Gcur[pr.x], gvv);
+          if (gvv != 0.0) red_add_f64(&Gcur[pr.x], gvv);
         }
       }
     }
@@ -476,7 +476,7 @@ __device__ __forceinline__ unsigned consume_stage(StageMeta<kMaxChunks> &mt, con
         for (int k = lane; k < len; k += 32) {
           const uint2 pr = __ldg(&grow[k]);
           const double gvv = filt(filt((double)__uint_as_float(pr.y)) * y);
-          if (gvv != 0.0) atomicAdd(&Gcur[pr.x], gvv);
+          if (gvv != 0.0) red_add_f64(&Gcur[pr.x], gvv);
         }
     }
   }
@@ -875,8 +875,8 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
     if (threadIdx.x == 0 && !last) {
       const unsigned h = sm.hinge_acc;
       if constexpr (kMulti) {
-        if (h) { atomicAdd(&Gcur[p.dim], (double)h); sm.hinge_acc = 0u; }
-        if (blockIdx.x == 0) atomicAdd(&Gcur[p.dim], (double)B * 4294967296.0);
+        if (h) { red_add_f64(&Gcur[p.dim], (double)h); sm.hinge_acc = 0u; }
+        if (blockIdx.x == 0) red_add_f64(&Gcur[p.dim], (double)B * 4294967296.0);
       } else {
         if (h) { atomicAdd(&p.hinge[t], h); sm.hinge_acc = 0u; }
       }

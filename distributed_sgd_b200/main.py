@@ -22,7 +22,9 @@ import numpy as np
 
 
 def scenario(cfg, data, *, rank: int = 0, world: int = 1, device: Optional[int] = None, seed: int = 0, log=print,
-             async_concurrency: int = 64, jvm_exact: bool = False) -> dict:
+             async_concurrency: int = 64, jvm_exact: bool = False, inspect=None) -> dict:
+    """Main.scenario (Main.scala:70-120).  inspect (tests): called as inspect("master", master) once the master exists
+    and as inspect("done", (master, state)) before the device context is released."""
     from . import EarlyStopping, Master, Slave, SparseSVM
     from .core import Group
 
@@ -31,6 +33,8 @@ def scenario(cfg, data, *, rank: int = 0, world: int = 1, device: Optional[int] 
     slave = Slave(rank, 0, train, model, cfg.is_async, world=world, device=device, test_data=test)
     master = Master.create(rank, train, test, model, cfg.is_async, cfg.node_count, slave=slave, group=Group(), seed=seed,
                            log=(log if rank == 0 else None), jvm_exact=jvm_exact)
+    if inspect:
+        inspect("master", master)
     w0 = np.zeros(data.dim)                                                    # data(0)._1.zerosLike (Main.scala:74)
     report = {"config": {k: getattr(cfg, k) for k in ("batch_size", "learning_rate", "lam", "node_count", "is_async",
                                                       "max_epochs", "check_every", "leaky_loss", "patience", "conv_delta")},
@@ -53,6 +57,8 @@ def scenario(cfg, data, *, rank: int = 0, world: int = 1, device: Optional[int] 
     report["final_test_loss"], report["final_test_accuracy"] = master.local_loss_accuracy(w1, test_data=True)  # :115-118
     report["final_weights_nonzero"] = int(np.count_nonzero(w1))
     report["updates"] = state.updates
+    if inspect:
+        inspect("done", (master, state))
     slave.stop()
     return report
 

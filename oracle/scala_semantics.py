@@ -283,3 +283,54 @@ def early_stopping_no_improvement(patience: int = 5, min_delta: float = 1e-3,
         return False if min_steps < len(losses) else check(losses)
 
     return crit
+
+
+class MasterAsyncLossChecker:
+    """core/MasterAsync.scala:66-177, the master side of an async run, replayed over a RECORDED stream.
+
+    The reference interleaves two activities on shared state: `updateGrad` (one call per delta a slave sends, :164-177) and
+    the polling task `startLossChecking.loop` (:96-162).  What the loop sees is fully described by the sequence of its
+    polls: at each poll the update counter `innerGradState.updates` and -- if it decides to compute -- the test loss and test
+    accuracy of `innerGradState.grad`.  `replay(polls)` restates the loop over such a sequence:
+      polls: iterable of (updates, test_loss, test_acc, weights_tag); test_loss / test_acc are only read when the loop
+             computes at that poll (pass None otherwise); weights_tag identifies the weight snapshot of the poll.
+    and returns the lists the reference would have built plus the state `endComputation` hands back.
+    """
+
+    def __init__(self, n_data: int, max_epochs: int, stopping_criterion: Callable[[Sequence[float]], bool],
+                 min_steps_between_checks: int, leak_coef: float):
+        if not (0 <= leak_coef <= 1):  # :97
+            raise ValueError("leaking coefficient must be between 0 and 1")
+        self.max_steps = n_data * max_epochs  # initState, :83
+        self.stop = stopping_criterion
+        self.min_steps = min_steps_between_checks
+        self.leak = leak_coef
+
+    def replay(self, polls: Iterable[Tuple[int, Optional[float], Optional[float], object]]) -> dict:
+        best_loss = 1.7976931348623157e308  # Number(Double.MaxValue), :69
+        best_grad: object = "Vec.zeros(1)"  # :68
+        last_step = -self.min_steps  # loop(-minStepsBetweenChecks, ...), :161
+        test_losses: List[float] = []  # newest first, like the Scala lists
+        test_accs: List[float] = []
+        computed_at: List[int] = []
+        ended_by = None
+        for updates, loss_t, acc_t, tag in polls:
+            if updates >= self.max_steps:  # updateGrad reached maxSteps before this poll: endComputation, :171-174
+                ended_by = "max_steps"
+                break
+            if updates - last_step < self.min_steps:  # :110 "Latest step was too close"
+                continue
+            # :116-125 (only the test-set numbers are live code)
+            loss_s = self.leak * loss_t + (1 - self.leak) * (test_losses[0] if test_losses else loss_t)
+            acc_s = self.leak * acc_t + (1 - self.leak) * (test_accs[0] if test_accs else acc_t)
+            if best_loss > loss_s:  # :132-139  `case oldLoss if oldLoss > lossTest => lossTest`
+                best_loss, best_grad = loss_s, tag
+            test_losses.insert(0, loss_s)  # :142-145
+            test_accs.insert(0, acc_s)
+            computed_at.append(updates)
+            if self.stop(test_losses):  # :147
+                ended_by = "converged"
+                break
+            last_step = updates  # loop(innerGradState.updates, ...), :156
+        return {"test_losses": test_losses, "test_accs": test_accs, "computed_at": computed_at, "best_loss": best_loss,
+                "best_grad": best_grad, "ended_by": ended_by}

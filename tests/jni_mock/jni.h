@@ -15,13 +15,18 @@ typedef struct _jobject *jobject;
 typedef jobject jstring, jarray, jintArray, jlongArray, jfloatArray, jdoubleArray, jbyteArray;
 #define JNIEXPORT __attribute__((visibility("default")))
 #define JNICALL
-#define JNI_ABORT 2
 struct JNINativeInterface_;
 typedef const struct JNINativeInterface_ *JNIEnv;
+#define DSGD_MOCK_REGION(Name, JT)                                                                   \
+  void (*Get##Name##ArrayRegion)(JNIEnv *env, JT##Array array, jsize start, jsize len, JT *buf);     \
+  void (*Set##Name##ArrayRegion)(JNIEnv *env, JT##Array array, jsize start, jsize len, const JT *buf);
 struct JNINativeInterface_ {
   jstring (*NewStringUTF)(JNIEnv *env, const char *utf);
   jsize (*GetArrayLength)(JNIEnv *env, jarray array);
-  void *(*GetPrimitiveArrayCritical)(JNIEnv *env, jarray array, unsigned char *isCopy);
-  void (*ReleasePrimitiveArrayCritical)(JNIEnv *env, jarray array, void *carray, jint mode);
+  DSGD_MOCK_REGION(Int, jint)
+  DSGD_MOCK_REGION(Long, jlong)
+  DSGD_MOCK_REGION(Float, jfloat)
+  DSGD_MOCK_REGION(Double, jdouble)
+  DSGD_MOCK_REGION(Byte, jbyte)
 };
 #endif

@@ -90,22 +90,82 @@ def test_sync_epoch_at_full_size_is_reproducible(full):
     assert np.isfinite(loss) and 0.0 <= acc <= 1.0 and np.all(np.isfinite(w2)) and np.count_nonzero(w2) > 10_000
 
 
-def test_main_scenario_sync_and_async():
-    """Main.scenario (Main.scala:70-120) through distributed_sgd_b200.main on a small synthetic set."""
+def test_configs0_small_slice_application_conf_defaults_match_oracle():
+    """BASELINE.json configs[0]: sync mode, 2 workers, application.conf defaults (batch 100, lr 0.5, lambda 1e-5, 10 epochs,
+    patience 5, conv-delta 0.01) on a 23 149-row slice (the size of RCV1's train file, utils/Dataset.scala:47-50), through
+    Main.scenario -- every per-epoch list, the stopping epoch and the final weights against the oracle driven with the same
+    batch draws (core/Master.scala:140-213; Main.scala:70-120)."""
     from distributed_sgd_b200.main import scenario
     from distributed_sgd_b200.utils import load_config, synthetic_rcv1
-    data = synthetic_rcv1(n_rows=6000, seed=5)
-    cfg = load_config(env={"DSGD_BATCH_SIZE": "50", "DSGD_NODE_COUNT": "2", "DSGD_MAX_EPOCHS": "3", "DSGD_LAMBDA": "0.00001"})
-    rep = scenario(cfg, data, rank=0, world=1, device=0, log=lambda s: None)
+    from distributed_sgd_b200.ml import EarlyStopping
+    from oracle.oracle import Oracle
+    data = synthetic_rcv1(n_rows=23149, seed=5)
+    cfg = load_config(env={"DSGD_NODE_COUNT": "2"})
+    assert (cfg.batch_size, cfg.learning_rate, cfg.lam, cfg.max_epochs, cfg.patience, cfg.conv_delta) == (100, 0.5, 1e-5, 10, 5, 0.01)
+    drawn, final = [], {}
+
+    def inspect(what, obj):
+        if what == "master":
+            orig = obj.draw_epoch
+            obj.draw_epoch = lambda groups, bs, *a: drawn.append(orig(groups, bs, *a)) or drawn[-1]
+        else:
+            final["master"], final["state"] = obj
+
+    rep = scenario(cfg, data, rank=0, world=1, device=0, log=lambda s: None, inspect=inspect)
+    n_train = int(data.n_rows * 0.8)
+    orc = Oracle(data.row_ptr, data.col, data.val, data.label, data.dim, cfg.lam)
+    orc.set_dim_sparsity(orc.dim_sparsity(n_train))
     assert rep["initial_loss"] == 1.0 and rep["initial_accuracy"] == 0.0    # w0 = 0 (Main.scala:74-78)
-    assert len(rep["history"]["losses"]) == 3 and len(rep["history"]["test_accs"]) == 3 and rep["updates"] == 3
-    # Main.scala:115-116 re-evaluates the returned weights
-    assert rep["final_test_loss"] == pytest.approx(rep["history"]["test_losses"][-1], rel=1e-12)
-    assert 0.0 <= rep["final_test_accuracy"] <= 1.0 and rep["final_weights_nonzero"] > 0
+    crit = EarlyStopping.no_improvement(patience=cfg.patience, min_delta=cfg.conv_delta, min_steps=None)
+    w = np.zeros(data.dim)
+    losses, accs, tlosses, taccs = [], [], [], []
+    epochs = 0
+    while not (epochs >= cfg.max_epochs or crit(tlosses[::-1])):            # Master.scala:154,166 (newest first)
+        for step in drawn[epochs]:
+            assert [len(b) for b in step][0] in (cfg.batch_size, 9260 % cfg.batch_size)
+            w, _ = orc.sync_steps(w, np.concatenate(step), [len(b) for b in step], cfg.learning_rate, n_steps=1)
+        l, a = orc.loss_acc(w, begin=0, n=n_train); losses.append(l); accs.append(a)
+        l, a = orc.loss_acc(w, begin=n_train, n=data.n_rows - n_train); tlosses.append(l); taccs.append(a)
+        epochs += 1
+    h = rep["history"]
+    assert rep["updates"] == epochs and len(h["losses"]) == epochs
+    np.testing.assert_allclose(h["losses"], losses, rtol=1e-11)
+    np.testing.assert_allclose(h["test_losses"], tlosses, rtol=1e-11)
+    assert h["accs"] == accs and h["test_accs"] == taccs
+    np.testing.assert_allclose(final["state"].grad, w, rtol=1e-10, atol=1e-15)
+    assert rep["final_test_loss"] == pytest.approx(tlosses[-1], rel=1e-11) and rep["final_test_accuracy"] == taccs[-1]
+
+
+def test_main_scenario_async_replays_through_the_literal_master_loop():
+    """Main.scenario in async mode (Main.scala:82-96): the run itself is a race (Hogwild), so the check is a replay: the
+    polls the master made (update counter, raw test loss / accuracy of the snapshot it took) go through the literal
+    restatement of core/MasterAsync.scala:96-177 and must give the same leaky lists, the same best snapshot, the same end."""
+    from distributed_sgd_b200.main import scenario
+    from distributed_sgd_b200.utils import load_config, synthetic_rcv1
+    from oracle import scala_semantics as S
+    data = synthetic_rcv1(n_rows=6000, seed=5)
     cfg = load_config(env={"DSGD_ASYNC": "true", "DSGD_BATCH_SIZE": "1", "DSGD_MAX_EPOCHS": "5", "DSGD_CHECK_EVERY": "2000",
                            "DSGD_LEARNING_RATE": "0.1"})
-    rep = scenario(cfg, data, rank=0, world=1, device=0, log=lambda s: None, async_concurrency=8)
-    assert rep["initial_loss"] == 1.0 and len(rep["history"]["test_losses"]) >= 1
+    final = {}
+    rep = scenario(cfg, data, rank=0, world=1, device=0, log=lambda s: None, async_concurrency=8,
+                   inspect=lambda what, obj: final.update({what: obj}))
+    master, state = final["done"]
+    h = master.history
+    assert rep["initial_loss"] == 1.0 and len(h["test_losses"]) >= 1
+    raw = iter(zip(h["raw_test_losses"], h["raw_test_accs"]))
+    polls = []
+    for i, (u, computed) in enumerate(h["polls"]):
+        l, a = next(raw) if computed else (None, None)
+        polls.append((u, l, a, i))
+    ref = S.MasterAsyncLossChecker(int(data.n_rows * 0.8), cfg.max_epochs,
+                                   S.early_stopping_no_improvement(cfg.patience, cfg.conv_delta), cfg.check_every,
+                                   cfg.leaky_loss).replay(polls)
+    assert ref["computed_at"] == h["checks_at"] and ref["ended_by"] == h["ended_by"]
+    assert ref["test_losses"] == h["test_losses"] and ref["test_accs"] == h["test_accs"]
+    assert state.loss == ref["best_loss"] == min(h["test_losses"])
+    # the returned weights are the snapshot of the best check: re-evaluating them gives that check's RAW test loss
+    loss_best, _ = master.local_loss_accuracy(state.grad, test_data=True)
+    assert loss_best == pytest.approx(h["raw_test_losses"][h["best_check"]], rel=1e-12)
     assert rep["final_test_accuracy"] > 0.5 and rep["final_weights_nonzero"] > 0
 
 

@@ -210,3 +210,80 @@ def test_jvm_async_draws():
     d = a.async_draws(assigned, 4, batch_size=7)                       # positions, not ids (quirk Q6)
     assert d.shape == (28,) and d.max() < 100
     assert d[:7].tolist() == b.shuffle(np.arange(100))[:7].tolist()
+
+
+class _AsyncScriptCtx:
+    """Stand-in device context for MasterAsync: the update counter and the test-set evaluation follow a script, so the
+    host-side loop (polling, leaky loss, best weights, stop rules) can be compared with the literal restatement of
+    core/MasterAsync.scala:66-177 on the SAME stream."""
+
+    def __init__(self, dim, counter_script, eval_script, n_test):
+        self.dim, self.counter, self.evals, self.n_test = dim, list(counter_script), list(eval_script), n_test
+        self.poll, self.snapshots, self.stopped = -1, [], False
+
+    def set_weights(self, w): pass
+    def async_host_master(self, w): pass
+
+    def async_updates(self):
+        self.poll += 1
+        return self.counter[min(self.poll, len(self.counter) - 1)]
+
+    def async_master_weights(self):
+        w = np.zeros(self.dim); w[0] = float(self.poll)       # tag the snapshot with the poll it was taken at
+        self.snapshots.append(self.poll)
+        return w
+
+    def eval_counts(self, lo, hi, w=None):
+        hinge, correct, n2 = self.evals[int(w[0])]
+        return hinge, correct, n2
+
+    def stop_async(self): self.stopped = True
+
+
+@pytest.mark.parametrize("case", ["converges", "max_steps", "no_check_before_max_steps"])
+def test_master_async_loop_matches_the_literal_restatement(case):
+    """A12: MasterAsync.fit's polling loop against oracle/scala_semantics.MasterAsyncLossChecker over one recorded stream:
+    which polls compute (`updates - lastStep < minStepsBetweenChecks`), the leaky averages, the best-loss rule (strict >),
+    the early stop and the `updates >= n * maxEpochs` stop, and what endComputation returns."""
+    from types import SimpleNamespace
+    from distributed_sgd_b200.core.master import MasterAsync
+    from distributed_sgd_b200.ml import SparseSVM
+    from distributed_sgd_b200.utils.dataset import Data
+    dim, n_train, n_test, lam, leak, every = 6, 50, 20, 0.25, 0.7, 30
+    rng = np.random.default_rng(3)
+    if case == "converges":
+        counter = np.cumsum(rng.integers(5, 25, size=200)).tolist()
+        hinge = [int(h) for h in np.r_[np.linspace(36, 8, 60), np.full(140, 8)] + rng.integers(0, 2, size=200)]
+        max_epoch = 1000
+    elif case == "max_steps":
+        counter = np.cumsum(rng.integers(5, 25, size=200)).tolist()
+        hinge = [int(h) for h in np.linspace(38, 2, 200)]                          # keeps improving: only maxSteps ends it
+        max_epoch = 20                                                              # 50 * 20 = 1000 updates
+    else:
+        counter = [5, 12, 2000]                                                    # maxSteps is hit before any check is due
+        hinge = [20, 20, 20]
+        max_epoch = 20
+        every = 400
+    evals = [(h, n_test - h // 2, 1.5 + 0.01 * i) for i, h in enumerate(hinge)]
+    stub = lambda n: Data(np.arange(n + 1, dtype=np.int64), np.zeros(n, np.int32), np.ones(n, np.float32), np.ones(n, np.int8), dim)
+    ctx = _AsyncScriptCtx(dim, counter, evals, n_test)
+    slave = SimpleNamespace(ctx=ctx, world=1, is_async=True, n_train=n_train, n_test=n_test, dim=dim,
+                            start_async=lambda *a, **k: None, stop_async=ctx.stop_async)
+    m = MasterAsync(0, stub(n_train), stub(n_test), SparseSVM(lam), 1, slave=slave)
+    crit = EarlyStopping.no_improvement(patience=3, min_delta=0.01)
+    state = m.fit(np.zeros(dim), max_epoch=max_epoch, batch_size=1, learning_rate=0.5, stopping_criterion=crit,
+                  check_every=every, leak_loss_coef=leak, poll_seconds=0.0)
+    # the same stream through the literal restatement
+    polls = [(u, lam * evals[i][2] + evals[i][0] / n_test, evals[i][1] / n_test, i) for i, u in enumerate(counter)]
+    ref = S.MasterAsyncLossChecker(n_train, max_epoch, S.early_stopping_no_improvement(3, 0.01), every, leak).replay(polls)
+    assert m.history["ended_by"] == ref["ended_by"] == {"converges": "converged", "max_steps": "max_steps",
+                                                       "no_check_before_max_steps": "max_steps"}[case]
+    assert m.history["checks_at"] == ref["computed_at"]
+    assert m.history["test_losses"] == ref["test_losses"] and m.history["test_accs"] == ref["test_accs"]   # bit-equal floats
+    assert ctx.stopped
+    if ref["computed_at"]:
+        assert state.loss == ref["best_loss"] and int(state.grad[0]) == ref["best_grad"]
+        assert m.history["best_check"] == ref["computed_at"].index(counter[ref["best_grad"]])
+    else:
+        assert ref["best_grad"] == "Vec.zeros(1)"       # the reference would hand back its initial bestGrad; see master.py
+    assert state.end is not None and state.updates == 1
