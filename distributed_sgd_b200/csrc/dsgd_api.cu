@@ -42,6 +42,7 @@ struct dsgd_ctx {
   uint32_t *rp16 = nullptr;
   uint2 *pairs = nullptr;
   int8_t *label = nullptr;
+  float *yabs = nullptr;   // label * sum_j |x_j| per row (dsgd_kernels.cuh: k_repack)
 
   // state (fp64, L2 resident) -- g has dim + 2 slots (hinge sum and batch size ride in the allreduce)
   double *w = nullptr, *g = nullptr, *d = nullptr, *w_req = nullptr;
@@ -70,11 +71,12 @@ struct dsgd_ctx {
   // persistent sync kernel resources (allocated on first use)
   double *p_wbuf[2] = {nullptr, nullptr};
   double *p_gbuf[3] = {nullptr, nullptr, nullptr};
-  double *p_partial = nullptr;
+  double2 *p_parts = nullptr;       // grid barrier: partials rows [2][kBarStride][kBarStride]
+  unsigned *p_flags = nullptr;      //               flag rows [kBarStride][kBarStride]
+  unsigned bar_epoch = 0;           // barrier phases used so far (flags are monotone across launches)
   unsigned *p_hinge = nullptr;
   int64_t p_hinge_cap = 0;
-  unsigned *p_bar = nullptr;   // [0]: barrier counter, [1]: abort flag
-  unsigned *p_bar_flags = nullptr;  // release flag lines of the flag barrier
+  unsigned *p_bar = nullptr;   // [1]: abort flag
   uint32_t *hot_bits = nullptr;     // hot-column bitmap / slot prefix / slot -> column of the streaming scatter (dsgd_stream.cuh)
   uint16_t *hot_prefix = nullptr;
   int32_t *hot_cols = nullptr;
@@ -283,9 +285,9 @@ extern "C" int dsgd_destroy(dsgd_ctx *ctx) {
   if (ctx->a_ev0) { cudaEventDestroy(ctx->a_ev0); cudaEventDestroy(ctx->a_ev1); }
   if (ctx->astream) cudaStreamDestroy(ctx->astream);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
-  void *ptrs[] = {ctx->rp16, ctx->pairs, ctx->label, ctx->w, ctx->g, ctx->d, ctx->w_req, ctx->w32, ctx->w32_req, ctx->n_exact, ctx->scal,
+  void *ptrs[] = {ctx->rp16, ctx->pairs, ctx->label, ctx->yabs, ctx->w, ctx->g, ctx->d, ctx->w_req, ctx->w32, ctx->w32_req, ctx->n_exact, ctx->scal,
                   ctx->cnt, ctx->partial, ctx->out2, ctx->gsum, ctx->p_wbuf[0], ctx->p_wbuf[1], ctx->p_gbuf[0],
-                  ctx->p_gbuf[1], ctx->p_gbuf[2], ctx->p_partial, ctx->p_hinge, ctx->p_bar, ctx->p_bar_flags, ctx->x_stats, ctx->hot_bits, ctx->hot_prefix, ctx->hot_cols, ctx->samples,
+                  ctx->p_gbuf[1], ctx->p_gbuf[2], ctx->p_parts, ctx->p_flags, ctx->p_hinge, ctx->p_bar, ctx->x_stats, ctx->hot_bits, ctx->hot_prefix, ctx->hot_cols, ctx->samples,
                   ctx->losses, ctx->preds};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -403,12 +405,13 @@ extern "C" int dsgd_load_csr(dsgd_ctx *ctx, int64_t n_rows, int64_t nnz, const i
     for (int64_t k = row_ptr[r] + 1; k < row_ptr[r + 1]; ++k)
       if (col[k] <= col[k - 1]) { unique = false; break; }
   CU(cudaSetDevice(ctx->device));
-  for (void *p : {(void *)ctx->rp16, (void *)ctx->pairs, (void *)ctx->label}) if (p) CU(cudaFree(p));
-  ctx->rp16 = nullptr; ctx->pairs = nullptr; ctx->label = nullptr;
+  for (void *p : {(void *)ctx->rp16, (void *)ctx->pairs, (void *)ctx->label, (void *)ctx->yabs}) if (p) CU(cudaFree(p));
+  ctx->rp16 = nullptr; ctx->pairs = nullptr; ctx->label = nullptr; ctx->yabs = nullptr;
   const int64_t n_pairs = (int64_t)acc * 2;
   CU(cudaMalloc(&ctx->rp16, sizeof(uint32_t) * ((size_t)n_rows + 1)));
   CU(cudaMalloc(&ctx->pairs, sizeof(uint2) * (size_t)std::max<int64_t>(n_pairs, 1)));
   CU(cudaMalloc(&ctx->label, (size_t)n_rows));
+  CU(cudaMalloc(&ctx->yabs, sizeof(float) * (size_t)n_rows));
   int64_t *d_rp = nullptr; int32_t *d_col = nullptr; float *d_val = nullptr;
   CU(cudaMalloc(&d_rp, sizeof(int64_t) * ((size_t)n_rows + 1)));
   CU(cudaMalloc(&d_col, sizeof(int32_t) * (size_t)std::max<int64_t>(nnz, 1)));
@@ -421,7 +424,7 @@ extern "C" int dsgd_load_csr(dsgd_ctx *ctx, int64_t n_rows, int64_t nnz, const i
   CU(cudaMemcpyAsync(ctx->rp16, rp16.data(), sizeof(uint32_t) * ((size_t)n_rows + 1), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->label, label, (size_t)n_rows, cudaMemcpyHostToDevice, ctx->stream));
   const int blocks = std::min<int64_t>(cdiv(n_rows, 8), (int64_t)ctx->sm_count * 16);
-  k_repack<<<blocks, 256, 0, ctx->stream>>>(d_rp, d_col, d_val, ctx->rp16, n_rows, ctx->pairs);
+  k_repack<<<blocks, 256, 0, ctx->stream>>>(d_rp, d_col, d_val, ctx->rp16, ctx->label, n_rows, ctx->pairs, ctx->yabs);
   LAUNCHED();
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(ctx->stream));
@@ -668,7 +671,7 @@ static int stream_launch(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t row_
     const int64_t m = std::min<int64_t>(max_rows, n - off);
     StreamParams sp;
     memset(&sp, 0, sizeof sp);
-    sp.rp16 = ctx->rp16; sp.units = reinterpret_cast<const uint4 *>(ctx->pairs); sp.label = ctx->label;
+    sp.rp16 = ctx->rp16; sp.units = reinterpret_cast<const uint4 *>(ctx->pairs); sp.yabs = ctx->yabs;
     sp.samples = samples_dev ? samples_dev + off : nullptr; sp.row_begin = row_begin + off; sp.n = m;
     sp.w = w_dev; sp.w32 = w32_dev; sp.dim = ctx->dim;
     sp.g = g; sp.preds = preds ? preds + off : nullptr; sp.cnt = ctx->cnt; sp.n_exact = ctx->n_exact; sp.next_block = ctx->n_exact + 1;
@@ -834,14 +837,12 @@ static persist_kernel_t persist_variant(int opt) {
     default: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, kMulti, 3>;
   }
 }
-// TEMPORARY A/B switch of round 2's first GPU session (removed once measured): bit 0 = flag barrier, bit 1 = one-pass
-// single-chunk rows
+// TEMPORARY A/B switch (removed once measured): bit 1 = one-pass single-chunk rows
 static int persist_opt() {
-  static const int v = getenv("DSGD_PERSIST_OPT") ? atoi(getenv("DSGD_PERSIST_OPT")) & 3 : 2;
+  static const int v = getenv("DSGD_PERSIST_OPT") ? atoi(getenv("DSGD_PERSIST_OPT")) & 2 : 2;
   return v;
 }
 static bool persist_timeline() { static const bool v = getenv("DSGD_PERSIST_TIMELINE") != nullptr; return v; }
-static size_t bar_flag_words(const dsgd_ctx *ctx) { return (size_t)kBarFlagStride * (size_t)(ctx->sm_count / kBarGroup + 1); }
 
 static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
   if (!ctx->p_ready) {
@@ -851,13 +852,15 @@ static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
       CU(cudaMalloc(&ctx->p_gbuf[i], vd));
       CU(cudaMemsetAsync(ctx->p_gbuf[i], 0, vd, ctx->stream));
     }
-    CU(cudaMalloc(&ctx->p_partial, sizeof(double) * 2 * 2 * (size_t)ctx->sm_count));
+    CU(cudaMalloc(&ctx->p_parts, sizeof(double2) * 2 * (size_t)kBarStride * kBarStride));
+    CU(cudaMemsetAsync(ctx->p_parts, 0, sizeof(double2) * 2 * (size_t)kBarStride * kBarStride, ctx->stream));
+    CU(cudaMalloc(&ctx->p_flags, sizeof(unsigned) * (size_t)kBarStride * kBarStride));
+    CU(cudaMemsetAsync(ctx->p_flags, 0, sizeof(unsigned) * (size_t)kBarStride * kBarStride, ctx->stream));
     CU(cudaMalloc(&ctx->p_bar, sizeof(unsigned) * 4));
     for (int opt = 0; opt < 4; ++opt) {
       CU(cudaFuncSetAttribute((const void *)persist_variant<false>(opt), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
       CU(cudaFuncSetAttribute((const void *)persist_variant<true>(opt), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
     }
-    CU(cudaMalloc(&ctx->p_bar_flags, sizeof(unsigned) * bar_flag_words(ctx)));
     ctx->p_ready = true;
   }
   if (ctx->p_hinge_cap < n_steps) {
@@ -884,21 +887,34 @@ static bool persist_multi_fits(const dsgd_ctx *ctx, int G) {
   return slice <= (kPCons + kPUpd) * 32;
 }
 
+// The kernel synchronises its CTAs itself, so all of them must be resident: a cooperative launch guarantees that.  With a
+// grid limit (several contexts sharing one GPU: the K-rank tests on one device) the kernels of the ranks must also run
+// CONCURRENTLY, which cooperative launches of different contexts do not (measured: they serialise and the ranks time
+// out waiting for each other); a plain launch of at most one CTA per SM on an otherwise idle GPU is resident in full too.
+static cudaError_t persist_launch(dsgd_ctx *ctx, void *fn, int G, void **args) {
+  if (ctx->grid_limit > 0) return cudaLaunchKernel(fn, dim3(G), dim3((kPCons + kPUpd + 1) * 32), args, sizeof(PSmem), ctx->stream);
+  return cudaLaunchCooperativeKernel(fn, dim3(G), dim3((kPCons + kPUpd + 1) * 32), args, sizeof(PSmem), ctx->stream);
+}
+
 // fields shared by the one-GPU and the K-GPU launch
 static int persist_params(dsgd_ctx *ctx, PersistParams &pp, const int32_t *samples_dev, int64_t n_per_step, int64_t n_steps,
-                          double lr, double *losses_dev, int opt) {
+                          double lr, double *losses_dev, int G) {
+  NEED(G <= kBarStride, DSGD_ERR_INVALID, "more CTAs (%d) than rows in the barrier's flag table (%d)", G, kBarStride);
   memset(&pp, 0, sizeof pp);
   pp.rp16 = ctx->rp16; pp.pairs = ctx->pairs; pp.label = ctx->label; pp.samples = samples_dev;
   pp.n_steps = n_steps; pp.batch = (int32_t)n_per_step; pp.dim = ctx->dim;
   pp.wbuf[0] = ctx->p_wbuf[0]; pp.wbuf[1] = ctx->p_wbuf[1];
   for (int i = 0; i < 3; ++i) pp.gbuf[i] = ctx->p_gbuf[i];
-  pp.d = ctx->d; pp.partial = ctx->p_partial; pp.hinge = ctx->p_hinge; pp.losses = losses_dev;
+  pp.d = ctx->d; pp.parts = ctx->p_parts; pp.flags = ctx->p_flags; pp.hinge = ctx->p_hinge; pp.losses = losses_dev;
   pp.w_out = ctx->w; pp.w32_out = ctx->w32; pp.scal = ctx->scal;
-  pp.bar = ctx->p_bar; pp.abort_flag = reinterpret_cast<int *>(ctx->p_bar + 1); pp.bar_flags = ctx->p_bar_flags;
+  pp.abort_flag = reinterpret_cast<int *>(ctx->p_bar + 1);
+  // flags hold step numbers that only grow: this launch uses phases bar_epoch + 1 .. bar_epoch + n_steps + 1 (an aborted
+  // launch leaves smaller numbers behind, which the next launch never waits for)
+  pp.phase_base = ctx->bar_epoch;
+  ctx->bar_epoch += (unsigned)(n_steps + 2);
   pp.lambda = ctx->lambda; pp.lr = lr; pp.world = 1;
   CU(cudaMemsetAsync(ctx->p_hinge, 0, sizeof(unsigned) * (size_t)n_steps, ctx->stream));
   CU(cudaMemsetAsync(ctx->p_bar, 0, sizeof(unsigned) * 4, ctx->stream));
-  if (opt & 1) CU(cudaMemsetAsync(ctx->p_bar_flags, 0, sizeof(unsigned) * bar_flag_words(ctx), ctx->stream));
   if (persist_timeline()) {
     if (!ctx->p_tl) CU(cudaMalloc(&ctx->p_tl, sizeof(long long) * kTlWords));
     CU(cudaMemsetAsync(ctx->p_tl, 0, sizeof(long long) * kTlWords, ctx->stream));
@@ -915,15 +931,14 @@ static int persist_run(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t n_per_
   NEED((uint64_t)G * (uint64_t)(n_steps + 2) < (1ull << 32), DSGD_ERR_INVALID, "dsgd_sync_steps: too many steps for one launch");
   const int opt = persist_opt();
   PersistParams pp;
-  if ((rc = persist_params(ctx, pp, samples_dev, n_per_step, n_steps, lr, losses_dev, opt))) return rc;
+  if ((rc = persist_params(ctx, pp, samples_dev, n_per_step, n_steps, lr, losses_dev, G))) return rc;
   CU(cudaMemcpyAsync(ctx->p_wbuf[1], ctx->w, sizeof(double) * (size_t)ctx->dim, cudaMemcpyDeviceToDevice, ctx->stream));
   pp.k_den = 1.0;
   pp.timeout_cycles = 4000000000ll;  // ~2 s at 1.9 GHz: a healthy barrier takes well under a microsecond
   void *args[] = {&pp};
   auto *pe = prof_slot(ctx);
   if (pe) cudaEventRecord(pe->first, ctx->stream);
-  CU(cudaLaunchCooperativeKernel((void *)persist_variant<false>(opt), dim3(G), dim3((kPCons + kPUpd + 1) * 32), args, sizeof(PSmem),
-                                 ctx->stream));
+  CU(persist_launch(ctx, (void *)persist_variant<false>(opt), G, args));
   if (pe) cudaEventRecord(pe->second, ctx->stream);
   LAUNCHED();
   return DSGD_OK;
@@ -962,7 +977,7 @@ static int persist_run_multi(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t 
   NEED((uint64_t)G * (uint64_t)(n_steps + 2) < (1ull << 32), DSGD_ERR_INVALID, "dsgd_sync_steps: too many steps for one launch");
   const int opt = persist_opt();
   PersistParams pp;
-  if ((rc = persist_params(ctx, pp, samples_dev, n_per_step, n_steps, lr, losses_dev, opt))) return rc;
+  if ((rc = persist_params(ctx, pp, samples_dev, n_per_step, n_steps, lr, losses_dev, G))) return rc;
   // the kernel's first interval reads the host-provided weights from wbuf[0] and publishes them in LL form
   CU(cudaMemcpyAsync(ctx->p_wbuf[0], ctx->w, sizeof(double) * (size_t)ctx->dim, cudaMemcpyDeviceToDevice, ctx->stream));
   pp.k_den = (double)ctx->world;
@@ -985,8 +1000,7 @@ static int persist_run_multi(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t 
   void *args[] = {&pp};
   auto *pe = prof_slot(ctx);
   if (pe) cudaEventRecord(pe->first, ctx->stream);
-  CU(cudaLaunchCooperativeKernel((void *)persist_variant<true>(opt), dim3(G), dim3((kPCons + kPUpd + 1) * 32), args, sizeof(PSmem),
-                                 ctx->stream));
+  CU(persist_launch(ctx, (void *)persist_variant<true>(opt), G, args));
   if (pe) cudaEventRecord(pe->second, ctx->stream);
   LAUNCHED();
   // The next launch must not meet LL words carrying tags this one used (the host may install new weights in between): the
@@ -1074,7 +1088,7 @@ static int persist_check(dsgd_ctx *ctx) {  // after a stream sync: did a device-
   if (!ctx->p_ready) return DSGD_OK;
   unsigned host[2] = {0, 0};
   CU(cudaMemcpy(host, ctx->p_bar, sizeof host, cudaMemcpyDeviceToHost));
-  NEED(host[1] == 0, DSGD_ERR_TIMEOUT, "persistent sync kernel: a grid barrier hit its watchdog (arrivals %u)", host[0]);
+  NEED(host[1] == 0, DSGD_ERR_TIMEOUT, "persistent sync kernel: a device-side wait (grid barrier, peer word) hit its watchdog");
   return DSGD_OK;
 }
 

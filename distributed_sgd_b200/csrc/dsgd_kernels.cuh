@@ -314,7 +314,8 @@ __global__ void __launch_bounds__(256) k_dim_sparsity(const unsigned *__restrict
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_repack(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                                                 const float *__restrict__ val, const uint32_t *__restrict__ rp16,
-                                                int64_t n_rows, uint2 *__restrict__ pairs) {
+                                                const int8_t *__restrict__ label, int64_t n_rows, uint2 *__restrict__ pairs,
+                                                float *__restrict__ yabs) {
   // one warp per row keeps the writes coalesced
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -323,16 +324,25 @@ __global__ void __launch_bounds__(256) k_repack(const int64_t *__restrict__ row_
     const int64_t sb = row_ptr[r], se = row_ptr[r + 1];
     const int64_t db = (int64_t)rp16[r] * 2, de = (int64_t)rp16[r + 1] * 2;
     const int64_t len = se - sb;
+    double asum = 0.0;
     for (int64_t k = lane; k < de - db; k += 32) {
       uint2 pr;
       if (k < len) {
         pr.x = (uint32_t)col[sb + k];
         pr.y = __float_as_uint(val[sb + k]);
+        asum += fabs((double)val[sb + k]);
       } else {
         pr.x = len > 0 ? (uint32_t)col[se - 1] : 0u;
         pr.y = 0u;
       }
       pairs[db + k] = pr;
+    }
+    // yabs[r] = label * sum_j |x_j| rounded UP to fp32 (the sign bit carries the label, also on a zero sum): the streaming
+    // pass reads the label and the rounding-band scale of a row with one 4-byte load
+    asum = warp_sum(asum);
+    if (lane == 0) {
+      const float a = __double2float_ru(asum);
+      yabs[r] = label[r] < 0 ? -a : a;
     }
   }
 }

@@ -15,11 +15,17 @@
 //     gate, RED of y*x into g.  Longer rows: partial dots per chunk (fixed order), then gate + scatter per chunk.
 //   * UPDATE warps: weights are double-buffered and gradients triple-buffered in L2 so the update of step
 //     t-1 and the gradient of step t share one barrier interval.
-//   * c_t = 2*lambda*(W_t . d) (SparseSVM.scala:31) is a dot over the whole weight vector that the NEXT interval
-//     needs first thing.  The update warps finish W_t early in interval t, so they run their own small barrier
-//     (a second counter, arrivals of one thread per CTA) and sum the per-CTA partials in a fixed order while the
-//     consumers are still busy: c_t is in shared memory before the grid barrier of step t completes
-//     (round 1 summed it after the barrier: 1 880 cycles on the critical path).
+//   * GRID BARRIER = all-to-all flags.  A counter barrier (148 arrivals and 148 pollers on one L2 line) measured 2 500
+//     cycles from the last arrival to the first exit on a B200 (profiles/r2_timeline.md).  Here every CTA owns a row of
+//     148 flag words; an arriving CTA fences once and stores the step number into its word of EVERY row (148 posted
+//     stores from one warp), then polls only its own row (five 128-byte lines, nobody else reads them).  Next to the flag
+//     it has already stored its partial {W.d, ||W||^2} into every CTA's private partials row, so
+//   * c_t = 2*lambda*(W_t . d) (SparseSVM.scala:31), a dot over the whole weight vector that the next interval needs,
+//     costs no second barrier and no shared hot line: after the barrier each CTA's update warp 0 reads ITS 148 partials
+//     (one L2 round trip, overlapped with the consumers' first gathers) and sums them in a fixed order -- the same values
+//     in the same order in every CTA, so all CTAs (and all GPUs) hold bit-identical c.  (Round 1 read one shared 2.4 KB
+//     area from 148 CTAs at once: c arrived 1 880 cycles into the interval.  Round 2's first attempt gave the update
+//     warps a second counter barrier: two serialised barriers per step, slower -- profiles/r2_timeline.md.)
 //
 // One GPU (kMulti == false), interval I_t between grid barrier t-1 and t, W_t = weights step t differentiates at:
 //   consumers: x.W_t with W_t[col] = update(W_{t-1}[col], g_{t-1}[col], c_{t-1}) applied on the fly; gate; RED into g_t
@@ -60,14 +66,14 @@ struct PersistParams {
   double *wbuf[2];  // one GPU: on entry wbuf[1] holds the initial weights; K GPUs: wbuf[0]
   double *gbuf[3];  // all zero on entry and on exit
   const double *d;
-  double *partial;  // [2][gridDim.x][2]: per-CTA partials of W.d and ||W||^2
+  double2 *parts;   // [2 parities][kBarStride dest][kBarStride src]: {W.d, ||W||^2} partial of CTA src, one copy per dest
   unsigned *hinge;  // [n_steps], zero on entry (one GPU)
   double *losses;   // [n_steps] or nullptr
   double *w_out;    // resident weights after the last step
   float *w32_out;
   double *scal;     // kScalC / kScalNrm2 of the resident weights
-  unsigned *bar;    // [0] grid barrier arrivals, [2] arrivals of the update warps' barrier; zero on entry
-  unsigned *bar_flags;  // release flags of the flag barrier (kOpt & 1), one 128-byte line per kBarGroup CTAs, zero on entry
+  unsigned *flags;  // grid barrier: [kBarStride dest][kBarStride src] step numbers (monotone across launches)
+  unsigned phase_base;  // barrier phases of this launch are phase_base + 1 ...
   int *abort_flag;  // set to 1 if a wait hit the watchdog
   double lambda, lr, k_den;
   long long timeout_cycles;
@@ -193,75 +199,62 @@ __device__ __forceinline__ double apply_update(double wv, double graw, double c,
   return wv;
 }
 
-// Fixed-order sums of the per-CTA partials {W.d, ||W||^2} (2 doubles per CTA); the same in every CTA.
-// All loads are issued before the first add (up to kPartLoads per lane: covers 160 CTAs).
-constexpr int kPartLoads = 5;
-__device__ __forceinline__ void sum_partials2(const double *p, int n_cta, int lane, double &s0, double &s1) {
-  double2 v[kPartLoads];
+// ---- grid barrier among the barrier-synchronised warps of every CTA (the producer warp stays out) -------------------
+// flags[dest][src] / parts[parity][dest][src]: row `dest` is read by CTA dest only, column `src` written by CTA src only.
+constexpr int kBarStride = 160;   // >= CTAs (148 SMs on a B200), multiple of 32
+__device__ __forceinline__ void st_relaxed_gpu_f64x2(double2 *p, double a, double b) {
+  asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ double2 ld_relaxed_gpu_f64x2(const double2 *p) {
+  double2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
+// Called by ONE whole warp (update warp 0) of every CTA after the CTA-level bar.sync; (sd, sn) = this CTA's partial.
+// Returns false if the watchdog fired.
+__device__ __forceinline__ bool grid_barrier_warp(unsigned *flags, double2 *parts_par, unsigned phase, int n_cta, int lane,
+                                                  double sd, double sn, int *abort_flag, long long timeout) {
+  const int me = blockIdx.x;
+  for (int dest = lane; dest < n_cta; dest += 32) st_relaxed_gpu_f64x2(parts_par + (size_t)dest * kBarStride + me, sd, sn);
+  fence_acq_rel_gpu();   // release: everything this CTA wrote (cumulative through the bar.sync) and the partials above
+  for (int dest = lane; dest < n_cta; dest += 32) st_relaxed_gpu(flags + (size_t)dest * kBarStride + me, phase);
+  const unsigned *mine = flags + (size_t)me * kBarStride;
+  const long long t0 = clock64();
+  unsigned spins = 0;
+  bool ok = true;
+  for (;;) {
+    bool all = true;
 #pragma unroll
-  for (int i = 0; i < kPartLoads; ++i) {
-    const int b = lane + 32 * i;
-    v[i] = make_double2(0.0, 0.0);
-    if (b < n_cta) v[i] = __ldcg(reinterpret_cast<const double2 *>(p) + b);
+    for (int k = 0; k < kBarStride / 32; ++k) {
+      const int src = lane + 32 * k;
+      if (src < n_cta) all = all && ((int)(ld_relaxed_gpu(mine + src) - phase) >= 0);
+    }
+    if (__all_sync(0xffffffffu, all)) break;
+    if ((++spins & 255u) == 0u && (clock64() - t0 > timeout || *(volatile int *)abort_flag)) {
+      *(volatile int *)abort_flag = 1;
+      ok = false;
+      break;
+    }
+  }
+  fence_acq_rel_gpu();   // acquire
+  return ok;
+}
+// The partials the barrier delivered to this CTA, summed in a fixed order (lane-strided, then a butterfly): the same
+// additions in every CTA of every GPU.  All lanes return the sums.
+__device__ __forceinline__ void sum_parts(const double2 *parts_par, int n_cta, int lane, double &s0, double &s1) {
+  const double2 *mine = parts_par + (size_t)blockIdx.x * kBarStride;
+  double2 v[kBarStride / 32];
+#pragma unroll
+  for (int k = 0; k < kBarStride / 32; ++k) {
+    const int src = lane + 32 * k;
+    v[k] = make_double2(0.0, 0.0);
+    if (src < n_cta) v[k] = ld_relaxed_gpu_f64x2(mine + src);
   }
   double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-  for (int i = 0; i < kPartLoads; ++i) { a0 += v[i].x; a1 += v[i].y; }
-  for (int b = lane + 32 * kPartLoads; b < n_cta; b += 32) {  // more than 160 CTAs: not on a B200
-    const double2 w2 = __ldcg(reinterpret_cast<const double2 *>(p) + b);
-    a0 += w2.x; a1 += w2.y;
-  }
+  for (int k = 0; k < kBarStride / 32; ++k) { a0 += v[k].x; a1 += v[k].y; }
   s0 = warp_sum(a0);
   s1 = warp_sum(a1);
-}
-
-// Relaxed polling of a monotone counter with the watchdog; returns false if it fired.
-__device__ __forceinline__ bool poll_counter(const unsigned *ctr, unsigned target, int *abort_flag, long long timeout) {
-  const long long t0 = clock64();
-  unsigned spins = 0;
-  while ((int)(ld_relaxed_gpu(ctr) - target) < 0) {
-    if ((++spins & 1023u) == 0u && (clock64() - t0 > timeout || *(volatile int *)abort_flag)) {
-      *(volatile int *)abort_flag = 1;
-      return false;
-    }
-  }
-  return true;
-}
-
-// One grid-wide barrier among the barrier-synchronised warps of every CTA (the producer warp stays out):
-// CTA-level named barrier, one release arrival, relaxed polling, one acquire fence.
-// kFlags == false: every CTA polls the word the arrivals are added to.
-// kFlags == true : nobody polls the counter: the arrival is an atom that returns the count, the LAST arriver raises
-//                  one flag per group of kBarGroup CTAs (each on its own 128-byte line), the others poll their group's.
-constexpr int kBarGroup = 8;
-constexpr int kBarFlagStride = 32;  // unsigned words per flag line
-template <bool kFlags>
-__device__ __forceinline__ bool grid_barrier(unsigned *bar, unsigned *flags, unsigned phase, unsigned n_cta, int *abort_flag,
-                                             long long timeout, int *smem_ok, int n_sync_threads, long long *tl, bool tl_ns) {
-  named_bar_sync(3, n_sync_threads);
-  if (threadIdx.x == 0) {
-    if (tl) tl[0] = tl_ns ? global_ns() : clock64();
-    int ok = 1;
-    if constexpr (kFlags) {
-      const unsigned old = atom_acq_rel_gpu_add(bar, 1u);  // release: this CTA's writes; acquire: every earlier arrival's
-      if (old + 1u == phase * n_cta) {
-        fence_acq_rel_gpu();                               // fence + relaxed stores: a release pattern per flag
-        const unsigned n_groups = (n_cta + kBarGroup - 1) / kBarGroup;
-        for (unsigned g = 0; g < n_groups; ++g) st_relaxed_gpu(flags + g * kBarFlagStride, phase);
-      } else {
-        ok = poll_counter(flags + (blockIdx.x / kBarGroup) * kBarFlagStride, phase, abort_flag, timeout) ? 1 : 0;
-        fence_acq_rel_gpu();
-      }
-    } else {
-      red_release_gpu_add(bar, 1u);
-      ok = poll_counter(bar, phase * n_cta, abort_flag, timeout) ? 1 : 0;
-      fence_acq_rel_gpu();
-    }
-    *smem_ok = ok;
-    if (tl) tl[1] = tl_ns ? global_ns() : clock64();
-  }
-  named_bar_sync(3, n_sync_threads);
-  return *(volatile int *)smem_ok != 0;
 }
 
 constexpr int kChunkPairs = 128;             // 4 pairs per lane per chunk
@@ -292,7 +285,6 @@ struct PersistSmem {
   uint64_t full[kStages];
   uint64_t empty[kStages];
   uint64_t c_bar[2];    // c of the weights interval t updates from: completed during interval t-1
-  uint64_t u_bar;       // K GPUs: every sync warp has published its partial of W_T.d, ||W_T||^2
   double c_val[2];
   double nrm_val[2];
   double red[kCons + kUpd][2];
@@ -392,7 +384,7 @@ struct FetchLL {
 // dot, from the registers that still hold its pairs (0.0 + acc == acc: the same dot as the two-pass form).
 template <int kCons, int kMaxChunks, bool kOnePass, class Fetch>
 __device__ __forceinline__ unsigned consume_stage(StageMeta<kMaxChunks> &mt, const uint2 *ring, const uint2 *pairs, double *Gcur,
-                                                  Fetch &fetch, int warp, int lane) {
+                                                  Fetch &fetch, int warp, int lane, long long *tl) {
   const int n_ch = mt.n_chunks;
   unsigned hinge = 0;  // lane 0 only
   // ---- pass 1: dots of this warp's chunks ----
@@ -411,7 +403,9 @@ __device__ __forceinline__ unsigned consume_stage(StageMeta<kMaxChunks> &mt, con
     double acc = 0.0;
 #pragma unroll
     for (int u = 0; u < 4; ++u) acc += filt(filt((double)__uint_as_float(pr[u].y)) * wv[u]);  // (x * w).sum
+    if (tl && lane == 0 && c == warp) tl[2] = clock64();   // first chunk: weights arrived, products done
     acc = warp_sum(acc);
+    if (tl && lane == 0 && c == warp) tl[4] = clock64();   // ... dot reduced
     if constexpr (kOnePass) {
       const int row1 = mt.ch_row[c];
       if (mt.row_nch[row1] == 1) {
@@ -483,13 +477,12 @@ __device__ __forceinline__ unsigned consume_stage(StageMeta<kMaxChunks> &mt, con
   return hinge;
 }
 
-// kOpt: bit 0 = flag barrier (grid_barrier<true>), bit 1 = one-pass single-chunk rows.
+// kOpt: bit 1 = one-pass single-chunk rows (bit 0 unused).
 template <int kCons, int kUpd, int kStages, int kStagePairs, int kMaxChunks, bool kMulti, int kOpt>
 __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(const PersistParams p) {
   using Smem = PersistSmem<kCons, kUpd, kStages, kStagePairs, kMaxChunks>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
-  constexpr bool kFlagBar = (kOpt & 1) != 0;
   constexpr bool kOnePass = (kOpt & 2) != 0;
 
   const int lane = threadIdx.x & 31;
@@ -510,7 +503,6 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
     }
     mbar_init(&sm.c_bar[0], 1u);
     mbar_init(&sm.c_bar[1], 1u);
-    mbar_init(&sm.u_bar, (unsigned)(kCons + kUpd));
     sm.c_val[0] = 0.0;   // interval 0 has no pending update (g_{-1} == 0): its c is never used
     sm.nrm_val[0] = 0.0;
     sm.hinge_acc = 0u;
@@ -606,7 +598,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
   // =========================================================================================================
   const double lr = p.lr;
   const int64_t base = kMulti ? p.step_base : 0;
-  unsigned phase = 0;
+  unsigned phase = p.phase_base;
   // one GPU: the update threads of all CTAs stride over the columns
   const int n_upd = G * kUpd * 32;
   const int u0 = blockIdx.x * kUpd * 32 + ((int)threadIdx.x - kCons * 32);
@@ -617,7 +609,6 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
   const int j_col = blockIdx.x * slice + (int)threadIdx.x;
   const bool col_act = kMulti && (int)threadIdx.x < slice && j_col <= p.dim;
   const int col_word = j_col >> 5;
-  double nrm_carry = 0.0;            // update warp 0: ||W_{t-1}||^2 (one GPU: for the loss of step t-1)
   unsigned long long st_val = 0, st_bm = 0;
 
   for (int64_t T = base; T <= base + S; ++T) {
@@ -626,13 +617,39 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
     const double *Gprev = p.gbuf[(T + 2) % 3];   // g_{T-1}
     double *Gcur = p.gbuf[T % 3];
     double *Gzero = p.gbuf[(T + 1) % 3];
-    double *part_cur = p.partial + (size_t)(T & 1) * G * 2;
+    const double2 *parts_prev = p.parts + (size_t)((t + 1) & 1) * kBarStride * kBarStride;   // delivered by barrier t-1
+    double2 *parts_cur = p.parts + (size_t)(t & 1) * kBarStride * kBarStride;                // pushed at barrier t
     const unsigned c_par = (unsigned)((t >> 1) & 1);
     const bool tl_cta = p.tl && t >= kTlFirst && t < kTlFirst + kTlSteps && blockIdx.x < kTlCtas;
     long long *tl_rec = tl_cta ? p.tl + 256 * 16 + ((t - kTlFirst) * kTlCtas + blockIdx.x) * kTlPerCta : nullptr;
+    long long *tl_row = (p.tl && blockIdx.x == 0 && t < 256) ? p.tl + t * 16 : nullptr;
     bool ok = true;
     if (warp == 0) DSGD_TL(0);
-    if (warp == kCons) DSGD_TL(8);
+
+    // ---- update warp 0, first thing: c_{T-1} and ||W_{T-1}||^2 from the partials the last barrier delivered ----
+    if (warp == kCons && !first) {
+      double c_prev, nrm_prev;
+      if (kMulti && t == 1) {
+        c_prev = p.scal[kScalC];                              // W_base came from the host: k_prepare / previous launch
+        nrm_prev = p.scal[kScalNrm2];
+      } else {
+        double sd, sn;
+        sum_parts(parts_prev, G, lane, sd, sn);
+        c_prev = p.lambda * 2.0 * sd;
+        nrm_prev = sn;
+      }
+      if (lane == 0) {
+        sm.c_val[t & 1] = c_prev;
+        sm.nrm_val[t & 1] = nrm_prev;
+        mbar_arrive(&sm.c_bar[t & 1]);
+        // one GPU: loss of step t-1 = lambda*||W_{t-1}||^2 + hinge_{t-1}/batch  (SparseSVM.scala:20-23)
+        if (!kMulti && p.losses && blockIdx.x == 0)
+          p.losses[t - 1] = p.lambda * nrm_prev + (double)__ldcg(&p.hinge[t - 1]) / (double)B;
+      }
+      __syncwarp();
+      DSGD_TL(9);
+    }
+    double pd = 0.0, pn = 0.0;   // this thread's share of W_T . d and ||W_T||^2
 
     if constexpr (kMulti) {
       // ---------------------------------------------------------------------------------------------------
@@ -643,7 +660,6 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
       const int parp = (int)((T + 1) & 1);                    // receive parity of step T-1
       const unsigned gtag = (unsigned)T;                      // words of step T-1 carry tag T
       const unsigned wtag = (unsigned)(T + 1);                // W_T words carry tag T+1
-      double pd = 0.0, pn = 0.0;
       if ((int)threadIdx.x < slice) {                         // whole warps: slice is a multiple of 32
         if (first) {
           // W_base arrives as plain doubles from the host (wbuf[0]): publish it in LL form, no update pending
@@ -670,18 +686,15 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
             if (lane == 0) { st_bm += 1; st_val += (unsigned)__popc(my_bits); }
           }
           if (warp == 0) DSGD_TL(11);
-          // c_{T-1}: completed by update warp 0 during the previous interval
-          mbar_wait(&sm.c_bar[t & 1], c_par, p.abort_flag, p.timeout_cycles);
-          const double c_prev = *(volatile double *)&sm.c_val[t & 1];
-          const bool add_c = (c_prev != 0.0) && (fabs(c_prev) > kEps);
           if (warp_act) {
             // bitmap words of the K-1 peers for this warp's 32 columns (one broadcast load each), then the value words
-            // whose bit is set: everything requested before anything is waited for
+            // whose bit is set: everything requested before anything is waited for -- c_{T-1} included
             double raw[kMaxWorld];
             unsigned need = 0;   // bit k: value word of peer k still to be waited for
             double wn = 0.0;
             bool got_w = true;
             if (col_act && j_col < p.dim) got_w = ll_try_load(LWprev + 2 * (size_t)j_col, gtag, wn);
+            const double dj = (col_act && j_col < p.dim) ? __ldg(&p.d[j_col]) : 0.0;
             const unsigned long long *bm0 = p.xbm[me] + (size_t)parp * p.xwords + (size_t)col_word;
             const unsigned long long *vl0 = p.xval[me] + 2 * ((size_t)parp * p.xstride + (size_t)j_col);
 #pragma unroll
@@ -707,6 +720,9 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
                 }
               }
             }
+            mbar_wait(&sm.c_bar[t & 1], c_par, p.abort_flag, p.timeout_cycles);
+            const double c_prev = *(volatile double *)&sm.c_val[t & 1];
+            const bool add_c = (c_prev != 0.0) && (fabs(c_prev) > kEps);
             if (col_act) {
               FetchLL sp{LWprev, gtag, p.abort_flag, p.timeout_cycles};
               if (!got_w) sp.spin(LWprev + 2 * (size_t)j_col, wn);
@@ -737,7 +753,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
                   wn = filt(wn - step);
                 }
                 ll_store(LWcur + 2 * (size_t)j_col, wn, wtag);
-                pd = filt(wn * __ldg(&p.d[j_col]));
+                pd = filt(wn * dj);
                 pn = wn * wn;
               }
               Gzero[j_col] = 0.0;
@@ -746,54 +762,14 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
         }
       }
       if (warp == 0) DSGD_TL(12);
-      if (!first) {
-        pd = warp_sum(pd);
-        pn = warp_sum(pn);
-        if (lane == 0) {
-          sm.red[warp][0] = pd;
-          sm.red[warp][1] = pn;
-          mbar_arrive(&sm.u_bar);
-        }
-      }
-      if (warp == kCons) {
-        // ---- c_T, ||W_T||^2 for the NEXT interval, off the consumers' critical path ----
-        double c_new, nrm_new;
-        if (first) {
-          c_new = p.scal[kScalC];                             // W_base came from the host: k_prepare / previous launch
-          nrm_new = p.scal[kScalNrm2];
-        } else {
-          mbar_wait(&sm.u_bar, (unsigned)((t - 1) & 1), p.abort_flag, p.timeout_cycles);
-          if (lane == 0) {
-            double sd = 0.0, sn = 0.0;
-#pragma unroll
-            for (int i = 0; i < kCons + kUpd; ++i) { sd += sm.red[i][0]; sn += sm.red[i][1]; }   // warps in index order
-            part_cur[2 * blockIdx.x] = sd;
-            part_cur[2 * blockIdx.x + 1] = sn;
-            red_release_gpu_add(p.bar + 2, 1u);
-            if (!poll_counter(p.bar + 2, (unsigned)t * (unsigned)G, p.abort_flag, p.timeout_cycles)) ok = false;
-            fence_acq_rel_gpu();
-          }
-          __syncwarp();
-          double sd, sn;
-          sum_partials2(part_cur, G, lane, sd, sn);
-          c_new = p.lambda * 2.0 * sd;
-          nrm_new = sn;
-        }
-        if (lane == 0) {
-          sm.c_val[(t + 1) & 1] = c_new;
-          sm.nrm_val[(t + 1) & 1] = nrm_new;
-          mbar_arrive(&sm.c_bar[(t + 1) & 1]);
-          if (last && blockIdx.x == 0) { p.scal[kScalC] = c_new; p.scal[kScalNrm2] = nrm_new; }
-        }
-        DSGD_TL(9);
-      }
       if (is_cons && !last) {
         const int st = (int)(t % kStages);
         auto &mt = sm.meta[st];
         mbar_wait(&sm.full[st], (unsigned)((t / kStages) & 1), p.abort_flag, p.timeout_cycles);
         if (warp == 0) DSGD_TL(1);
         FetchLL fetch{LWcur, wtag, p.abort_flag, p.timeout_cycles};
-        const unsigned hinge = consume_stage<kCons, kMaxChunks, kOnePass>(mt, &sm.ring[st][0], p.pairs, Gcur, fetch, warp, lane);
+        const unsigned hinge = consume_stage<kCons, kMaxChunks, kOnePass>(mt, &sm.ring[st][0], p.pairs, Gcur, fetch, warp, lane,
+                                                                          warp == 0 ? tl_row : nullptr);
         ok = ok && fetch.good;
         if (lane == 0 && hinge) atomicAdd(&sm.hinge_acc, hinge);
         if (tl_rec && warp == 0 && lane == 0) tl_rec[2] = mt.n_pairs;
@@ -814,7 +790,8 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
           mbar_wait(&sm.full[st], (unsigned)((t / kStages) & 1), p.abort_flag, p.timeout_cycles);
           if (warp == 0) DSGD_TL(1);
           FetchLocal fetch{Wprev, Gprev, &sm.c_bar[t & 1], c_par, &sm.c_val[t & 1], p.abort_flag, p.timeout_cycles, p.k_den, lr};
-          const unsigned hinge = consume_stage<kCons, kMaxChunks, kOnePass>(mt, &sm.ring[st][0], p.pairs, Gcur, fetch, warp, lane);
+          const unsigned hinge = consume_stage<kCons, kMaxChunks, kOnePass>(mt, &sm.ring[st][0], p.pairs, Gcur, fetch, warp, lane,
+                                                                            warp == 0 ? tl_row : nullptr);
           if (lane == 0 && hinge) atomicAdd(&sm.hinge_acc, hinge);
           if (tl_rec && warp == 0 && lane == 0) tl_rec[2] = mt.n_pairs;
           __syncwarp();
@@ -822,77 +799,85 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
           if (warp == 0) DSGD_TL(3);
         }
       } else {
-        const int uw = warp - kCons;
-        mbar_wait(&sm.c_bar[t & 1], c_par, p.abort_flag, p.timeout_cycles);   // c_{t-1}: completed during interval t-1
+        // ---- update warps: W_t <- update(W_{t-1}, g_{t-1}, c_{t-1}) over this thread's columns (two per thread on a
+        //      B200: both requested before c is waited for) ----
+        constexpr int kCols = 2;
+        double wv[kCols], gv[kCols], dv[kCols];
+#pragma unroll
+        for (int i = 0; i < kCols; ++i) {
+          const int j = u0 + i * n_upd;
+          wv[i] = gv[i] = dv[i] = 0.0;
+          if (j < p.dim) { wv[i] = __ldcg(&Wprev[j]); gv[i] = __ldcg(&Gprev[j]); dv[i] = __ldg(&p.d[j]); }
+        }
+        mbar_wait(&sm.c_bar[t & 1], c_par, p.abort_flag, p.timeout_cycles);
         const double c_prev = *(volatile double *)&sm.c_val[t & 1];
         const bool add_c = (c_prev != 0.0) && (fabs(c_prev) > kEps);
-        // loss of step t-1 = lambda*||W_{t-1}||^2 + hinge_{t-1}/batch  (SparseSVM.scala:20-23)
-        if (uw == 0 && t > 0 && p.losses && blockIdx.x == 0 && lane == 0)
-          p.losses[t - 1] = p.lambda * nrm_carry + (double)__ldcg(&p.hinge[t - 1]) / (double)B;
-        double pd = 0.0, pn = 0.0;
-        for (int j = u0; j < p.dim; j += n_upd) {
+#pragma unroll
+        for (int i = 0; i < kCols; ++i) {
+          const int j = u0 + i * n_upd;
+          if (j < p.dim) {
+            const double wn = apply_update(wv[i], gv[i], c_prev, add_c, p.k_den, lr);
+            Wcur[j] = wn;
+            Gzero[j] = 0.0;
+            pd += filt(wn * dv[i]);
+            pn += wn * wn;
+          }
+        }
+        for (int j = u0 + kCols * n_upd; j < p.dim; j += n_upd) {   // more columns than 2 * update threads
           const double wn = apply_update(__ldcg(&Wprev[j]), __ldcg(&Gprev[j]), c_prev, add_c, p.k_den, lr);
           Wcur[j] = wn;
           Gzero[j] = 0.0;
           pd += filt(wn * __ldg(&p.d[j]));
           pn += wn * wn;
         }
-        pd = warp_sum(pd);
-        pn = warp_sum(pn);
-        if (lane == 0) { sm.red[uw][0] = pd; sm.red[uw][1] = pn; }
-        named_bar_sync(1, kUpd * 32);
-        if (uw == 0) {
-          DSGD_TL(10);
-          // ---- the update warps' own barrier: c_t, ||W_t||^2 for the NEXT interval ----
-          if (lane == 0) {
-            double sd = 0.0, sn = 0.0;
-#pragma unroll
-            for (int i = 0; i < kUpd; ++i) { sd += sm.red[i][0]; sn += sm.red[i][1]; }
-            part_cur[2 * blockIdx.x] = sd;
-            part_cur[2 * blockIdx.x + 1] = sn;
-            red_release_gpu_add(p.bar + 2, 1u);
-            if (!poll_counter(p.bar + 2, (unsigned)(t + 1) * (unsigned)G, p.abort_flag, p.timeout_cycles)) ok = false;
-            fence_acq_rel_gpu();
-          }
-          __syncwarp();
-          double sd, sn;
-          sum_partials2(part_cur, G, lane, sd, sn);
-          nrm_carry = sn;
-          if (lane == 0) {
-            sm.c_val[(t + 1) & 1] = p.lambda * 2.0 * sd;
-            mbar_arrive(&sm.c_bar[(t + 1) & 1]);
-            if (last && blockIdx.x == 0) { p.scal[kScalC] = p.lambda * 2.0 * sd; p.scal[kScalNrm2] = sn; }
-          }
-          DSGD_TL(9);
-        }
+        if (warp == kCons) DSGD_TL(10);
       }
     }
 
+    // ---- grid barrier T: the CTA's partial {W_T . d, ||W_T||^2} and hinge total ride on it ----
+    pd = warp_sum(pd);
+    pn = warp_sum(pn);
+    if (lane == 0) { sm.red[warp][0] = pd; sm.red[warp][1] = pn; }
     if (!ok) *(volatile int *)&sm.ok = 0;
-    // ---- grid barrier T (the CTA's hinge total rides in front of the arrival) ----
     named_bar_sync(3, kSyncThreads);
-    if (*(volatile int *)&sm.ok == 0) *(volatile int *)p.abort_flag = 1;
-    if (threadIdx.x == 0 && !last) {
-      const unsigned h = sm.hinge_acc;
-      if constexpr (kMulti) {
-        if (h) { red_add_f64(&Gcur[p.dim], (double)h); sm.hinge_acc = 0u; }
-        if (blockIdx.x == 0) red_add_f64(&Gcur[p.dim], (double)B * 4294967296.0);
-      } else {
-        if (h) { atomicAdd(&p.hinge[t], h); sm.hinge_acc = 0u; }
+    ++phase;
+    if (warp == kCons) {
+      double sd = 0.0, sn = 0.0;
+#pragma unroll
+      for (int i = 0; i < kCons + kUpd; ++i) { sd += sm.red[i][0]; sn += sm.red[i][1]; }   // warps in index order
+      if (lane == 0) {
+        if (!last) {   // the CTA's hinge total (and, K GPUs, the step's sample count) ahead of the arrival
+          const unsigned h = sm.hinge_acc;
+          if constexpr (kMulti) {
+            if (h) red_add_f64(&Gcur[p.dim], (double)h);
+            if (blockIdx.x == 0) red_add_f64(&Gcur[p.dim], (double)B * 4294967296.0);
+          } else {
+            if (h) atomicAdd(&p.hinge[t], h);
+          }
+          sm.hinge_acc = 0u;
+        }
+        if (tl_rec) tl_rec[0] = global_ns();
+        else if (tl_row) tl_row[6] = clock64();
+      }
+      __syncwarp();   // lane 0's reductions above happen-before every lane's fence in the barrier
+      bool bar_ok = grid_barrier_warp(p.flags, parts_cur, phase, G, lane, sd, sn, p.abort_flag, p.timeout_cycles);
+      if (*(volatile int *)&sm.ok == 0) { *(volatile int *)p.abort_flag = 1; bar_ok = false; }
+      if (lane == 0) {
+        sm.ok = bar_ok ? 1 : 0;
+        if (tl_rec) tl_rec[1] = global_ns();
+        else if (tl_row) tl_row[7] = clock64();
       }
     }
-    ++phase;
-    long long *tl_slot = nullptr;
-    bool tl_ns = false;
-    if (tl_rec) { tl_slot = tl_rec; tl_ns = true; }
-    else if (p.tl && blockIdx.x == 0 && t < 256) tl_slot = p.tl + t * 16 + 6;
-    if (!grid_barrier<kFlagBar>(p.bar, p.bar_flags, phase, (unsigned)G, p.abort_flag, p.timeout_cycles, &sm.ok, kSyncThreads,
-                                tl_slot, tl_ns))
-      return;
-    if (*(volatile int *)p.abort_flag) return;
+    named_bar_sync(3, kSyncThreads);
+    if (*(volatile int *)&sm.ok == 0) return;
   }
 
   // ---- epilogue: publish W_{base+S} as the resident weights ----------------------------------------------------
+  if (blockIdx.x == 0 && warp == kCons && S > 0) {
+    double sd, sn;
+    sum_parts(p.parts + (size_t)(S & 1) * kBarStride * kBarStride, G, lane, sd, sn);   // delivered by the last barrier
+    if (lane == 0) { p.scal[kScalC] = p.lambda * 2.0 * sd; p.scal[kScalNrm2] = sn; }
+  }
   if constexpr (kMulti) {
     const unsigned long long *LW = p.llw[(base + S) & 1];
     const unsigned wtag = (unsigned)(base + S + 1);

@@ -12,12 +12,18 @@
 //     evaluation pass make every warp load one contiguous 512-byte request.
 //   * The dot is needed for its SIGN only (prediction, gate: SparseSVM.scala:14,28), so it is accumulated with fp32
 //     FMAs against the fp32 weights -- no fp32->fp64 conversions (ncu, round 1: the XU pipe they run on was 46 %
-//     busy).  A lane accumulates its units of the open row; the warp reduces once per ROW END, not per load.
+//     busy).  A lane accumulates its units of the open row; the warp reduces once per ROW END (one 5-step butterfly
+//     of ONE float), not per load, and the row's lane just keeps the sum: predictions, counters and gates of the 32
+//     rows are worked out by 32 lanes in parallel after the block's stream.  The kernel is ISSUE-bound before it is
+//     HBM-bound (ncu, round 2 first cut: 108 warp instructions per 64 pairs = 131 us per pass; this form: see
+//     profiles/), so every per-slot instruction counts: no bounds predicates except in a block's last group, row ends
+//     located once per 4 slots.
 //   * Exactness against the fp64 arithmetic of the reference: the fp32 result differs from x.w by at most
 //       (D + 1) * 2^-24 * max|w| * sum|x|,   D = units/32 + 9 roundings on the longest add chain, + 1 for rounding w
-//     (first-order bound, 1.5x slack).  Rows whose |dot| is inside that band are recomputed with the fp64 weights
-//     from L2 after the block's stream, so every prediction and gate decision is that of the fp64 arithmetic
-//     (tests/test_gpu_parity.py::test_streaming_exact_fallback_decides_like_fp64).
+//     (first-order bound, 1.5x slack); sum|x| per row is computed once when the rows are loaded (k_repack, rounded
+//     up, stored with the label in its sign bit: one 4-byte load per row).  Rows whose |dot| is inside that band are
+//     recomputed with the fp64 weights from L2 after the block's stream, so every prediction and gate decision is
+//     that of the fp64 arithmetic (tests/test_gpu_parity.py::test_streaming_exact_fallback_decides_like_fp64).
 //   * Scatter (gradient): rows that pass the gate are re-walked after the block's stream (their units are in
 //     L1/L2) and y*x goes to g with fp64 REDs.  kHot: the kHotSlots most frequent columns get a per-CTA exact
 //     fixed-point accumulator in the shared memory left beside the weights (three 32-bit limbs of g * 2^40; shared
@@ -39,7 +45,7 @@ constexpr int64_t kHotMaxRows = 1 << 18;   // limb headroom: 2^18 adds of < 2^14
 struct StreamParams {
   const uint32_t *rp16;
   const uint4 *units;      // the pair array viewed as 16-byte units (2 pairs)
-  const int8_t *label;
+  const float *yabs;       // per row: label * sum_j |x_j| (rounded up); the sign bit is the label
   const int32_t *samples;  // nullptr: rows [row_begin, row_begin + n)
   int64_t row_begin, n;
   const double *w;         // fp64 weights (exact fallback, L2)
@@ -143,14 +149,15 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
   unsigned hinge = 0, correct = 0, n_exact = 0;
 
   // bounds of the block being processed / the next one: lane l holds row l of the block
-  auto load_block = [&](int64_t blk, uint32_t &b, uint32_t &e, int &y) {
+  auto load_block = [&](int64_t blk, uint32_t &b, uint32_t &e, float &ya, bool &valid) {
     const int64_t i = (blk << 5) + lane;
-    b = 0u; e = 0u; y = 0;   // y == 0: no such row
-    if (blk < n_blocks && i < p.n) {
+    b = 0u; e = 0u; ya = 0.f;
+    valid = blk < n_blocks && i < p.n;
+    if (valid) {
       const int64_t rid = p.samples ? (int64_t)__ldg(&p.samples[i]) : p.row_begin + i;
       b = __ldg(&p.rp16[rid]);
       e = __ldg(&p.rp16[rid + 1]);
-      y = (int)__ldg(&p.label[rid]);
+      ya = __ldg(&p.yabs[rid]);
     }
   };
   // Work distribution: the first wave is static (block = warp id), later blocks are claimed from a global counter
@@ -160,32 +167,37 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
     if (lane == 0) v = atomicAdd(p.next_block, 1ull);
     return (int64_t)__shfl_sync(0xffffffffu, v, 0) + n_warps;
   };
-  uint32_t nb, ne; int ny;
+  uint32_t nb, ne; float nya; bool nvalid;
   int64_t blk = warp_global;
   int64_t blk_next = (blk < n_blocks) ? claim() : n_blocks;
-  load_block(blk, nb, ne, ny);
+  load_block(blk, nb, ne, nya, nvalid);
   for (; blk < n_blocks;) {
     uint32_t b = nb;
     int len = (int)(ne - nb);   // units
-    int y = ny;
-    load_block(blk_next, nb, ne, ny);
+    float ya = nya;
+    bool valid = nvalid;
+    load_block(blk_next, nb, ne, nya, nvalid);
     int opos = lane;            // position of this lane's row inside the block (before compaction)
     // empty rows: dot 0 -> prediction 0, hinge 1, never correct, nothing to scatter (SparseSVM.scala:14-16)
-    if (y != 0 && len == 0) {
+    if (valid && len == 0) {
       hinge += 1u;
       if (kPreds) p.preds[(blk << 5) + lane] = 0.0;
     }
-    const unsigned ne_mask = __ballot_sync(0xffffffffu, y != 0 && len > 0);
+    const unsigned ne_mask = __ballot_sync(0xffffffffu, valid && len > 0);
     if (ne_mask != 0xffffffffu) {   // compact the non-empty rows to lanes 0 .. n-1 (order kept)
       const unsigned src = __fns(ne_mask, 0, lane + 1);
       const bool has = src < 32u;
       const int sl = has ? (int)src : 0;
       b = __shfl_sync(0xffffffffu, b, sl);
       len = __shfl_sync(0xffffffffu, len, sl);
-      y = __shfl_sync(0xffffffffu, y, sl);
+      ya = __shfl_sync(0xffffffffu, ya, sl);
       opos = sl;
-      if (!has) { len = 0; y = 0; }
+      valid = has;
+      if (!has) len = 0;
+    } else {
+      valid = true;
     }
+    const int y = (__float_as_uint(ya) >> 31) ? -1 : 1;
     // P = inclusive prefix sum of the row lengths: row l covers virtual units [P - len, P)
     int P = len;
 #pragma unroll
@@ -195,7 +207,60 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
     }
     const int total = __shfl_sync(0xffffffffu, P, 31);
     const uint32_t base = b - (uint32_t)(P - len);   // unit address of virtual unit v of this row = base + v (mod 2^32)
-    float acc_p = 0.f, acc_a = 0.f;                   // this lane's share of the OPEN row: sum x*w, sum |x|
+    const int my_end = len > 0 ? P - 1 : -1;          // virtual position of this row's LAST unit
+    float acc_p = 0.f;                                // this lane's share of the OPEN row: sum x*w
+    float dot_mine = 0.f;                             // this lane's row: x.w in fp32 once the row is closed
+    int row0 = 0;                                     // rows closed so far (warp-uniform)
+
+    for (int v0 = 0; v0 < total; v0 += 32 * kStreamUnroll) {
+      uint4 q[kStreamUnroll];
+      unsigned ends[kStreamUnroll];   // bit j: a row's LAST unit sits at lane j of this slot
+      int rmy[kStreamUnroll];         // row of this lane's unit
+      {
+        // where this lane's row ends inside the group: one or-reduction per slot
+        const unsigned pos = (unsigned)(my_end - v0);          // < 128 iff the row ends in this group
+        const unsigned bit = 1u << (pos & 31u);
+        int r0 = row0;
+#pragma unroll
+        for (int i = 0; i < kStreamUnroll; ++i) {
+          ends[i] = __reduce_or_sync(0xffffffffu, (pos >> 5) == (unsigned)i ? bit : 0u);
+          rmy[i] = r0 + __popc(ends[i] & lt_mask);
+          r0 += __popc(ends[i]);
+        }
+      }
+      const bool full = v0 + 32 * kStreamUnroll <= total;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < kStreamUnroll; ++i) {
+          const uint32_t bs = __shfl_sync(0xffffffffu, base, rmy[i]);
+          q[i] = __ldg(&p.units[bs + (uint32_t)(v0 + 32 * i + lane)]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < kStreamUnroll; ++i) {
+          const uint32_t bs = __shfl_sync(0xffffffffu, base, rmy[i] & 31);
+          q[i] = make_uint4(0u, 0u, 0u, 0u);  // col 0, val +0.0f
+          if (v0 + 32 * i + lane < total) q[i] = __ldg(&p.units[bs + (uint32_t)(v0 + 32 * i + lane)]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kStreamUnroll; ++i) {
+        float pp = __fmaf_rn(__uint_as_float(q[i].w), ws[q[i].z], __uint_as_float(q[i].y) * ws[q[i].x]);
+        if (!full && !(v0 + 32 * i + lane < total)) pp = 0.f;   // a masked unit reads ws[0]: keep a NaN / inf weight out
+        unsigned m = ends[i];
+        while (m) {   // warp-uniform: close the rows that end inside this slot, in order
+          m &= m - 1u;
+          float sp = acc_p + (rmy[i] == row0 ? pp : 0.f);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sp += __shfl_xor_sync(0xffffffffu, sp, o);
+          if (lane == row0) dot_mine = sp;
+          acc_p = 0.f;
+          ++row0;
+        }
+        acc_p += (rmy[i] == row0) ? pp : 0.f;
+      }
+    }
+    // ---- 32 rows decided by 32 lanes: inside the rounding band -> exact recomputation; else the sign is certain ----
     bool need_exact = false, do_scatter = false;
     int pred_mine = 0;
     // prediction known for this lane's row: counters and the gate (y * dot < 0  <=>  pred == y)
@@ -205,53 +270,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
       correct += (unsigned)(pr == y);
       do_scatter = kScatter && (pr != y);
     };
-
-    for (int v0 = 0; v0 < total; v0 += 32 * kStreamUnroll) {
-      uint4 q[kStreamUnroll];
-      unsigned ends[kStreamUnroll];   // bit j: a row's LAST unit sits at lane j of this slot
-      int rlo[kStreamUnroll];         // row of the slot's first unit
-      int rmy[kStreamUnroll];         // row of this lane's unit
-#pragma unroll
-      for (int i = 0; i < kStreamUnroll; ++i) {
-        const int vs = v0 + 32 * i;
-        rlo[i] = __popc(__ballot_sync(0xffffffffu, P <= vs));
-        const unsigned d = (unsigned)(P - vs - 1);
-        ends[i] = __reduce_or_sync(0xffffffffu, (len > 0 && d < 32u) ? (1u << d) : 0u);
-        rmy[i] = rlo[i] + __popc(ends[i] & lt_mask);
-        const uint32_t bs = __shfl_sync(0xffffffffu, base, rmy[i] & 31);
-        q[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (vs + lane < total) q[i] = __ldg(&p.units[bs + (uint32_t)(vs + lane)]);
-      }
-#pragma unroll
-      for (int i = 0; i < kStreamUnroll; ++i) {
-        const float x0 = __uint_as_float(q[i].y), x1 = __uint_as_float(q[i].w);
-        float pp = 0.f;
-        if (v0 + 32 * i + lane < total) pp = __fmaf_rn(x1, ws[q[i].z], x0 * ws[q[i].x]);
-        const float aa = fabsf(x0) + fabsf(x1);
-        unsigned m = ends[i];
-        int k = rlo[i];
-        while (m) {   // warp-uniform: close the rows that end inside this slot, in order
-          m &= m - 1u;
-          const bool sel = (rmy[i] == k);
-          float sp = acc_p + (sel ? pp : 0.f), sa = acc_a + (sel ? aa : 0.f);
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            sp += __shfl_xor_sync(0xffffffffu, sp, o);
-            sa += __shfl_xor_sync(0xffffffffu, sa, o);
-          }
-          if (lane == k) {
-            const float thresh = band_scale * sa * (float)((len >> 5) + 10) + 1e-30f;
-            if (!(fabsf(sp) > thresh)) need_exact = true;   // also catches NaN
-            else finalize(sp > 0.f ? -1 : 1);
-          }
-          acc_p = 0.f;
-          acc_a = 0.f;
-          ++k;
-        }
-        const bool sel = (rmy[i] == k);
-        acc_p += sel ? pp : 0.f;
-        acc_a += sel ? aa : 0.f;
-      }
+    if (valid) {
+      const float thresh = band_scale * fabsf(ya) * (float)((len >> 5) + 10) + 1e-30f;
+      if (!(fabsf(dot_mine) > thresh)) need_exact = true;   // also catches NaN
+      else finalize(dot_mine > 0.f ? -1 : 1);
     }
     // ---- exact recomputation of the rows the fp32 sign could not decide ----
     unsigned ex = __ballot_sync(0xffffffffu, need_exact);
@@ -273,7 +295,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
       }
     }
     if (kPreds) {
-      if (y != 0) p.preds[(blk << 5) + opos] = (double)pred_mine;
+      if (valid) p.preds[(blk << 5) + opos] = (double)pred_mine;
     }
     // ---- scatter y*x of the rows that passed the gate (SparseSVM.scala:28) ----
     if (kScatter) {

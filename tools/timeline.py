@@ -9,9 +9,10 @@ sys.path.insert(0, ROOT)
 import numpy as np
 
 NAMES = {0: "interval start (consumer warp 0)", 11: "K GPUs: push of g_{T-1} issued", 12: "K GPUs: column updated, W_T word published",
-         1: "stage full (TMA landed)", 3: "rows done (scatter issued)", 6: "CTA synced, arriving at grid barrier",
-         7: "grid barrier passed", 8: "interval start (update warp 0)", 10: "update slice + partial published",
-         9: "c_t summed (update warps' barrier passed)"}
+         1: "stage full (TMA landed)", 2: "first chunk: weights gathered, products done", 4: "first chunk: dot reduced",
+         3: "rows done (scatter issued)", 6: "CTA synced, arriving at grid barrier",
+         7: "grid barrier passed", 10: "update warp 0: its columns updated",
+         9: "c_{t-1} summed from the barrier's partials, handed over"}
 
 
 def report(tl_all, B, ms, S, world):
@@ -66,7 +67,10 @@ def run(rank, world, port, B):
         ctx.sync_steps_staged(0, B, S, 0.5, want_losses=True)
         ms = ctx.timer_stop()
     if rank == 0:
-        report(ctx.debug_timeline(), B, ms, S, world)
+        tl = ctx.debug_timeline()
+        report(tl, B, ms, S, world)
+        if os.environ.get("TIMELINE_DUMP"):
+            np.save(os.environ["TIMELINE_DUMP"], tl)
         if world > 1:
             v, b, n = ctx.xchg_stats()
             print(f"  pushed per peer and step: {v / max(n, 1):.0f} value words (16 B) + {b / max(n, 1):.0f} bitmap words (8 B) "
