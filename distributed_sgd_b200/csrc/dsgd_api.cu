@@ -71,12 +71,10 @@ struct dsgd_ctx {
   // persistent sync kernel resources (allocated on first use)
   double *p_wbuf[2] = {nullptr, nullptr};
   double *p_gbuf[3] = {nullptr, nullptr, nullptr};
-  double2 *p_parts = nullptr;       // grid barrier: partials rows [2][kBarStride][kBarStride]
-  unsigned *p_flags = nullptr;      //               flag rows [kBarStride][kBarStride]
-  unsigned bar_epoch = 0;           // barrier phases used so far (flags are monotone across launches)
+  unsigned long long *p_acc = nullptr;   // fixed-point accumulators of the per-CTA partials [3][kAccSets][8]
   unsigned *p_hinge = nullptr;
   int64_t p_hinge_cap = 0;
-  unsigned *p_bar = nullptr;   // [1]: abort flag
+  unsigned *p_bar = nullptr;   // [0]: grid barrier counter, [1]: abort flag
   uint32_t *hot_bits = nullptr;     // hot-column bitmap / slot prefix / slot -> column of the streaming scatter (dsgd_stream.cuh)
   uint16_t *hot_prefix = nullptr;
   int32_t *hot_cols = nullptr;
@@ -287,7 +285,7 @@ extern "C" int dsgd_destroy(dsgd_ctx *ctx) {
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   void *ptrs[] = {ctx->rp16, ctx->pairs, ctx->label, ctx->yabs, ctx->w, ctx->g, ctx->d, ctx->w_req, ctx->w32, ctx->w32_req, ctx->n_exact, ctx->scal,
                   ctx->cnt, ctx->partial, ctx->out2, ctx->gsum, ctx->p_wbuf[0], ctx->p_wbuf[1], ctx->p_gbuf[0],
-                  ctx->p_gbuf[1], ctx->p_gbuf[2], ctx->p_parts, ctx->p_flags, ctx->p_hinge, ctx->p_bar, ctx->x_stats, ctx->hot_bits, ctx->hot_prefix, ctx->hot_cols, ctx->samples,
+                  ctx->p_gbuf[1], ctx->p_gbuf[2], ctx->p_acc, ctx->p_hinge, ctx->p_bar, ctx->x_stats, ctx->hot_bits, ctx->hot_prefix, ctx->hot_cols, ctx->samples,
                   ctx->losses, ctx->preds};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -852,10 +850,7 @@ static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
       CU(cudaMalloc(&ctx->p_gbuf[i], vd));
       CU(cudaMemsetAsync(ctx->p_gbuf[i], 0, vd, ctx->stream));
     }
-    CU(cudaMalloc(&ctx->p_parts, sizeof(double2) * 2 * (size_t)kBarStride * kBarStride));
-    CU(cudaMemsetAsync(ctx->p_parts, 0, sizeof(double2) * 2 * (size_t)kBarStride * kBarStride, ctx->stream));
-    CU(cudaMalloc(&ctx->p_flags, sizeof(unsigned) * (size_t)kBarStride * kBarStride));
-    CU(cudaMemsetAsync(ctx->p_flags, 0, sizeof(unsigned) * (size_t)kBarStride * kBarStride, ctx->stream));
+    CU(cudaMalloc(&ctx->p_acc, sizeof(unsigned long long) * 3 * kAccSets * 8));
     CU(cudaMalloc(&ctx->p_bar, sizeof(unsigned) * 4));
     for (int opt = 0; opt < 4; ++opt) {
       CU(cudaFuncSetAttribute((const void *)persist_variant<false>(opt), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
@@ -899,19 +894,16 @@ static cudaError_t persist_launch(dsgd_ctx *ctx, void *fn, int G, void **args) {
 // fields shared by the one-GPU and the K-GPU launch
 static int persist_params(dsgd_ctx *ctx, PersistParams &pp, const int32_t *samples_dev, int64_t n_per_step, int64_t n_steps,
                           double lr, double *losses_dev, int G) {
-  NEED(G <= kBarStride, DSGD_ERR_INVALID, "more CTAs (%d) than rows in the barrier's flag table (%d)", G, kBarStride);
+  (void)G;
   memset(&pp, 0, sizeof pp);
   pp.rp16 = ctx->rp16; pp.pairs = ctx->pairs; pp.label = ctx->label; pp.samples = samples_dev;
   pp.n_steps = n_steps; pp.batch = (int32_t)n_per_step; pp.dim = ctx->dim;
   pp.wbuf[0] = ctx->p_wbuf[0]; pp.wbuf[1] = ctx->p_wbuf[1];
   for (int i = 0; i < 3; ++i) pp.gbuf[i] = ctx->p_gbuf[i];
-  pp.d = ctx->d; pp.parts = ctx->p_parts; pp.flags = ctx->p_flags; pp.hinge = ctx->p_hinge; pp.losses = losses_dev;
+  pp.d = ctx->d; pp.acc = ctx->p_acc; pp.bar = ctx->p_bar; pp.hinge = ctx->p_hinge; pp.losses = losses_dev;
   pp.w_out = ctx->w; pp.w32_out = ctx->w32; pp.scal = ctx->scal;
   pp.abort_flag = reinterpret_cast<int *>(ctx->p_bar + 1);
-  // flags hold step numbers that only grow: this launch uses phases bar_epoch + 1 .. bar_epoch + n_steps + 1 (an aborted
-  // launch leaves smaller numbers behind, which the next launch never waits for)
-  pp.phase_base = ctx->bar_epoch;
-  ctx->bar_epoch += (unsigned)(n_steps + 2);
+  CU(cudaMemsetAsync(ctx->p_acc, 0, sizeof(unsigned long long) * 3 * kAccSets * 8, ctx->stream));
   pp.lambda = ctx->lambda; pp.lr = lr; pp.world = 1;
   CU(cudaMemsetAsync(ctx->p_hinge, 0, sizeof(unsigned) * (size_t)n_steps, ctx->stream));
   CU(cudaMemsetAsync(ctx->p_bar, 0, sizeof(unsigned) * 4, ctx->stream));

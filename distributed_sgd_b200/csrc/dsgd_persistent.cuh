@@ -15,17 +15,18 @@
 //     gate, RED of y*x into g.  Longer rows: partial dots per chunk (fixed order), then gate + scatter per chunk.
 //   * UPDATE warps: weights are double-buffered and gradients triple-buffered in L2 so the update of step
 //     t-1 and the gradient of step t share one barrier interval.
-//   * GRID BARRIER = all-to-all flags.  A counter barrier (148 arrivals and 148 pollers on one L2 line) measured 2 500
-//     cycles from the last arrival to the first exit on a B200 (profiles/r2_timeline.md).  Here every CTA owns a row of
-//     148 flag words; an arriving CTA fences once and stores the step number into its word of EVERY row (148 posted
-//     stores from one warp), then polls only its own row (five 128-byte lines, nobody else reads them).  Next to the flag
-//     it has already stored its partial {W.d, ||W||^2} into every CTA's private partials row, so
-//   * c_t = 2*lambda*(W_t . d) (SparseSVM.scala:31), a dot over the whole weight vector that the next interval needs,
-//     costs no second barrier and no shared hot line: after the barrier each CTA's update warp 0 reads ITS 148 partials
-//     (one L2 round trip, overlapped with the consumers' first gathers) and sums them in a fixed order -- the same values
-//     in the same order in every CTA, so all CTAs (and all GPUs) hold bit-identical c.  (Round 1 read one shared 2.4 KB
-//     area from 148 CTAs at once: c arrived 1 880 cycles into the interval.  Round 2's first attempt gave the update
-//     warps a second counter barrier: two serialised barriers per step, slower -- profiles/r2_timeline.md.)
+//   * c_t = 2*lambda*(W_t . d) (SparseSVM.scala:31) is a dot over the whole weight vector that the NEXT interval needs
+//     first thing, and it must be the same bits in every CTA and on every GPU.  Each CTA adds its partial {W.d, ||W||^2}
+//     to a small EXACT fixed-point accumulator (three 40-bit limbs per value, 64-bit integer REDs, striped over 8 copies)
+//     before it arrives at the grid barrier: integer sums do not depend on the order of arrival, so there is nothing to
+//     sort out afterwards -- update warp 0 of every CTA reads the 512 bytes after the barrier (one L2 round trip,
+//     overlapped with the consumers' first gathers) and has c.  Measured history (profiles/r2_timeline.md): round 1 summed
+//     148 fp64 partials from one shared area after the barrier, c arrived 1 880 cycles into the interval; a second counter
+//     barrier among the update warps serialised with the grid barrier (+2 200 cycles per step); an all-to-all flag barrier
+//     carrying the partials took 5 100 cycles from the last arrival to the first exit against 2 450 for the counter.
+//   * GRID BARRIER: one release arrival on a counter, relaxed polling, one acquire fence: 2 412 cycles for 148 CTAs on a
+//     B200 (tools/microbench.cu: 1 721 for 2 CTAs -- it is fences and L2 round trips, not contention; cooperative
+//     groups' grid.sync() 2 472; +1 300 with 448 REDs per CTA in flight).  It is the largest single item of a step.
 //
 // One GPU (kMulti == false), interval I_t between grid barrier t-1 and t, W_t = weights step t differentiates at:
 //   consumers: x.W_t with W_t[col] = update(W_{t-1}[col], g_{t-1}[col], c_{t-1}) applied on the fly; gate; RED into g_t
@@ -66,14 +67,13 @@ struct PersistParams {
   double *wbuf[2];  // one GPU: on entry wbuf[1] holds the initial weights; K GPUs: wbuf[0]
   double *gbuf[3];  // all zero on entry and on exit
   const double *d;
-  double2 *parts;   // [2 parities][kBarStride dest][kBarStride src]: {W.d, ||W||^2} partial of CTA src, one copy per dest
+  unsigned long long *acc;  // [3 rotating][kAccSets][8]: fixed-point accumulators of {W.d, ||W||^2}; zero on entry
   unsigned *hinge;  // [n_steps], zero on entry (one GPU)
   double *losses;   // [n_steps] or nullptr
   double *w_out;    // resident weights after the last step
   float *w32_out;
   double *scal;     // kScalC / kScalNrm2 of the resident weights
-  unsigned *flags;  // grid barrier: [kBarStride dest][kBarStride src] step numbers (monotone across launches)
-  unsigned phase_base;  // barrier phases of this launch are phase_base + 1 ...
+  unsigned *bar;    // grid barrier: arrival counter, zero on entry
   int *abort_flag;  // set to 1 if a wait hit the watchdog
   double lambda, lr, k_den;
   long long timeout_cycles;
@@ -200,61 +200,84 @@ __device__ __forceinline__ double apply_update(double wv, double graw, double c,
 }
 
 // ---- grid barrier among the barrier-synchronised warps of every CTA (the producer warp stays out) -------------------
-// flags[dest][src] / parts[parity][dest][src]: row `dest` is read by CTA dest only, column `src` written by CTA src only.
-constexpr int kBarStride = 160;   // >= CTAs (148 SMs on a B200), multiple of 32
-__device__ __forceinline__ void st_relaxed_gpu_f64x2(double2 *p, double a, double b) {
-  asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
-}
-__device__ __forceinline__ double2 ld_relaxed_gpu_f64x2(const double2 *p) {
-  double2 v;
-  asm volatile("ld.relaxed.gpu.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
-  return v;
-}
-// Called by ONE whole warp (update warp 0) of every CTA after the CTA-level bar.sync; (sd, sn) = this CTA's partial.
+// Called by thread 0 between two CTA-level bar.syncs: one release arrival, relaxed polling, one acquire fence.
 // Returns false if the watchdog fired.
-__device__ __forceinline__ bool grid_barrier_warp(unsigned *flags, double2 *parts_par, unsigned phase, int n_cta, int lane,
-                                                  double sd, double sn, int *abort_flag, long long timeout) {
-  const int me = blockIdx.x;
-  for (int dest = lane; dest < n_cta; dest += 32) st_relaxed_gpu_f64x2(parts_par + (size_t)dest * kBarStride + me, sd, sn);
-  fence_acq_rel_gpu();   // release: everything this CTA wrote (cumulative through the bar.sync) and the partials above
-  for (int dest = lane; dest < n_cta; dest += 32) st_relaxed_gpu(flags + (size_t)dest * kBarStride + me, phase);
-  const unsigned *mine = flags + (size_t)me * kBarStride;
+__device__ __forceinline__ bool grid_barrier_arrive_wait(unsigned *bar, unsigned target, int *abort_flag, long long timeout) {
+  red_release_gpu_add(bar, 1u);
   const long long t0 = clock64();
   unsigned spins = 0;
   bool ok = true;
-  for (;;) {
-    bool all = true;
-#pragma unroll
-    for (int k = 0; k < kBarStride / 32; ++k) {
-      const int src = lane + 32 * k;
-      if (src < n_cta) all = all && ((int)(ld_relaxed_gpu(mine + src) - phase) >= 0);
-    }
-    if (__all_sync(0xffffffffu, all)) break;
-    if ((++spins & 255u) == 0u && (clock64() - t0 > timeout || *(volatile int *)abort_flag)) {
+  while ((int)(ld_relaxed_gpu(bar) - target) < 0) {
+    if ((++spins & 1023u) == 0u && (clock64() - t0 > timeout || *(volatile int *)abort_flag)) {
       *(volatile int *)abort_flag = 1;
       ok = false;
       break;
     }
   }
-  fence_acq_rel_gpu();   // acquire
+  fence_acq_rel_gpu();
   return ok;
 }
-// The partials the barrier delivered to this CTA, summed in a fixed order (lane-strided, then a butterfly): the same
-// additions in every CTA of every GPU.  All lanes return the sums.
-__device__ __forceinline__ void sum_parts(const double2 *parts_par, int n_cta, int lane, double &s0, double &s1) {
-  const double2 *mine = parts_par + (size_t)blockIdx.x * kBarStride;
-  double2 v[kBarStride / 32];
-#pragma unroll
-  for (int k = 0; k < kBarStride / 32; ++k) {
-    const int src = lane + 32 * k;
-    v[k] = make_double2(0.0, 0.0);
-    if (src < n_cta) v[k] = ld_relaxed_gpu_f64x2(mine + src);
+
+// ---- order-free exact sums of the per-CTA partials -------------------------------------------------------------------
+// A double v with |v| < 2^52 is cut into three integers: |v| = l2 + l1 * 2^-40 + l0 * 2^-80, l1 and l0 in [0, 2^40] (l0
+// rounded: resolution 2^-80), every cut exact in fp64 arithmetic; negative v contribute the negated limbs.  The limbs of 148 CTAs are added with 64-bit integer REDs
+// (no overflow: 148 * 2^40 < 2^48) and converted back once.  Slot layout of one set (8 x u64): {sd.l0, sd.l1, sd.l2, sn.l0,
+// sn.l1, sn.l2, overflow count, pad}; kAccSets sets, CTA b adds to set b % kAccSets (same-address REDs serialise at
+// 2.7 cycles each, tools/microbench.cu).
+constexpr int kAccSets = 8;
+__device__ __forceinline__ void red_add_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void acc_push_one(unsigned long long *slot3, unsigned long long *ovf, double v) {
+  if (!(fabs(v) < 4503599627370496.0)) {   // 2^52; also NaN / inf: the sum is reported as NaN
+    red_add_u64(ovf, 1ull);
+    return;
   }
-  double a0 = 0.0, a1 = 0.0;
+  const double a = fabs(v);
+  const double f2 = floor(a);
+  const double r1 = (a - f2) * 1099511627776.0;        // exact: the fraction of a non-negative double, scaled by 2^40
+  const double f1 = floor(r1);
+  const double r0 = rint((r1 - f1) * 1099511627776.0);  // [0, 2^40]: the only rounding, at 2^-80
+  const bool neg = v < 0.0;                             // negative values add the negated limbs (two's complement wraps)
+  auto put = [&](unsigned long long *dst, double limb) {
+    if (limb != 0.0) {
+      const unsigned long long u = (unsigned long long)(long long)limb;
+      red_add_u64(dst, neg ? (0ull - u) : u);
+    }
+  };
+  put(slot3 + 0, r0);
+  put(slot3 + 1, f1);
+  put(slot3 + 2, f2);
+}
+__device__ __forceinline__ void acc_push(unsigned long long *acc, double sd, double sn) {
+  unsigned long long *set = acc + (size_t)(blockIdx.x % kAccSets) * 8;
+  acc_push_one(set + 0, set + 6, sd);
+  acc_push_one(set + 3, set + 6, sn);
+}
+// All lanes return the two sums (identical in every CTA: integer additions commute).
+__device__ __forceinline__ void acc_read(const unsigned long long *acc, int lane, double &sd, double &sn) {
+  long long l[7];
 #pragma unroll
-  for (int k = 0; k < kBarStride / 32; ++k) { a0 += v[k].x; a1 += v[k].y; }
-  s0 = warp_sum(a0);
-  s1 = warp_sum(a1);
+  for (int i = 0; i < 7; ++i) l[i] = 0;
+  if (lane < kAccSets) {
+    const ulonglong2 *set = reinterpret_cast<const ulonglong2 *>(acc + (size_t)lane * 8);
+    ulonglong2 q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(q[i].x), "=l"(q[i].y) : "l"(set + i) : "memory");
+    l[0] = (long long)q[0].x; l[1] = (long long)q[0].y; l[2] = (long long)q[1].x; l[3] = (long long)q[1].y;
+    l[4] = (long long)q[2].x; l[5] = (long long)q[2].y; l[6] = (long long)q[3].x;
+  }
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+#pragma unroll
+    for (int o = kAccSets / 2; o > 0; o >>= 1) l[i] += __shfl_xor_sync(0xffffffffu, l[i], o);
+    l[i] = __shfl_sync(0xffffffffu, l[i], 0);
+  }
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  sd = ((double)l[0] * 0x1p-80 + (double)l[1] * 0x1p-40) + (double)l[2];
+  sn = ((double)l[3] * 0x1p-80 + (double)l[4] * 0x1p-40) + (double)l[5];
+  if (l[6] != 0) { sd = nan; sn = nan; }
 }
 
 constexpr int kChunkPairs = 128;             // 4 pairs per lane per chunk
@@ -598,7 +621,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
   // =========================================================================================================
   const double lr = p.lr;
   const int64_t base = kMulti ? p.step_base : 0;
-  unsigned phase = p.phase_base;
+  unsigned phase = 0;
   // one GPU: the update threads of all CTAs stride over the columns
   const int n_upd = G * kUpd * 32;
   const int u0 = blockIdx.x * kUpd * 32 + ((int)threadIdx.x - kCons * 32);
@@ -617,8 +640,9 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
     const double *Gprev = p.gbuf[(T + 2) % 3];   // g_{T-1}
     double *Gcur = p.gbuf[T % 3];
     double *Gzero = p.gbuf[(T + 1) % 3];
-    const double2 *parts_prev = p.parts + (size_t)((t + 1) & 1) * kBarStride * kBarStride;   // delivered by barrier t-1
-    double2 *parts_cur = p.parts + (size_t)(t & 1) * kBarStride * kBarStride;                // pushed at barrier t
+    const unsigned long long *acc_prev = p.acc + (size_t)((t + 2) % 3) * kAccSets * 8;   // partials of W_{T-1}: complete at barrier t-1
+    unsigned long long *acc_cur = p.acc + (size_t)(t % 3) * kAccSets * 8;                // partials of W_T: added before barrier t
+    unsigned long long *acc_next = p.acc + (size_t)((t + 1) % 3) * kAccSets * 8;         // read during interval t-1: zeroed now
     const unsigned c_par = (unsigned)((t >> 1) & 1);
     const bool tl_cta = p.tl && t >= kTlFirst && t < kTlFirst + kTlSteps && blockIdx.x < kTlCtas;
     long long *tl_rec = tl_cta ? p.tl + 256 * 16 + ((t - kTlFirst) * kTlCtas + blockIdx.x) * kTlPerCta : nullptr;
@@ -634,10 +658,11 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
         nrm_prev = p.scal[kScalNrm2];
       } else {
         double sd, sn;
-        sum_parts(parts_prev, G, lane, sd, sn);
+        acc_read(acc_prev, lane, sd, sn);
         c_prev = p.lambda * 2.0 * sd;
         nrm_prev = sn;
       }
+      if (blockIdx.x == 0) { acc_next[lane] = 0ull; acc_next[lane + 32] = 0ull; }   // kAccSets * 8 == 64 words
       if (lane == 0) {
         sm.c_val[t & 1] = c_prev;
         sm.nrm_val[t & 1] = nrm_prev;
@@ -841,32 +866,28 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
     if (!ok) *(volatile int *)&sm.ok = 0;
     named_bar_sync(3, kSyncThreads);
     ++phase;
-    if (warp == kCons) {
+    if (threadIdx.x == 0) {
       double sd = 0.0, sn = 0.0;
 #pragma unroll
       for (int i = 0; i < kCons + kUpd; ++i) { sd += sm.red[i][0]; sn += sm.red[i][1]; }   // warps in index order
-      if (lane == 0) {
-        if (!last) {   // the CTA's hinge total (and, K GPUs, the step's sample count) ahead of the arrival
-          const unsigned h = sm.hinge_acc;
-          if constexpr (kMulti) {
-            if (h) red_add_f64(&Gcur[p.dim], (double)h);
-            if (blockIdx.x == 0) red_add_f64(&Gcur[p.dim], (double)B * 4294967296.0);
-          } else {
-            if (h) atomicAdd(&p.hinge[t], h);
-          }
-          sm.hinge_acc = 0u;
+      acc_push(acc_cur, sd, sn);
+      if (!last) {   // the CTA's hinge total (and, K GPUs, the step's sample count) ahead of the arrival
+        const unsigned h = sm.hinge_acc;
+        if constexpr (kMulti) {
+          if (h) red_add_f64(&Gcur[p.dim], (double)h);
+          if (blockIdx.x == 0) red_add_f64(&Gcur[p.dim], (double)B * 4294967296.0);
+        } else {
+          if (h) atomicAdd(&p.hinge[t], h);
         }
-        if (tl_rec) tl_rec[0] = global_ns();
-        else if (tl_row) tl_row[6] = clock64();
+        sm.hinge_acc = 0u;
       }
-      __syncwarp();   // lane 0's reductions above happen-before every lane's fence in the barrier
-      bool bar_ok = grid_barrier_warp(p.flags, parts_cur, phase, G, lane, sd, sn, p.abort_flag, p.timeout_cycles);
+      if (tl_rec) tl_rec[0] = global_ns();
+      else if (tl_row) tl_row[6] = clock64();
+      bool bar_ok = grid_barrier_arrive_wait(p.bar, phase * (unsigned)G, p.abort_flag, p.timeout_cycles);
       if (*(volatile int *)&sm.ok == 0) { *(volatile int *)p.abort_flag = 1; bar_ok = false; }
-      if (lane == 0) {
-        sm.ok = bar_ok ? 1 : 0;
-        if (tl_rec) tl_rec[1] = global_ns();
-        else if (tl_row) tl_row[7] = clock64();
-      }
+      sm.ok = bar_ok ? 1 : 0;
+      if (tl_rec) tl_rec[1] = global_ns();
+      else if (tl_row) tl_row[7] = clock64();
     }
     named_bar_sync(3, kSyncThreads);
     if (*(volatile int *)&sm.ok == 0) return;
@@ -875,7 +896,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
   // ---- epilogue: publish W_{base+S} as the resident weights ----------------------------------------------------
   if (blockIdx.x == 0 && warp == kCons && S > 0) {
     double sd, sn;
-    sum_parts(p.parts + (size_t)(S & 1) * kBarStride * kBarStride, G, lane, sd, sn);   // delivered by the last barrier
+    acc_read(p.acc + (size_t)(S % 3) * kAccSets * 8, lane, sd, sn);   // partials of W_S: complete at the last barrier
     if (lane == 0) { p.scal[kScalC] = p.lambda * 2.0 * sd; p.scal[kScalNrm2] = sn; }
   }
   if constexpr (kMulti) {

@@ -53,7 +53,8 @@ def scenario(cfg, data, *, rank: int = 0, world: int = 1, device: Optional[int] 
                            virtual_workers=cfg.node_count // world)
     report["fit_seconds"] = time.perf_counter() - t0                          # Measure.durationLog(log, "fit") (Main.scala:80)
     w1 = state.grad
-    report["history"] = {k: [float(x) for x in v] for k, v in getattr(master, "history", {}).items()}
+    report["history"] = {k: [float(x) for x in v] for k, v in getattr(master, "history", {}).items()
+                         if isinstance(v, list) and all(isinstance(x, (int, float)) for x in v)}
     report["final_test_loss"], report["final_test_accuracy"] = master.local_loss_accuracy(w1, test_data=True)  # :115-118
     report["final_weights_nonzero"] = int(np.count_nonzero(w1))
     report["updates"] = state.updates
