@@ -954,6 +954,13 @@ static int xblk_ensure(dsgd_ctx *ctx) {
   return DSGD_OK;
 }
 
+static int xllw_ensure(dsgd_ctx *ctx) {
+  if (ctx->x_llw) return DSGD_OK;
+  CU(cudaMalloc(&ctx->x_llw, 2 * 2 * sizeof(unsigned long long) * xblk_stride(ctx)));
+  CU(cudaMemsetAsync(ctx->x_llw, 0, 2 * 2 * sizeof(unsigned long long) * xblk_stride(ctx), ctx->stream));
+  return DSGD_OK;
+}
+
 static bool xchg_complete(const dsgd_ctx *ctx) {
   if (ctx->world <= 1 || ctx->world > kMaxWorld || !ctx->xblk) return false;
   for (int r = 0; r < ctx->world; ++r)
@@ -982,10 +989,7 @@ static int persist_run_multi(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t 
     pp.xval[r] = blk;
     pp.xbm[r] = blk + xblk_bm_offset(ctx);
   }
-  if (!ctx->x_llw) {
-    CU(cudaMalloc(&ctx->x_llw, 2 * 2 * sizeof(unsigned long long) * xblk_stride(ctx)));
-    CU(cudaMemsetAsync(ctx->x_llw, 0, 2 * 2 * sizeof(unsigned long long) * xblk_stride(ctx), ctx->stream));
-  }
+  if ((rc = xllw_ensure(ctx))) return rc;
   pp.llw[0] = ctx->x_llw;
   pp.llw[1] = ctx->x_llw + 2 * xblk_stride(ctx);
   pp.xstats = ctx->x_stats;
@@ -1001,6 +1005,23 @@ static int persist_run_multi(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t 
   // a slow peer is NOT reading in launch n's last interval (+3 put them on the same one: ADVICE.md round 1).
   ctx->x_step += n_steps + 6;
   ctx->x_steps_run += n_steps;
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_reserve(dsgd_ctx *ctx, int64_t n_samples, int64_t n_steps) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(n_samples >= 0 && n_steps >= 0, DSGD_ERR_INVALID, "dsgd_reserve: negative size");
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_i32(ctx, &ctx->samples, &ctx->samples_cap, n_samples);
+  if (rc) return rc;
+  if ((rc = ensure_f64(ctx, &ctx->losses, &ctx->losses_cap, n_steps))) return rc;
+  if ((rc = persist_prepare(ctx, n_steps))) return rc;
+  if (persist_timeline() && !ctx->p_tl) CU(cudaMalloc(&ctx->p_tl, sizeof(long long) * kTlWords));
+  if (ctx->world > 1 && !(ctx->flags & DSGD_FLAG_ASYNC)) {
+    if ((rc = xblk_ensure(ctx))) return rc;
+    if ((rc = xllw_ensure(ctx))) return rc;
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
   return DSGD_OK;
 }
 

@@ -160,16 +160,23 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
       ya = __ldg(&p.yabs[rid]);
     }
   };
-  // Work distribution: the first wave is static (block = warp id), later blocks are claimed from a global counter
-  // one step ahead (so the next block's bounds are prefetched while the current one is processed).
-  auto claim = [&]() -> int64_t {
-    unsigned long long v = 0;
-    if (lane == 0) v = atomicAdd(p.next_block, 1ull);
-    return (int64_t)__shfl_sync(0xffffffffu, v, 0) + n_warps;
+  // Work distribution: the first wave is static (block = warp id), later blocks are claimed from a global counter TWO
+  // steps ahead: the ticket of the block after next is requested (an atomic with a return value, ~1000 cycles under
+  // contention) while the current block is processed and only read a whole block later; the next block's bounds are
+  // prefetched meanwhile.  (Reading the ticket right after requesting it was 44 % of the stall samples, ncu r2c.)
+  unsigned long long ticket = 0;   // lane 0: the pending claim
+  auto claim_issue = [&]() {
+    if (lane == 0) ticket = atomicAdd(p.next_block, 1ull);
   };
+  auto claim_get = [&]() -> int64_t { return (int64_t)__shfl_sync(0xffffffffu, ticket, 0) + n_warps; };
   uint32_t nb, ne; float nya; bool nvalid;
   int64_t blk = warp_global;
-  int64_t blk_next = (blk < n_blocks) ? claim() : n_blocks;
+  int64_t blk_next = n_blocks;
+  if (blk < n_blocks) {
+    claim_issue();
+    blk_next = claim_get();
+    claim_issue();
+  }
   load_block(blk, nb, ne, nya, nvalid);
   for (; blk < n_blocks;) {
     uint32_t b = nb;
@@ -314,7 +321,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
       }
     }
     blk = blk_next;
-    blk_next = (blk < n_blocks) ? claim() : n_blocks;
+    if (blk < n_blocks) {
+      blk_next = claim_get();
+      claim_issue();
+    }
   }
   // ---- counters: lane -> warp -> CTA -> one atomic per CTA ----
   hinge = __reduce_add_sync(0xffffffffu, hinge);

@@ -103,6 +103,7 @@ ABI = {
     "dsgd_xchg_stats": [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)],
     "dsgd_debug_timeline": [_vp, _vp],
     "dsgd_set_grid_limit": [_vp, _i32],
+    "dsgd_reserve": [_vp, _i64, _i64],
     "dsgd_set_workers": [_vp, _i32, _vp, _i32],
     "dsgd_sync_step": [_vp, _vp, _i64, _f64, C.POINTER(_f64)],
     "dsgd_sync_steps": [_vp, _vp, _i64, _i64, _f64, _vp],
@@ -352,6 +353,10 @@ class NativeCtx:
         v, b, n = C.c_int64(), C.c_int64(), C.c_int64()
         self._ck(self._l.dsgd_xchg_stats(self._h, C.byref(v), C.byref(b), C.byref(n)))
         return v.value, b.value, n.value
+
+    def reserve(self, n_samples: int, n_steps: int):
+        """Allocate the sync path's device buffers now (see dsgd_reserve: needed when several ctxs share one GPU)."""
+        self._ck(self._l.dsgd_reserve(self._h, n_samples, n_steps))
 
     def set_grid_limit(self, n_ctas: int):
         """CTAs of the persistent sync kernel (0: one per SM) -- lets several ranks share one GPU in tests."""

@@ -76,6 +76,12 @@ int dsgd_launch_count(const dsgd_ctx *ctx, int64_t *count);
  * returns their mean duration and how many launches were sampled. */
 int dsgd_profile_begin(dsgd_ctx *ctx, int32_t sample_every);
 int dsgd_profile_end(dsgd_ctx *ctx, float *mean_ms, int64_t *n_sampled);
+/* Optional: allocate every device buffer the sync path needs for calls of up to n_samples sample ids and n_steps steps
+ * now (staging, per-step losses, the persistent kernel's buffers, the exchange's weight words) instead of on first
+ * use.  cudaMalloc synchronises the whole device: a host that drives several contexts on ONE GPU from several threads
+ * must reserve before the first fused step, or a rank allocating late waits for a rank that already runs and waits for
+ * it.  (One context per GPU never needs this.) */
+int dsgd_reserve(dsgd_ctx *ctx, int64_t n_samples, int64_t n_steps);
 /* CTAs of the persistent sync kernel (0 = one per SM, the default and the fastest).  The kernel is cooperative and its
  * ranks wait for each other, so K contexts that share ONE GPU (the K-rank tests on a single-GPU box: tests/
  * test_gpu_fused_one_gpu.py) must each take at most 1/K of the SMs. */

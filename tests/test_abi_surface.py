@@ -83,7 +83,7 @@ def test_jni_shim_type_checks_and_covers_every_native(tmp_path):
     # staged-sample split of the bench harness, developer aids, and dsgd_sync_step (= dsgd_sync_steps with one step).
     not_bound = {"dsgd_last_error", "dsgd_create", "dsgd_destroy",               # bound, but nm lists them too: fine either way
                  "dsgd_info", "dsgd_set_stream", "dsgd_synchronize", "dsgd_timer_start", "dsgd_timer_stop", "dsgd_launch_count",
-                 "dsgd_profile_begin", "dsgd_profile_end", "dsgd_set_grid_limit", "dsgd_debug_timeline", "dsgd_sync_step",
+                 "dsgd_profile_begin", "dsgd_profile_end", "dsgd_set_grid_limit", "dsgd_reserve", "dsgd_debug_timeline", "dsgd_sync_step",
                  "dsgd_stage_samples", "dsgd_sync_steps_staged", "dsgd_read_losses", "dsgd_async_replay", "dsgd_async_elapsed_ms"}
     declared = set(re.findall(r"^(?:int|const char \*)\s*(dsgd_\w+)\(", header, re.M))
     missing = declared - called - not_bound

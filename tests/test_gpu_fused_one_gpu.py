@@ -46,6 +46,7 @@ def test_fused_k_ranks_on_one_gpu_match_oracle(K, batch, dim):
     for r in range(K):
         ctx, orc = make_pair(data, lam, n_train=n_train, device=0, rank=r, world=K)
         ctx.set_grid_limit(sms // K)
+        ctx.reserve(steps * batch, steps)      # no cudaMalloc (a device-wide sync) once the ranks wait for each other
         ctxs.append(ctx)
     for r in range(K):
         for q in range(K):
@@ -101,6 +102,7 @@ def test_fused_ranks_exact_cancellation_and_empty_support():
     for r in range(2):
         ctx, orc = make_pair(data, lam, n_train=4, device=0, rank=r, world=2)
         ctx.set_grid_limit(sms // 2)
+        ctx.reserve(64, 16)
         ctxs.append(ctx)
     ctxs[0].xchg_attach(1, ctxs[1]); ctxs[1].xchg_attach(0, ctxs[0])
     w0 = np.zeros(dim); w0[[3, 5, 9, 20]] = [0.3, -0.2, 0.1, -0.4]

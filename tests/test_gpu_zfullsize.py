@@ -147,8 +147,14 @@ def test_main_scenario_async_replays_through_the_literal_master_loop():
     cfg = load_config(env={"DSGD_ASYNC": "true", "DSGD_BATCH_SIZE": "1", "DSGD_MAX_EPOCHS": "5", "DSGD_CHECK_EVERY": "2000",
                            "DSGD_LEARNING_RATE": "0.1"})
     final = {}
-    rep = scenario(cfg, data, rank=0, world=1, device=0, log=lambda s: None, async_concurrency=8,
-                   inspect=lambda what, obj: final.update({what: obj}))
+
+    def inspect(what, obj):
+        final[what] = obj
+        if what == "done":      # the device context is still alive here: re-evaluate the returned weights
+            master, state = obj
+            final["loss_of_returned_weights"] = master.local_loss_accuracy(state.grad, test_data=True)[0]
+
+    rep = scenario(cfg, data, rank=0, world=1, device=0, log=lambda s: None, async_concurrency=8, inspect=inspect)
     master, state = final["done"]
     h = master.history
     assert rep["initial_loss"] == 1.0 and len(h["test_losses"]) >= 1
@@ -164,8 +170,7 @@ def test_main_scenario_async_replays_through_the_literal_master_loop():
     assert ref["test_losses"] == h["test_losses"] and ref["test_accs"] == h["test_accs"]
     assert state.loss == ref["best_loss"] == min(h["test_losses"])
     # the returned weights are the snapshot of the best check: re-evaluating them gives that check's RAW test loss
-    loss_best, _ = master.local_loss_accuracy(state.grad, test_data=True)
-    assert loss_best == pytest.approx(h["raw_test_losses"][h["best_check"]], rel=1e-12)
+    assert final["loss_of_returned_weights"] == pytest.approx(h["raw_test_losses"][h["best_check"]], rel=1e-12)
     assert rep["final_test_accuracy"] > 0.5 and rep["final_weights_nonzero"] > 0
 
 
