@@ -69,8 +69,9 @@ struct dsgd_ctx {
   ncclComm_t comm = nullptr;
 
   // persistent sync kernel resources (allocated on first use)
-  double *p_wbuf[2] = {nullptr, nullptr};
-  double *p_gbuf[3] = {nullptr, nullptr, nullptr};
+  double *p_wbuf[2] = {nullptr, nullptr};            // K GPUs
+  double *p_gbuf[3] = {nullptr, nullptr, nullptr};   // K GPUs
+  double2 *p_rec[3] = {nullptr, nullptr, nullptr};   // one GPU: rotating {W, g} records
   unsigned long long *p_acc = nullptr;   // fixed-point accumulators of the per-CTA partials [3][kAccSets][8]
   unsigned *p_hinge = nullptr;
   int64_t p_hinge_cap = 0;
@@ -285,7 +286,7 @@ extern "C" int dsgd_destroy(dsgd_ctx *ctx) {
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   void *ptrs[] = {ctx->rp16, ctx->pairs, ctx->label, ctx->yabs, ctx->w, ctx->g, ctx->d, ctx->w_req, ctx->w32, ctx->w32_req, ctx->n_exact, ctx->scal,
                   ctx->cnt, ctx->partial, ctx->out2, ctx->gsum, ctx->p_wbuf[0], ctx->p_wbuf[1], ctx->p_gbuf[0],
-                  ctx->p_gbuf[1], ctx->p_gbuf[2], ctx->p_acc, ctx->p_hinge, ctx->p_bar, ctx->x_stats, ctx->hot_bits, ctx->hot_prefix, ctx->hot_cols, ctx->samples,
+                  ctx->p_gbuf[1], ctx->p_gbuf[2], ctx->p_rec[0], ctx->p_rec[1], ctx->p_rec[2], ctx->p_acc, ctx->p_hinge, ctx->p_bar, ctx->x_stats, ctx->hot_bits, ctx->hot_prefix, ctx->hot_cols, ctx->samples,
                   ctx->losses, ctx->preds};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -675,8 +676,12 @@ static int stream_launch(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t row_
     sp.g = g; sp.preds = preds ? preds + off : nullptr; sp.cnt = ctx->cnt; sp.n_exact = ctx->n_exact; sp.next_block = ctx->n_exact + 1;
     sp.hot_bits = ctx->hot_bits; sp.hot_prefix = ctx->hot_prefix; sp.hot_cols = ctx->hot_cols; sp.n_hot = ctx->n_hot;
     CU(cudaMemsetAsync(ctx->n_exact + 1, 0, sizeof(unsigned long long), ctx->stream));
-    const int64_t blocks32 = (m + 31) / 32;
-    const int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, cdiv(blocks32, kStreamThreads / 32)));
+    // rows per block (the unit of the dynamic work distribution): 32, or fewer when that leaves a warp fewer than ~6 blocks
+    const int64_t n_warps_all = (int64_t)ctx->sm_count * (kStreamThreads / 32);
+    sp.rows_log2 = 5;
+    while (sp.rows_log2 > 3 && ((m + (1 << sp.rows_log2) - 1) >> sp.rows_log2) < 6 * n_warps_all) --sp.rows_log2;
+    const int64_t n_blk = (m + (1 << sp.rows_log2) - 1) >> sp.rows_log2;
+    const int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, cdiv(n_blk, kStreamThreads / 32)));
     auto *pe = prof_slot(ctx);
     if (pe) cudaEventRecord(pe->first, ctx->stream);
     if (kScatter && hot) k_stream_rows<kScatter, kPreds, kScatter><<<grid, kStreamThreads, stream_smem_bytes(ctx->dim, true), ctx->stream>>>(sp);
@@ -849,6 +854,8 @@ static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
     for (int i = 0; i < 3; ++i) {
       CU(cudaMalloc(&ctx->p_gbuf[i], vd));
       CU(cudaMemsetAsync(ctx->p_gbuf[i], 0, vd, ctx->stream));
+      CU(cudaMalloc(&ctx->p_rec[i], 2 * vd));
+      CU(cudaMemsetAsync(ctx->p_rec[i], 0, 2 * vd, ctx->stream));
     }
     CU(cudaMalloc(&ctx->p_acc, sizeof(unsigned long long) * 3 * kAccSets * 8));
     CU(cudaMalloc(&ctx->p_bar, sizeof(unsigned) * 4));
@@ -899,7 +906,7 @@ static int persist_params(dsgd_ctx *ctx, PersistParams &pp, const int32_t *sampl
   pp.rp16 = ctx->rp16; pp.pairs = ctx->pairs; pp.label = ctx->label; pp.samples = samples_dev;
   pp.n_steps = n_steps; pp.batch = (int32_t)n_per_step; pp.dim = ctx->dim;
   pp.wbuf[0] = ctx->p_wbuf[0]; pp.wbuf[1] = ctx->p_wbuf[1];
-  for (int i = 0; i < 3; ++i) pp.gbuf[i] = ctx->p_gbuf[i];
+  for (int i = 0; i < 3; ++i) { pp.gbuf[i] = ctx->p_gbuf[i]; pp.rec[i] = ctx->p_rec[i]; }
   pp.d = ctx->d; pp.acc = ctx->p_acc; pp.bar = ctx->p_bar; pp.hinge = ctx->p_hinge; pp.losses = losses_dev;
   pp.w_out = ctx->w; pp.w32_out = ctx->w32; pp.scal = ctx->scal;
   pp.abort_flag = reinterpret_cast<int *>(ctx->p_bar + 1);
@@ -924,7 +931,8 @@ static int persist_run(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t n_per_
   const int opt = persist_opt();
   PersistParams pp;
   if ((rc = persist_params(ctx, pp, samples_dev, n_per_step, n_steps, lr, losses_dev, G))) return rc;
-  CU(cudaMemcpyAsync(ctx->p_wbuf[1], ctx->w, sizeof(double) * (size_t)ctx->dim, cudaMemcpyDeviceToDevice, ctx->stream));
+  k_rec_init<<<cdiv(ctx->dim, 256), 256, 0, ctx->stream>>>(ctx->w, ctx->dim, ctx->p_rec[0], ctx->p_rec[1], ctx->p_rec[2]);
+  LAUNCHED();
   pp.k_den = 1.0;
   pp.timeout_cycles = 4000000000ll;  // ~2 s at 1.9 GHz: a healthy barrier takes well under a microsecond
   void *args[] = {&pp};

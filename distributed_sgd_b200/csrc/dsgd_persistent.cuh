@@ -31,6 +31,9 @@
 // One GPU (kMulti == false), interval I_t between grid barrier t-1 and t, W_t = weights step t differentiates at:
 //   consumers: x.W_t with W_t[col] = update(W_{t-1}[col], g_{t-1}[col], c_{t-1}) applied on the fly; gate; RED into g_t
 //   updaters : W_t buffer <- update(W_{t-1}, g_{t-1}, c_{t-1}); zero g_{t+1}'s buffer; c_t, ||W_t||^2
+//   W and g of a column sit side by side in one 16-byte record {W, g} (three rotating record arrays): a consumer needs
+//   ONE 128-bit gather per non-zero -- the scattered 8-byte accesses of a CTA's non-zeros are what its time grows with
+//   (measured: 5 cycles per pair with two gathers and one RED, profiles/r2_timeline.md).
 //
 // K GPUs (kMulti == true; one process or ctx per GPU, every rank's receive area mapped into every peer over
 // NVLink), interval I_T:
@@ -64,8 +67,9 @@ struct PersistParams {
   int64_t n_steps;
   int32_t batch;
   int32_t dim;
-  double *wbuf[2];  // one GPU: on entry wbuf[1] holds the initial weights; K GPUs: wbuf[0]
-  double *gbuf[3];  // all zero on entry and on exit
+  double *wbuf[2];  // K GPUs: on entry wbuf[0] holds the initial weights
+  double *gbuf[3];  // K GPUs: gradient buffers, all zero on entry and on exit
+  double2 *rec[3];  // one GPU: rotating records {W, g} per column; on entry rec[2] = {W_init, 0}, rec[0].g = rec[1].g = 0
   const double *d;
   unsigned long long *acc;  // [3 rotating][kAccSets][8]: fixed-point accumulators of {W.d, ||W||^2}; zero on entry
   unsigned *hinge;  // [n_steps], zero on entry (one GPU)
@@ -249,8 +253,8 @@ __device__ __forceinline__ void acc_push_one(unsigned long long *slot3, unsigned
   put(slot3 + 1, f1);
   put(slot3 + 2, f2);
 }
-__device__ __forceinline__ void acc_push(unsigned long long *acc, double sd, double sn) {
-  unsigned long long *set = acc + (size_t)(blockIdx.x % kAccSets) * 8;
+__device__ __forceinline__ void acc_push(unsigned long long *acc, double sd, double sn, int warp) {
+  unsigned long long *set = acc + (size_t)((blockIdx.x + warp) % kAccSets) * 8;
   acc_push_one(set + 0, set + 6, sd);
   acc_push_one(set + 3, set + 6, sn);
 }
@@ -310,7 +314,6 @@ struct PersistSmem {
   uint64_t c_bar[2];    // c of the weights interval t updates from: completed during interval t-1
   double c_val[2];
   double nrm_val[2];
-  double red[kCons + kUpd][2];
   unsigned hinge_acc;
   int ok;
 };
@@ -326,7 +329,7 @@ constexpr int kTlWords = 256 * 16 + kTlSteps * kTlCtas * kTlPerCta;
 // One GPU: the update of step t-1 applied on the fly to (W_{t-1}[col], g_{t-1}[col]); c_{t-1} arrives through an
 // mbarrier (completed during the previous interval, so the wait normally falls through).
 struct FetchLocal {
-  const double *W, *G;
+  const double2 *R;   // records {W_{t-1}, g_{t-1}}
   uint64_t *cbar;
   unsigned cpar;
   const double *cval;
@@ -344,23 +347,20 @@ struct FetchLocal {
     }
   }
   __device__ __forceinline__ void get4(const uint2 (&pr)[4], double (&wv)[4]) {
-    double gv[4];
+    double2 r[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      wv[u] = 0.0;
-      gv[u] = 0.0;
-      if (pr[u].y << 1) {  // val != +-0: a zero value contributes filt(0 * w) == 0 whatever the weight
-        wv[u] = __ldcg(&W[pr[u].x]);
-        gv[u] = __ldcg(&G[pr[u].x]);
-      }
+      r[u] = make_double2(0.0, 0.0);
+      if (pr[u].y << 1) r[u] = __ldcg(&R[pr[u].x]);  // val != +-0: a zero value contributes filt(0 * w) == 0 whatever the weight
     }
     need_c();
 #pragma unroll
-    for (int u = 0; u < 4; ++u) wv[u] = apply_update(wv[u], gv[u], c, add_c, k_den, lr);
+    for (int u = 0; u < 4; ++u) wv[u] = apply_update(r[u].x, r[u].y, c, add_c, k_den, lr);
   }
   __device__ __forceinline__ double get1(uint32_t col) {
     need_c();
-    return apply_update(__ldcg(&W[col]), __ldcg(&G[col]), c, add_c, k_den, lr);
+    const double2 r = __ldcg(&R[col]);
+    return apply_update(r.x, r.y, c, add_c, k_den, lr);
   }
 };
 // K GPUs: the LL word of W_T[col] published by the column's thread of this GPU, spinning on its tag.
@@ -403,11 +403,11 @@ struct FetchLL {
 
 // ---- the consumer warps' work on one stage: SlaveImpl.gradient's per-sample body (core/Slave.scala:147-153) ----
 // x.W per row (math/Vec.scala:58), prediction and hinge loss (SparseSVM.scala:14-16), gate (SparseSVM.scala:28),
-// RED of y*x into Gcur.  kOnePass: a row that is one chunk is gated and scattered by the warp that computed its
+// RED of y*x into g (entry of column c at gbase + gstride * c).  kOnePass: a row that is one chunk is gated and scattered by the warp that computed its
 // dot, from the registers that still hold its pairs (0.0 + acc == acc: the same dot as the two-pass form).
 template <int kCons, int kMaxChunks, bool kOnePass, class Fetch>
-__device__ __forceinline__ unsigned consume_stage(StageMeta<kMaxChunks> &mt, const uint2 *ring, const uint2 *pairs, double *Gcur,
-                                                  Fetch &fetch, int warp, int lane, long long *tl) {
+__device__ __forceinline__ unsigned consume_stage(StageMeta<kMaxChunks> &mt, const uint2 *ring, const uint2 *pairs, double *gbase,
+                                                  const int gstride, Fetch &fetch, int warp, int lane, long long *tl) {
   const int n_ch = mt.n_chunks;
   unsigned hinge = 0;  // lane 0 only
   // ---- pass 1: dots of this warp's chunks ----
@@ -439,7 +439,7 @@ __device__ __forceinline__ unsigned consume_stage(StageMeta<kMaxChunks> &mt, con
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const double gvv = filt(filt((double)__uint_as_float(pr[u].y)) * y);
-            if (gvv != 0.0) red_add_f64(&Gcur[pr[u].x], gvv);
+            if (gvv != 0.0) red_add_f64(gbase + (size_t)gstride * pr[u].x, gvv);
           }
         }
         continue;
@@ -466,7 +466,7 @@ __device__ __forceinline__ unsigned consume_stage(StageMeta<kMaxChunks> &mt, con
         for (int k = lane; k < n; k += 32) {
           const uint2 pr = src[k];
           const double gvv = filt(filt((double)__uint_as_float(pr.y)) * y);
-          if (gvv != 0.0) red_add_f64(&Gcur[pr.x], gvv);
+          if (gvv != 0.0) red_add_f64(gbase + (size_t)gstride * pr.x, gvv);
         }
       }
     }
@@ -493,7 +493,7 @@ __device__ __forceinline__ unsigned consume_stage(StageMeta<kMaxChunks> &mt, con
         for (int k = lane; k < len; k += 32) {
           const uint2 pr = __ldg(&grow[k]);
           const double gvv = filt(filt((double)__uint_as_float(pr.y)) * y);
-          if (gvv != 0.0) red_add_f64(&Gcur[pr.x], gvv);
+          if (gvv != 0.0) red_add_f64(gbase + (size_t)gstride * pr.x, gvv);
         }
     }
   }
@@ -793,7 +793,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
         mbar_wait(&sm.full[st], (unsigned)((t / kStages) & 1), p.abort_flag, p.timeout_cycles);
         if (warp == 0) DSGD_TL(1);
         FetchLL fetch{LWcur, wtag, p.abort_flag, p.timeout_cycles};
-        const unsigned hinge = consume_stage<kCons, kMaxChunks, kOnePass>(mt, &sm.ring[st][0], p.pairs, Gcur, fetch, warp, lane,
+        const unsigned hinge = consume_stage<kCons, kMaxChunks, kOnePass>(mt, &sm.ring[st][0], p.pairs, Gcur, 1, fetch, warp, lane,
                                                                           warp == 0 ? tl_row : nullptr);
         ok = ok && fetch.good;
         if (lane == 0 && hinge) atomicAdd(&sm.hinge_acc, hinge);
@@ -806,17 +806,18 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
       // ---------------------------------------------------------------------------------------------------
       // one GPU
       // ---------------------------------------------------------------------------------------------------
-      const double *Wprev = p.wbuf[(t + 1) & 1];
-      double *Wcur = p.wbuf[t & 1];
+      const double2 *Rprev = p.rec[(t + 2) % 3];   // {W_{t-1}, g_{t-1}}
+      double2 *Rcur = p.rec[t % 3];                // {W_t (written by the updaters), g_t (RED by the consumers)}
+      double2 *Rnext = p.rec[(t + 1) % 3];         // its g half is zeroed for step t+1
       if (is_cons) {
         if (!last) {
           const int st = (int)(t % kStages);
           auto &mt = sm.meta[st];
           mbar_wait(&sm.full[st], (unsigned)((t / kStages) & 1), p.abort_flag, p.timeout_cycles);
           if (warp == 0) DSGD_TL(1);
-          FetchLocal fetch{Wprev, Gprev, &sm.c_bar[t & 1], c_par, &sm.c_val[t & 1], p.abort_flag, p.timeout_cycles, p.k_den, lr};
-          const unsigned hinge = consume_stage<kCons, kMaxChunks, kOnePass>(mt, &sm.ring[st][0], p.pairs, Gcur, fetch, warp, lane,
-                                                                            warp == 0 ? tl_row : nullptr);
+          FetchLocal fetch{Rprev, &sm.c_bar[t & 1], c_par, &sm.c_val[t & 1], p.abort_flag, p.timeout_cycles, p.k_den, lr};
+          const unsigned hinge = consume_stage<kCons, kMaxChunks, kOnePass>(mt, &sm.ring[st][0], p.pairs, &Rcur[0].y, 2, fetch, warp,
+                                                                            lane, warp == 0 ? tl_row : nullptr);
           if (lane == 0 && hinge) atomicAdd(&sm.hinge_acc, hinge);
           if (tl_rec && warp == 0 && lane == 0) tl_rec[2] = mt.n_pairs;
           __syncwarp();
@@ -827,12 +828,14 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
         // ---- update warps: W_t <- update(W_{t-1}, g_{t-1}, c_{t-1}) over this thread's columns (two per thread on a
         //      B200: both requested before c is waited for) ----
         constexpr int kCols = 2;
-        double wv[kCols], gv[kCols], dv[kCols];
+        double2 rv[kCols];
+        double dv[kCols];
 #pragma unroll
         for (int i = 0; i < kCols; ++i) {
           const int j = u0 + i * n_upd;
-          wv[i] = gv[i] = dv[i] = 0.0;
-          if (j < p.dim) { wv[i] = __ldcg(&Wprev[j]); gv[i] = __ldcg(&Gprev[j]); dv[i] = __ldg(&p.d[j]); }
+          rv[i] = make_double2(0.0, 0.0);
+          dv[i] = 0.0;
+          if (j < p.dim) { rv[i] = __ldcg(&Rprev[j]); dv[i] = __ldg(&p.d[j]); }
         }
         mbar_wait(&sm.c_bar[t & 1], c_par, p.abort_flag, p.timeout_cycles);
         const double c_prev = *(volatile double *)&sm.c_val[t & 1];
@@ -841,17 +844,18 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
         for (int i = 0; i < kCols; ++i) {
           const int j = u0 + i * n_upd;
           if (j < p.dim) {
-            const double wn = apply_update(wv[i], gv[i], c_prev, add_c, p.k_den, lr);
-            Wcur[j] = wn;
-            Gzero[j] = 0.0;
+            const double wn = apply_update(rv[i].x, rv[i].y, c_prev, add_c, p.k_den, lr);
+            Rcur[j].x = wn;
+            Rnext[j].y = 0.0;
             pd += filt(wn * dv[i]);
             pn += wn * wn;
           }
         }
         for (int j = u0 + kCols * n_upd; j < p.dim; j += n_upd) {   // more columns than 2 * update threads
-          const double wn = apply_update(__ldcg(&Wprev[j]), __ldcg(&Gprev[j]), c_prev, add_c, p.k_den, lr);
-          Wcur[j] = wn;
-          Gzero[j] = 0.0;
+          const double2 r = __ldcg(&Rprev[j]);
+          const double wn = apply_update(r.x, r.y, c_prev, add_c, p.k_den, lr);
+          Rcur[j].x = wn;
+          Rnext[j].y = 0.0;
           pd += filt(wn * __ldg(&p.d[j]));
           pn += wn * wn;
         }
@@ -859,18 +863,17 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
       }
     }
 
-    // ---- grid barrier T: the CTA's partial {W_T . d, ||W_T||^2} and hinge total ride on it ----
-    pd = warp_sum(pd);
-    pn = warp_sum(pn);
-    if (lane == 0) { sm.red[warp][0] = pd; sm.red[warp][1] = pn; }
+    // ---- grid barrier T.  Every warp that owns columns adds its share of {W_T . d, ||W_T||^2} to the fixed-point
+    //      accumulators first (integer sums: any order), well before the arrival ----
+    if (kMulti || is_upd) {
+      pd = warp_sum(pd);
+      pn = warp_sum(pn);
+      if (lane == 0 && (pd != 0.0 || pn != 0.0)) acc_push(acc_cur, pd, pn, warp);
+    }
     if (!ok) *(volatile int *)&sm.ok = 0;
     named_bar_sync(3, kSyncThreads);
     ++phase;
     if (threadIdx.x == 0) {
-      double sd = 0.0, sn = 0.0;
-#pragma unroll
-      for (int i = 0; i < kCons + kUpd; ++i) { sd += sm.red[i][0]; sn += sm.red[i][1]; }   // warps in index order
-      acc_push(acc_cur, sd, sn);
       if (!last) {   // the CTA's hinge total (and, K GPUs, the step's sample count) ahead of the arrival
         const unsigned h = sm.hinge_acc;
         if constexpr (kMulti) {
@@ -914,14 +917,23 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
       atomicAdd(&p.xstats[1], st_bm);
     }
   } else if (is_upd) {
-    const double *Wfin = p.wbuf[S & 1];
-    double *Glast = p.gbuf[(S + 2) % 3];
+    const double2 *Rfin = p.rec[S % 3];
     for (int j = u0; j < p.dim; j += n_upd) {
-      const double wv = __ldcg(&Wfin[j]);
+      const double wv = __ldcg(&Rfin[j]).x;
       p.w_out[j] = wv;
       p.w32_out[j] = (float)wv;
-      Glast[j] = 0.0;
     }
+  }
+}
+
+// One GPU: the records a launch starts from -- rec2 = {W, 0} (read by the first interval), g halves of rec0 / rec1 zero.
+__global__ void __launch_bounds__(256) k_rec_init(const double *__restrict__ w, int dim, double2 *__restrict__ rec0,
+                                                  double2 *__restrict__ rec1, double2 *__restrict__ rec2) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < dim) {
+    rec2[j] = make_double2(w[j], 0.0);
+    rec0[j].y = 0.0;
+    rec1[j].y = 0.0;
   }
 }
 

@@ -37,7 +37,7 @@
 
 namespace dsgd {
 
-constexpr int kStreamThreads = 1024;
+constexpr int kStreamThreads = 768;   // 24 warps x 80 registers: room for two groups of loads per lane
 constexpr int kStreamUnroll = 4;
 constexpr int kHotSlots = 2688;
 constexpr int64_t kHotMaxRows = 1 << 18;   // limb headroom: 2^18 adds of < 2^14 (resp. <= 2^12 in magnitude)
@@ -56,6 +56,8 @@ struct StreamParams {
   unsigned long long *cnt; // kCntHinge / kCntCorrect
   unsigned long long *n_exact;     // rows that took the exact fallback (diagnostic)
   unsigned long long *next_block;  // work counter (zero on entry): blocks beyond the first wave are claimed dynamically
+  int rows_log2;               // rows per block = 1 << rows_log2 (5, 4 or 3): the host picks it so that every warp gets
+                               // several blocks (a block is the unit of the dynamic work distribution)
   const uint32_t *hot_bits;    // kHot: bit c set = column c has a shared-memory accumulator slot
   const uint16_t *hot_prefix;  //       slots before word c >> 5 (slot = prefix + popc of the lower bits of the word)
   const int32_t *hot_cols;     //       slot -> column
@@ -143,16 +145,17 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
     atomicAdd(&p.g[col], gv);
   };
 
-  const int64_t n_blocks = (p.n + 31) >> 5;
+  const int rlog = p.rows_log2, rows_per_block = 1 << rlog;
+  const int64_t n_blocks = (p.n + rows_per_block - 1) >> rlog;
   const int64_t warp_global = (int64_t)blockIdx.x * (kStreamThreads / 32) + warp;
   const int64_t n_warps = (int64_t)gridDim.x * (kStreamThreads / 32);
   unsigned hinge = 0, correct = 0, n_exact = 0;
 
   // bounds of the block being processed / the next one: lane l holds row l of the block
   auto load_block = [&](int64_t blk, uint32_t &b, uint32_t &e, float &ya, bool &valid) {
-    const int64_t i = (blk << 5) + lane;
+    const int64_t i = (blk << rlog) + lane;
     b = 0u; e = 0u; ya = 0.f;
-    valid = blk < n_blocks && i < p.n;
+    valid = blk < n_blocks && lane < rows_per_block && i < p.n;
     if (valid) {
       const int64_t rid = p.samples ? (int64_t)__ldg(&p.samples[i]) : p.row_begin + i;
       b = __ldg(&p.rp16[rid]);
@@ -160,10 +163,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
       ya = __ldg(&p.yabs[rid]);
     }
   };
-  // Work distribution: the first wave is static (block = warp id), later blocks are claimed from a global counter TWO
-  // steps ahead: the ticket of the block after next is requested (an atomic with a return value, ~1000 cycles under
-  // contention) while the current block is processed and only read a whole block later; the next block's bounds are
-  // prefetched meanwhile.  (Reading the ticket right after requesting it was 44 % of the stall samples, ncu r2c.)
+  // Work distribution: the first wave is static (block = warp id), later blocks are claimed from a global counter one
+  // step ahead; the ticket (an atomic with a return value) is requested when a block starts and read when it ends, the
+  // next block's bounds were prefetched a block earlier.
   unsigned long long ticket = 0;   // lane 0: the pending claim
   auto claim_issue = [&]() {
     if (lane == 0) ticket = atomicAdd(p.next_block, 1ull);
@@ -175,7 +177,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
   if (blk < n_blocks) {
     claim_issue();
     blk_next = claim_get();
-    claim_issue();
   }
   load_block(blk, nb, ne, nya, nvalid);
   for (; blk < n_blocks;) {
@@ -184,11 +185,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
     float ya = nya;
     bool valid = nvalid;
     load_block(blk_next, nb, ne, nya, nvalid);
+    if (blk_next < n_blocks) claim_issue();   // for the block after next: read at the end of this block
     int opos = lane;            // position of this lane's row inside the block (before compaction)
     // empty rows: dot 0 -> prediction 0, hinge 1, never correct, nothing to scatter (SparseSVM.scala:14-16)
     if (valid && len == 0) {
       hinge += 1u;
-      if (kPreds) p.preds[(blk << 5) + lane] = 0.0;
+      if (kPreds) p.preds[(blk << rlog) + lane] = 0.0;
     }
     const unsigned ne_mask = __ballot_sync(0xffffffffu, valid && len > 0);
     if (ne_mask != 0xffffffffu) {   // compact the non-empty rows to lanes 0 .. n-1 (order kept)
@@ -219,52 +221,58 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
     float dot_mine = 0.f;                             // this lane's row: x.w in fp32 once the row is closed
     int row0 = 0;                                     // rows closed so far (warp-uniform)
 
-    for (int v0 = 0; v0 < total; v0 += 32 * kStreamUnroll) {
-      uint4 q[kStreamUnroll];
-      unsigned ends[kStreamUnroll];   // bit j: a row's LAST unit sits at lane j of this slot
-      int rmy[kStreamUnroll];         // row of this lane's unit
-      {
-        // where this lane's row ends inside the group: one or-reduction per slot
-        const unsigned pos = (unsigned)(my_end - v0);          // < 128 iff the row ends in this group
-        const unsigned bit = 1u << (pos & 31u);
-        int r0 = row0;
-#pragma unroll
-        for (int i = 0; i < kStreamUnroll; ++i) {
-          ends[i] = __reduce_or_sync(0xffffffffu, (pos >> 5) == (unsigned)i ? bit : 0u);
-          rmy[i] = r0 + __popc(ends[i] & lt_mask);
-          r0 += __popc(ends[i]);
-        }
-      }
+    // One GROUP = kStreamUnroll slots of 32 units.  fetch_group(): where rows end inside the group (one or-reduction per
+    // slot), hence the row of each lane's unit, and the 128-bit loads.  Group g + 1 is fetched BEFORE group g is
+    // processed: two groups of loads per lane are in flight at any time (4 KB per warp, 96 KB per SM).
+    auto fetch_group = [&](int v0, int r_begin, unsigned (&ends)[kStreamUnroll], uint4 (&q)[kStreamUnroll]) -> int {
+      const unsigned pos = (unsigned)(my_end - v0);          // < 32 * kStreamUnroll iff the row ends in this group
+      const unsigned bit = 1u << (pos & 31u);
       const bool full = v0 + 32 * kStreamUnroll <= total;
-      if (full) {
+      int r0 = r_begin;
 #pragma unroll
-        for (int i = 0; i < kStreamUnroll; ++i) {
-          const uint32_t bs = __shfl_sync(0xffffffffu, base, rmy[i]);
+      for (int i = 0; i < kStreamUnroll; ++i) {
+        ends[i] = __reduce_or_sync(0xffffffffu, (pos >> 5) == (unsigned)i ? bit : 0u);
+        const int rmy = r0 + __popc(ends[i] & lt_mask);      // row of this lane's unit
+        r0 += __popc(ends[i]);
+        const uint32_t bs = __shfl_sync(0xffffffffu, base, rmy & 31);
+        if (full) {
           q[i] = __ldg(&p.units[bs + (uint32_t)(v0 + 32 * i + lane)]);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < kStreamUnroll; ++i) {
-          const uint32_t bs = __shfl_sync(0xffffffffu, base, rmy[i] & 31);
+        } else {
           q[i] = make_uint4(0u, 0u, 0u, 0u);  // col 0, val +0.0f
           if (v0 + 32 * i + lane < total) q[i] = __ldg(&p.units[bs + (uint32_t)(v0 + 32 * i + lane)]);
         }
       }
+      return r0;
+    };
+    uint4 q[kStreamUnroll], qn[kStreamUnroll];
+    unsigned ends[kStreamUnroll], endsn[kStreamUnroll];   // bit j: a row's LAST unit sits at lane j of this slot
+    int r_next = 0;
+    if (total > 0) r_next = fetch_group(0, 0, ends, q);
+    for (int v0 = 0; v0 < total; v0 += 32 * kStreamUnroll) {
+      const int v1 = v0 + 32 * kStreamUnroll;
+      const bool more = v1 < total;
+      if (more) r_next = fetch_group(v1, r_next, endsn, qn);
+      const bool full = v1 <= total;
 #pragma unroll
       for (int i = 0; i < kStreamUnroll; ++i) {
         float pp = __fmaf_rn(__uint_as_float(q[i].w), ws[q[i].z], __uint_as_float(q[i].y) * ws[q[i].x]);
         if (!full && !(v0 + 32 * i + lane < total)) pp = 0.f;   // a masked unit reads ws[0]: keep a NaN / inf weight out
+        const int rmy = row0 + __popc(ends[i] & lt_mask);       // row0 == rows closed before this slot
         unsigned m = ends[i];
         while (m) {   // warp-uniform: close the rows that end inside this slot, in order
           m &= m - 1u;
-          float sp = acc_p + (rmy[i] == row0 ? pp : 0.f);
+          float sp = acc_p + (rmy == row0 ? pp : 0.f);
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) sp += __shfl_xor_sync(0xffffffffu, sp, o);
           if (lane == row0) dot_mine = sp;
           acc_p = 0.f;
           ++row0;
         }
-        acc_p += (rmy[i] == row0) ? pp : 0.f;
+        acc_p += (rmy == row0) ? pp : 0.f;
+      }
+      if (more) {
+#pragma unroll
+        for (int i = 0; i < kStreamUnroll; ++i) { q[i] = qn[i]; ends[i] = endsn[i]; }
       }
     }
     // ---- 32 rows decided by 32 lanes: inside the rounding band -> exact recomputation; else the sign is certain ----
@@ -302,7 +310,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
       }
     }
     if (kPreds) {
-      if (valid) p.preds[(blk << 5) + opos] = (double)pred_mine;
+      if (valid) p.preds[(blk << rlog) + opos] = (double)pred_mine;
     }
     // ---- scatter y*x of the rows that passed the gate (SparseSVM.scala:28) ----
     if (kScatter) {
@@ -321,10 +329,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
       }
     }
     blk = blk_next;
-    if (blk < n_blocks) {
-      blk_next = claim_get();
-      claim_issue();
-    }
+    if (blk < n_blocks) blk_next = claim_get();
   }
   // ---- counters: lane -> warp -> CTA -> one atomic per CTA ----
   hinge = __reduce_add_sync(0xffffffffu, hinge);
