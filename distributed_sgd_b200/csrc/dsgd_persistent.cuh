@@ -69,7 +69,7 @@ struct PersistParams {
   int32_t dim;
   double *wbuf[2];  // K GPUs: on entry wbuf[0] holds the initial weights
   double *gbuf[3];  // K GPUs: gradient buffers, all zero on entry and on exit
-  double2 *rec[3];  // one GPU: rotating records {W, g} per column; on entry rec[2] = {W_init, 0}, rec[0].g = rec[1].g = 0
+  double2 *rec[3];  // one GPU: rotating records {W, g} per column; on entry all three = {W_init, 0}
   const double *d;
   unsigned long long *acc;  // [3 rotating][kAccSets][8]: fixed-point accumulators of {W.d, ||W||^2}; zero on entry
   unsigned *hinge;  // [n_steps], zero on entry (one GPU)
@@ -316,6 +316,7 @@ struct PersistSmem {
   double nrm_val[2];
   unsigned hinge_acc;
   int ok;
+  long long tl_warp[kCons + kUpd];   // debug timeline: when each warp reached the CTA barrier
 };
 
 #define DSGD_TL(slot_)                                                                        \
@@ -633,6 +634,25 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
   const bool col_act = kMulti && (int)threadIdx.x < slice && j_col <= p.dim;
   const int col_word = j_col >> 5;
   unsigned long long st_val = 0, st_bm = 0;
+  // one GPU, update threads: the columns this thread owns for the whole launch (W_{t-1}[j], d[j], buffers still to refresh,
+  // "the g half seen last interval was non-zero"); K GPUs, column threads: W_{T-1}[j_col] and d[j_col]
+  constexpr int kUpdCols = 2;
+  double wreg[kUpdCols], dreg[kUpdCols];
+  int ttl[kUpdCols];
+  bool gnz[kUpdCols];
+#pragma unroll
+  for (int i = 0; i < kUpdCols; ++i) {
+    wreg[i] = dreg[i] = 0.0;
+    ttl[i] = 0;
+    gnz[i] = false;
+    if constexpr (!kMulti) {
+      const int j = u0 + i * n_upd;
+      if (is_upd && j < p.dim) { wreg[i] = __ldcg(&p.rec[2][j].x); dreg[i] = __ldg(&p.d[j]); }
+    }
+  }
+  if constexpr (kMulti) {
+    if (col_act && j_col < p.dim) { wreg[0] = __ldcg(&p.wbuf[0][j_col]); dreg[0] = __ldg(&p.d[j_col]); }
+  }
 
   for (int64_t T = base; T <= base + S; ++T) {
     const int64_t t = T - base;
@@ -680,7 +700,6 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
       // ---------------------------------------------------------------------------------------------------
       // push g_{T-1} (sparse) and update this thread's column
       // ---------------------------------------------------------------------------------------------------
-      const unsigned long long *LWprev = p.llw[(T + 1) & 1];  // LL words of W_{T-1}, tag T
       unsigned long long *LWcur = p.llw[T & 1];               // LL words of W_T, tag T+1
       const int parp = (int)((T + 1) & 1);                    // receive parity of step T-1
       const unsigned gtag = (unsigned)T;                      // words of step T-1 carry tag T
@@ -689,7 +708,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
         if (first) {
           // W_base arrives as plain doubles from the host (wbuf[0]): publish it in LL form, no update pending
           if (col_act) {
-            if (j_col < p.dim) ll_store(LWcur + 2 * (size_t)j_col, __ldcg(&p.wbuf[0][j_col]), wtag);
+            if (j_col < p.dim) ll_store(LWcur + 2 * (size_t)j_col, wreg[0], wtag);
             Gzero[j_col] = 0.0;
           }
         } else {
@@ -716,10 +735,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
             // whose bit is set: everything requested before anything is waited for -- c_{T-1} included
             double raw[kMaxWorld];
             unsigned need = 0;   // bit k: value word of peer k still to be waited for
-            double wn = 0.0;
-            bool got_w = true;
-            if (col_act && j_col < p.dim) got_w = ll_try_load(LWprev + 2 * (size_t)j_col, gtag, wn);
-            const double dj = (col_act && j_col < p.dim) ? __ldg(&p.d[j_col]) : 0.0;
+            double wn = wreg[0];                 // W_{T-1}[j_col]: this thread computed it one interval ago
             const unsigned long long *bm0 = p.xbm[me] + (size_t)parp * p.xwords + (size_t)col_word;
             const unsigned long long *vl0 = p.xval[me] + 2 * ((size_t)parp * p.xstride + (size_t)j_col);
 #pragma unroll
@@ -749,8 +765,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
             const double c_prev = *(volatile double *)&sm.c_val[t & 1];
             const bool add_c = (c_prev != 0.0) && (fabs(c_prev) > kEps);
             if (col_act) {
-              FetchLL sp{LWprev, gtag, p.abort_flag, p.timeout_cycles};
-              if (!got_w) sp.spin(LWprev + 2 * (size_t)j_col, wn);
+              FetchLL sp{nullptr, gtag, p.abort_flag, p.timeout_cycles};
               double s = 0.0;
 #pragma unroll
               for (int k = 0; k < kMaxWorld; ++k) {
@@ -777,8 +792,9 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
                   const double step = filt(mean * lr);
                   wn = filt(wn - step);
                 }
+                wreg[0] = wn;
                 ll_store(LWcur + 2 * (size_t)j_col, wn, wtag);
-                pd = filt(wn * dj);
+                pd = filt(wn * dreg[0]);
                 pn = wn * wn;
               }
               Gzero[j_col] = 0.0;
@@ -825,33 +841,35 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
           if (warp == 0) DSGD_TL(3);
         }
       } else {
-        // ---- update warps: W_t <- update(W_{t-1}, g_{t-1}, c_{t-1}) over this thread's columns (two per thread on a
-        //      B200: both requested before c is waited for) ----
-        constexpr int kCols = 2;
-        double2 rv[kCols];
-        double dv[kCols];
+        // ---- update warps: W_t <- update(W_{t-1}, g_{t-1}, c_{t-1}).  A thread owns the same (up to kUpdCols) columns for
+        //      the whole launch: their W and d stay in registers, only g_{t-1} is read (requested before c is waited
+        //      for), and W_t is stored only into the record buffers that do not hold it yet (the three buffers after a
+        //      change), a g half is zeroed only if it was non-zero: most columns of a step cost one 8-byte load ----
+        double gv[kUpdCols];
 #pragma unroll
-        for (int i = 0; i < kCols; ++i) {
+        for (int i = 0; i < kUpdCols; ++i) {
           const int j = u0 + i * n_upd;
-          rv[i] = make_double2(0.0, 0.0);
-          dv[i] = 0.0;
-          if (j < p.dim) { rv[i] = __ldcg(&Rprev[j]); dv[i] = __ldg(&p.d[j]); }
+          gv[i] = (j < p.dim) ? __ldcg(&Rprev[j].y) : 0.0;
         }
         mbar_wait(&sm.c_bar[t & 1], c_par, p.abort_flag, p.timeout_cycles);
         const double c_prev = *(volatile double *)&sm.c_val[t & 1];
         const bool add_c = (c_prev != 0.0) && (fabs(c_prev) > kEps);
 #pragma unroll
-        for (int i = 0; i < kCols; ++i) {
+        for (int i = 0; i < kUpdCols; ++i) {
           const int j = u0 + i * n_upd;
           if (j < p.dim) {
-            const double wn = apply_update(rv[i].x, rv[i].y, c_prev, add_c, p.k_den, lr);
-            Rcur[j].x = wn;
-            Rnext[j].y = 0.0;
-            pd += filt(wn * dv[i]);
-            pn += wn * wn;
+            if (gv[i] != 0.0) {
+              wreg[i] = apply_update(wreg[i], gv[i], c_prev, add_c, p.k_den, lr);
+              ttl[i] = 3;
+            }
+            if (ttl[i] > 0) { Rcur[j].x = wreg[i]; --ttl[i]; }
+            if (gnz[i]) Rnext[j].y = 0.0;          // held g_{t-2}, read for the last time during interval t-1
+            gnz[i] = gv[i] != 0.0;
+            pd += filt(wreg[i] * dreg[i]);
+            pn += wreg[i] * wreg[i];
           }
         }
-        for (int j = u0 + kCols * n_upd; j < p.dim; j += n_upd) {   // more columns than 2 * update threads
+        for (int j = u0 + kUpdCols * n_upd; j < p.dim; j += n_upd) {   // more columns than kUpdCols per update thread
           const double2 r = __ldcg(&Rprev[j]);
           const double wn = apply_update(r.x, r.y, c_prev, add_c, p.k_den, lr);
           Rcur[j].x = wn;
@@ -871,9 +889,17 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
       if (lane == 0 && (pd != 0.0 || pn != 0.0)) acc_push(acc_cur, pd, pn, warp);
     }
     if (!ok) *(volatile int *)&sm.ok = 0;
+    if (tl_row && lane == 0) sm.tl_warp[warp] = clock64();
     named_bar_sync(3, kSyncThreads);
     ++phase;
     if (threadIdx.x == 0) {
+      if (tl_row) {   // when the slowest consumer warp / update warp of CTA 0 reached the CTA barrier
+        long long mc = 0, mu = 0;
+        for (int i = 0; i < kCons; ++i) mc = max(mc, sm.tl_warp[i]);
+        for (int i = kCons; i < kCons + kUpd; ++i) mu = max(mu, sm.tl_warp[i]);
+        tl_row[13] = mc;
+        tl_row[14] = mu;
+      }
       if (!last) {   // the CTA's hinge total (and, K GPUs, the step's sample count) ahead of the arrival
         const unsigned h = sm.hinge_acc;
         if constexpr (kMulti) {
@@ -918,7 +944,12 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
     }
   } else if (is_upd) {
     const double2 *Rfin = p.rec[S % 3];
-    for (int j = u0; j < p.dim; j += n_upd) {
+#pragma unroll
+    for (int i = 0; i < kUpdCols; ++i) {
+      const int j = u0 + i * n_upd;
+      if (j < p.dim) { p.w_out[j] = wreg[i]; p.w32_out[j] = (float)wreg[i]; }
+    }
+    for (int j = u0 + kUpdCols * n_upd; j < p.dim; j += n_upd) {
       const double wv = __ldcg(&Rfin[j]).x;
       p.w_out[j] = wv;
       p.w32_out[j] = (float)wv;
@@ -926,14 +957,15 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
   }
 }
 
-// One GPU: the records a launch starts from -- rec2 = {W, 0} (read by the first interval), g halves of rec0 / rec1 zero.
+// One GPU: the records a launch starts from -- all three buffers = {W, 0}.
 __global__ void __launch_bounds__(256) k_rec_init(const double *__restrict__ w, int dim, double2 *__restrict__ rec0,
                                                   double2 *__restrict__ rec1, double2 *__restrict__ rec2) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < dim) {
-    rec2[j] = make_double2(w[j], 0.0);
-    rec0[j].y = 0.0;
-    rec1[j].y = 0.0;
+    const double2 r = make_double2(w[j], 0.0);
+    rec0[j] = r;
+    rec1[j] = r;
+    rec2[j] = r;
   }
 }
 

@@ -10,7 +10,7 @@ import numpy as np
 
 NAMES = {0: "interval start (consumer warp 0)", 11: "K GPUs: push of g_{T-1} issued", 12: "K GPUs: column updated, W_T word published",
          1: "stage full (TMA landed)", 2: "first chunk: weights gathered, products done", 4: "first chunk: dot reduced",
-         3: "rows done (scatter issued)", 6: "CTA synced, arriving at grid barrier",
+         3: "rows done (scatter issued)", 13: "slowest consumer warp at the CTA barrier", 14: "slowest update warp at the CTA barrier", 6: "CTA synced, arriving at grid barrier",
          7: "grid barrier passed", 10: "update warp 0: its columns updated",
          9: "c_{t-1} summed from the barrier's partials, handed over"}
 
