@@ -72,7 +72,7 @@ struct dsgd_ctx {
   double *p_wbuf[2] = {nullptr, nullptr};            // K GPUs
   double *p_gbuf[3] = {nullptr, nullptr, nullptr};   // K GPUs
   double2 *p_rec[3] = {nullptr, nullptr, nullptr};   // one GPU: rotating {W, g} records
-  unsigned long long *p_acc = nullptr;   // fixed-point accumulators of the per-CTA partials [3][kAccSets][8]
+  unsigned long long *p_acc = nullptr;   // fixed-point accumulators of the per-CTA partials [3][kAccStride]
   unsigned *p_hinge = nullptr;
   int64_t p_hinge_cap = 0;
   unsigned *p_bar = nullptr;   // [0]: grid barrier counter, [1]: abort flag
@@ -231,8 +231,11 @@ extern "C" int dsgd_create(dsgd_ctx **out, int device, int32_t dim, double lambd
     { int rc = fail(nullptr, DSGD_ERR_CUDA, "dsgd_create: device %d is sm_%d%d; this library is built for sm_100a only",
                     device, prop.major, prop.minor); delete ctx; return rc; }
   if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
-  if ((e = cudaStreamCreateWithFlags(&ctx->astream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
-  if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if (flags & DSGD_FLAG_ASYNC) {   // the worker loop's stream and the service stream exist in async mode only: streams
+                                   // beyond the device's hardware queues (8 by default) alias and serialise each other
+    if ((e = cudaStreamCreateWithFlags(&ctx->astream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  }
   if ((e = cudaMalloc(&ctx->a_stop, sizeof(int))) != cudaSuccess) return bail("cudaMalloc a_stop", e);
   if ((e = cudaMalloc(&ctx->a_cnt, sizeof(unsigned long long) * 2)) != cudaSuccess) return bail("cudaMalloc a_cnt", e);
   cudaMemsetAsync(ctx->a_stop, 0, sizeof(int), ctx->own_stream);
@@ -857,7 +860,7 @@ static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
       CU(cudaMalloc(&ctx->p_rec[i], 2 * vd));
       CU(cudaMemsetAsync(ctx->p_rec[i], 0, 2 * vd, ctx->stream));
     }
-    CU(cudaMalloc(&ctx->p_acc, sizeof(unsigned long long) * 3 * kAccSets * 8));
+    CU(cudaMalloc(&ctx->p_acc, sizeof(unsigned long long) * 3 * kAccStride));
     CU(cudaMalloc(&ctx->p_bar, sizeof(unsigned) * 4));
     for (int opt = 0; opt < 4; ++opt) {
       CU(cudaFuncSetAttribute((const void *)persist_variant<false>(opt), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
@@ -910,7 +913,7 @@ static int persist_params(dsgd_ctx *ctx, PersistParams &pp, const int32_t *sampl
   pp.d = ctx->d; pp.acc = ctx->p_acc; pp.bar = ctx->p_bar; pp.hinge = ctx->p_hinge; pp.losses = losses_dev;
   pp.w_out = ctx->w; pp.w32_out = ctx->w32; pp.scal = ctx->scal;
   pp.abort_flag = reinterpret_cast<int *>(ctx->p_bar + 1);
-  CU(cudaMemsetAsync(ctx->p_acc, 0, sizeof(unsigned long long) * 3 * kAccSets * 8, ctx->stream));
+  CU(cudaMemsetAsync(ctx->p_acc, 0, sizeof(unsigned long long) * 3 * kAccStride, ctx->stream));
   pp.lambda = ctx->lambda; pp.lr = lr; pp.world = 1;
   CU(cudaMemsetAsync(ctx->p_hinge, 0, sizeof(unsigned) * (size_t)n_steps, ctx->stream));
   CU(cudaMemsetAsync(ctx->p_bar, 0, sizeof(unsigned) * 4, ctx->stream));
@@ -1490,6 +1493,7 @@ static double *master_replica(dsgd_ctx *ctx) {
 
 extern "C" int dsgd_async_updates(dsgd_ctx *ctx, int64_t *count) {
   if (!ctx || !count) return DSGD_ERR_INVALID;
+  NEED(ctx->flags & DSGD_FLAG_ASYNC, DSGD_ERR_STATE, "dsgd_async_updates: ctx is in synchronous mode");
   CU(cudaSetDevice(ctx->device));
   unsigned long long v = 0;
   double *m = master_replica(ctx);
@@ -1502,6 +1506,7 @@ extern "C" int dsgd_async_updates(dsgd_ctx *ctx, int64_t *count) {
 
 extern "C" int dsgd_async_master_weights(dsgd_ctx *ctx, double *w_out) {
   if (!ctx || !w_out) return DSGD_ERR_INVALID;
+  NEED(ctx->flags & DSGD_FLAG_ASYNC, DSGD_ERR_STATE, "dsgd_async_master_weights: ctx is in synchronous mode");
   double *m = master_replica(ctx);
   NEED(m, DSGD_ERR_STATE, "dsgd_async_master_weights: no master replica hosted or imported");
   CU(cudaSetDevice(ctx->device));

@@ -71,7 +71,7 @@ struct PersistParams {
   double *gbuf[3];  // K GPUs: gradient buffers, all zero on entry and on exit
   double2 *rec[3];  // one GPU: rotating records {W, g} per column; on entry all three = {W_init, 0}
   const double *d;
-  unsigned long long *acc;  // [3 rotating][kAccSets][8]: fixed-point accumulators of {W.d, ||W||^2}; zero on entry
+  unsigned long long *acc;  // [3 rotating][kAccStride]: fixed-point accumulators of {W.d, ||W||^2}; zero on entry
   unsigned *hinge;  // [n_steps], zero on entry (one GPU)
   double *losses;   // [n_steps] or nullptr
   double *w_out;    // resident weights after the last step
@@ -224,11 +224,13 @@ __device__ __forceinline__ bool grid_barrier_arrive_wait(unsigned *bar, unsigned
 
 // ---- order-free exact sums of the per-CTA partials -------------------------------------------------------------------
 // A double v with |v| < 2^52 is cut into three integers: |v| = l2 + l1 * 2^-40 + l0 * 2^-80, l1 and l0 in [0, 2^40] (l0
-// rounded: resolution 2^-80), every cut exact in fp64 arithmetic; negative v contribute the negated limbs.  The limbs of 148 CTAs are added with 64-bit integer REDs
-// (no overflow: 148 * 2^40 < 2^48) and converted back once.  Slot layout of one set (8 x u64): {sd.l0, sd.l1, sd.l2, sn.l0,
-// sn.l1, sn.l2, overflow count, pad}; kAccSets sets, CTA b adds to set b % kAccSets (same-address REDs serialise at
-// 2.7 cycles each, tools/microbench.cu).
-constexpr int kAccSets = 8;
+// rounded: resolution 2^-80), every cut exact in fp64 arithmetic; negative v contribute the negated limbs.  The limbs of
+// 148 CTAs are added with 64-bit integer REDs (no overflow: 148 * 2^40 < 2^48) and converted back once.  One accumulator
+// = 8 x u64 = 64 bytes {sd.l0, sd.l1, sd.l2, sn.l0, sn.l1, sn.l2, overflow count, pad} on its own 128-byte line: every CTA
+// adds ONE partial per step (148 same-address REDs per limb: ~400 cycles at 2.7 cycles each, tools/microbench.cu) and
+// reads the 64 bytes back with ONE coalesced request.  (First cut: 8 striped copies read with 16-byte loads = 2 368
+// requests on 4 lines after every barrier: c arrived 2 170 cycles into the interval, profiles/r2_timeline.md.)
+constexpr int kAccStride = 16;   // u64 words between the three rotating accumulators (128 bytes)
 __device__ __forceinline__ void red_add_u64(unsigned long long *p, unsigned long long v) {
   asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -253,31 +255,18 @@ __device__ __forceinline__ void acc_push_one(unsigned long long *slot3, unsigned
   put(slot3 + 1, f1);
   put(slot3 + 2, f2);
 }
-__device__ __forceinline__ void acc_push(unsigned long long *acc, double sd, double sn, int warp) {
-  unsigned long long *set = acc + (size_t)((blockIdx.x + warp) % kAccSets) * 8;
-  acc_push_one(set + 0, set + 6, sd);
-  acc_push_one(set + 3, set + 6, sn);
+__device__ __forceinline__ void acc_push(unsigned long long *acc, double sd, double sn) {
+  acc_push_one(acc + 0, acc + 6, sd);
+  acc_push_one(acc + 3, acc + 6, sn);
 }
-// All lanes return the two sums (identical in every CTA: integer additions commute).
+// Called by a whole warp; all lanes return the two sums (identical in every CTA: integer additions commute).
 __device__ __forceinline__ void acc_read(const unsigned long long *acc, int lane, double &sd, double &sn) {
+  unsigned long long q0 = 0, q1 = 0;
+  if (lane < 4)   // 4 lanes x 16 bytes = the 64-byte accumulator in one request
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(q0), "=l"(q1) : "l"(acc + 2 * lane) : "memory");
   long long l[7];
 #pragma unroll
-  for (int i = 0; i < 7; ++i) l[i] = 0;
-  if (lane < kAccSets) {
-    const ulonglong2 *set = reinterpret_cast<const ulonglong2 *>(acc + (size_t)lane * 8);
-    ulonglong2 q[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(q[i].x), "=l"(q[i].y) : "l"(set + i) : "memory");
-    l[0] = (long long)q[0].x; l[1] = (long long)q[0].y; l[2] = (long long)q[1].x; l[3] = (long long)q[1].y;
-    l[4] = (long long)q[2].x; l[5] = (long long)q[2].y; l[6] = (long long)q[3].x;
-  }
-#pragma unroll
-  for (int i = 0; i < 7; ++i) {
-#pragma unroll
-    for (int o = kAccSets / 2; o > 0; o >>= 1) l[i] += __shfl_xor_sync(0xffffffffu, l[i], o);
-    l[i] = __shfl_sync(0xffffffffu, l[i], 0);
-  }
+  for (int i = 0; i < 7; ++i) l[i] = (long long)__shfl_sync(0xffffffffu, (i & 1) ? q1 : q0, i >> 1);
   const double nan = __longlong_as_double(0x7ff8000000000000ll);
   sd = ((double)l[0] * 0x1p-80 + (double)l[1] * 0x1p-40) + (double)l[2];
   sn = ((double)l[3] * 0x1p-80 + (double)l[4] * 0x1p-40) + (double)l[5];
@@ -311,7 +300,9 @@ struct PersistSmem {
   StageMeta<kMaxChunks> meta[kStages];
   uint64_t full[kStages];
   uint64_t empty[kStages];
-  uint64_t c_bar[2];    // c of the weights interval t updates from: completed during interval t-1
+  uint64_t c_bar[2];    // c of the weights interval t updates from
+  uint64_t u_bar;       // every warp that owns columns has published its share of {W_T . d, ||W_T||^2} in red[]
+  double red[kCons + kUpd][2];
   double c_val[2];
   double nrm_val[2];
   unsigned hinge_acc;
@@ -527,6 +518,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
     }
     mbar_init(&sm.c_bar[0], 1u);
     mbar_init(&sm.c_bar[1], 1u);
+    mbar_init(&sm.u_bar, (unsigned)(kMulti ? kCons + kUpd : kUpd));
     sm.c_val[0] = 0.0;   // interval 0 has no pending update (g_{-1} == 0): its c is never used
     sm.nrm_val[0] = 0.0;
     sm.hinge_acc = 0u;
@@ -660,9 +652,9 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
     const double *Gprev = p.gbuf[(T + 2) % 3];   // g_{T-1}
     double *Gcur = p.gbuf[T % 3];
     double *Gzero = p.gbuf[(T + 1) % 3];
-    const unsigned long long *acc_prev = p.acc + (size_t)((t + 2) % 3) * kAccSets * 8;   // partials of W_{T-1}: complete at barrier t-1
-    unsigned long long *acc_cur = p.acc + (size_t)(t % 3) * kAccSets * 8;                // partials of W_T: added before barrier t
-    unsigned long long *acc_next = p.acc + (size_t)((t + 1) % 3) * kAccSets * 8;         // read during interval t-1: zeroed now
+    const unsigned long long *acc_prev = p.acc + (size_t)((t + 2) % 3) * kAccStride;   // partials of W_{T-1}: complete at barrier t-1
+    unsigned long long *acc_cur = p.acc + (size_t)(t % 3) * kAccStride;                // partials of W_T: added before barrier t
+    unsigned long long *acc_next = p.acc + (size_t)((t + 1) % 3) * kAccStride;         // read during interval t-1: zeroed now
     const unsigned c_par = (unsigned)((t >> 1) & 1);
     const bool tl_cta = p.tl && t >= kTlFirst && t < kTlFirst + kTlSteps && blockIdx.x < kTlCtas;
     long long *tl_rec = tl_cta ? p.tl + 256 * 16 + ((t - kTlFirst) * kTlCtas + blockIdx.x) * kTlPerCta : nullptr;
@@ -682,7 +674,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
         c_prev = p.lambda * 2.0 * sd;
         nrm_prev = sn;
       }
-      if (blockIdx.x == 0) { acc_next[lane] = 0ull; acc_next[lane + 32] = 0ull; }   // kAccSets * 8 == 64 words
+      if (blockIdx.x == 0 && lane < 8) acc_next[lane] = 0ull;
       if (lane == 0) {
         sm.c_val[t & 1] = c_prev;
         sm.nrm_val[t & 1] = nrm_prev;
@@ -695,6 +687,28 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
       DSGD_TL(9);
     }
     double pd = 0.0, pn = 0.0;   // this thread's share of W_T . d and ||W_T||^2
+    // The CTA's partial {W_T . d, ||W_T||^2}: every warp that owns columns leaves its share in shared memory as soon as its
+    // columns are done (no waiting); update warp 0 -- idle until the barrier anyway -- sums them in warp order and adds
+    // ONE fixed-point value per CTA to the step's accumulator, well before the arrival.
+    auto publish_partial = [&]() {
+      pd = warp_sum(pd);
+      pn = warp_sum(pn);
+      if (lane == 0) {
+        sm.red[warp][0] = pd;
+        sm.red[warp][1] = pn;
+        mbar_arrive(&sm.u_bar);
+      }
+      if (warp == kCons) {
+        mbar_wait(&sm.u_bar, (unsigned)(t & 1), p.abort_flag, p.timeout_cycles);
+        if (lane == 0) {
+          double sd = 0.0, sn = 0.0;
+#pragma unroll
+          for (int i = kMulti ? 0 : kCons; i < kCons + kUpd; ++i) { sd += sm.red[i][0]; sn += sm.red[i][1]; }
+          if (sd != 0.0 || sn != 0.0) acc_push(acc_cur, sd, sn);
+        }
+        __syncwarp();
+      }
+    };
 
     if constexpr (kMulti) {
       // ---------------------------------------------------------------------------------------------------
@@ -803,6 +817,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
         }
       }
       if (warp == 0) DSGD_TL(12);
+      publish_partial();
       if (is_cons && !last) {
         const int st = (int)(t % kStages);
         auto &mt = sm.meta[st];
@@ -878,16 +893,10 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
           pn += wn * wn;
         }
         if (warp == kCons) DSGD_TL(10);
+        publish_partial();
       }
     }
 
-    // ---- grid barrier T.  Every warp that owns columns adds its share of {W_T . d, ||W_T||^2} to the fixed-point
-    //      accumulators first (integer sums: any order), well before the arrival ----
-    if (kMulti || is_upd) {
-      pd = warp_sum(pd);
-      pn = warp_sum(pn);
-      if (lane == 0 && (pd != 0.0 || pn != 0.0)) acc_push(acc_cur, pd, pn, warp);
-    }
     if (!ok) *(volatile int *)&sm.ok = 0;
     if (tl_row && lane == 0) sm.tl_warp[warp] = clock64();
     named_bar_sync(3, kSyncThreads);
@@ -925,7 +934,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
   // ---- epilogue: publish W_{base+S} as the resident weights ----------------------------------------------------
   if (blockIdx.x == 0 && warp == kCons && S > 0) {
     double sd, sn;
-    acc_read(p.acc + (size_t)(S % 3) * kAccSets * 8, lane, sd, sn);   // partials of W_S: complete at the last barrier
+    acc_read(p.acc + (size_t)(S % 3) * kAccStride, lane, sd, sn);   // partials of W_S: complete at the last barrier
     if (lane == 0) { p.scal[kScalC] = p.lambda * 2.0 * sd; p.scal[kScalNrm2] = sn; }
   }
   if constexpr (kMulti) {

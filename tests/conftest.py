@@ -4,6 +4,10 @@ import sys
 import numpy as np
 import pytest
 
+# K ranks share one GPU in tests/test_gpu_fused_one_gpu.py and their kernels must run concurrently: give the device more
+# hardware queues than streams (the default is 8; must be set before CUDA initialises)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

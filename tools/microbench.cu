@@ -148,6 +148,43 @@ __global__ void k_cluster_barrier(int iters, long long *out) {
   if (blockIdx.x == 0 && threadIdx.x == 0) *out = (t1 - t0) / iters;
 }
 
+// 8. latency of the first scattered loads AFTER a grid barrier (what a step's consumers do): every warp of the first
+//    n_warps warps issues LOADS independent 16-byte ld.cg gathers per lane from an L2-resident vector and waits for them.
+//    BAR: 0 = no barrier, 1 = release/acquire counter barrier (as shipped), 2 = relaxed barrier, 3 = barrier + every thread
+//    issued one fp64 RED before it
+template <int BAR, int LOADS>
+__global__ void k_post_barrier_load(unsigned *bar, const double2 *buf, double *redbuf, int n_addr, int n_warps, int iters,
+                                    long long *out, double *sink) {
+  __shared__ int dummy;
+  const int warp = threadIdx.x >> 5;
+  unsigned a = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u;
+  long long tot = 0;
+  double acc = 0.0;
+  for (int it = 1; it <= iters; ++it) {
+    if (BAR == 3) { a = a * 1664525u + 1013904223u; atomicAdd(&redbuf[(a >> 8) % n_addr], 1.0); }
+    __syncthreads();
+    if (BAR != 0 && threadIdx.x == 0) {
+      const unsigned target = (unsigned)it * gridDim.x;
+      if (BAR == 2) { red_relaxed_gpu_add(bar, 1u); while (ld_relaxed_gpu(bar) < target) {} }
+      else { red_release_gpu_add(bar, 1u); while (ld_relaxed_gpu(bar) < target) {} asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+      dummy = it;
+    }
+    __syncthreads();
+    if (warp < n_warps) {
+      const long long t0 = clock64();
+      double2 v[LOADS];
+#pragma unroll
+      for (int u = 0; u < LOADS; ++u) { a = a * 1664525u + 1013904223u; v[u] = __ldcg(&buf[(a >> 8) % n_addr]); }
+#pragma unroll
+      for (int u = 0; u < LOADS; ++u) acc += v[u].x + v[u].y;
+      if (acc == 12345.678) *sink = acc;     // forces the wait
+      const long long t1 = clock64();
+      tot += t1 - t0;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out = tot / iters;
+}
+
 int main() {
   int dev = 0; CK(cudaSetDevice(dev));
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, dev));
@@ -221,6 +258,24 @@ int main() {
       printf("scattered 8 B over 47236 doubles, %3d CTAs x %4d thr: RED.f64 %.3f /SM-cycle, ld.cg %.3f /SM-cycle\n", blocks, threads,
              per_sm / a, per_sm / b);
     }
+  {
+    const int G = prop.multiProcessorCount; int iters = 1000, n_addr = 47236;
+    double2 *rb; CK(cudaMalloc(&rb, sizeof(double2) * n_addr)); CK(cudaMemset(rb, 0, sizeof(double2) * n_addr));
+    auto run = [&](void *fn, int n_warps, const char *name) {
+      CK(cudaMemset(bar, 0, 1024));
+      void *args[] = {&bar, &rb, &bd, &n_addr, &n_warps, &iters, &out, &bd};
+      CK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(448), args, 0, 0)); CK(cudaDeviceSynchronize());
+      printf("post-barrier gathers, %2d warps/SM x %-28s %lld cyc until the loads are back\n", n_warps, name, *out);
+    };
+    for (int nw : {1, 8, 14}) {
+      run((void *)k_post_barrier_load<0, 1>, nw, "1 load/lane, no barrier:");
+      run((void *)k_post_barrier_load<1, 1>, nw, "1 load/lane, rel/acq barrier:");
+      run((void *)k_post_barrier_load<2, 1>, nw, "1 load/lane, relaxed barrier:");
+      run((void *)k_post_barrier_load<0, 4>, nw, "4 loads/lane, no barrier:");
+      run((void *)k_post_barrier_load<1, 4>, nw, "4 loads/lane, rel/acq barrier:");
+      run((void *)k_post_barrier_load<3, 4>, nw, "4 loads/lane, RED + barrier:");
+    }
+  }
   for (int csz : {8, 16}) {
     for (int relaxed = 0; relaxed < 2; ++relaxed) {
       void *fn = relaxed ? (void *)k_cluster_barrier<true> : (void *)k_cluster_barrier<false>;
