@@ -845,7 +845,7 @@ static persist_kernel_t persist_variant(int opt) {
 }
 // TEMPORARY A/B switch (removed once measured): bit 1 = one-pass single-chunk rows
 static int persist_opt() {
-  static const int v = getenv("DSGD_PERSIST_OPT") ? atoi(getenv("DSGD_PERSIST_OPT")) & 2 : 2;
+  static const int v = getenv("DSGD_PERSIST_OPT") ? atoi(getenv("DSGD_PERSIST_OPT")) & 3 : 2;
   return v;
 }
 static bool persist_timeline() { static const bool v = getenv("DSGD_PERSIST_TIMELINE") != nullptr; return v; }

@@ -206,6 +206,7 @@ __device__ __forceinline__ double apply_update(double wv, double graw, double c,
 // ---- grid barrier among the barrier-synchronised warps of every CTA (the producer warp stays out) -------------------
 // Called by thread 0 between two CTA-level bar.syncs: one release arrival, relaxed polling, one acquire fence.
 // Returns false if the watchdog fired.
+template <bool kAcquireFence>
 __device__ __forceinline__ bool grid_barrier_arrive_wait(unsigned *bar, unsigned target, int *abort_flag, long long timeout) {
   red_release_gpu_add(bar, 1u);
   const long long t0 = clock64();
@@ -218,7 +219,7 @@ __device__ __forceinline__ bool grid_barrier_arrive_wait(unsigned *bar, unsigned
       break;
     }
   }
-  fence_acq_rel_gpu();
+  if (kAcquireFence) fence_acq_rel_gpu();
   return ok;
 }
 
@@ -492,7 +493,7 @@ __device__ __forceinline__ unsigned consume_stage(StageMeta<kMaxChunks> &mt, con
   return hinge;
 }
 
-// kOpt: bit 1 = one-pass single-chunk rows (bit 0 unused).
+// kOpt: bit 1 = one-pass single-chunk rows; bit 0 = EXPERIMENT: no acquire fence after the barrier poll.
 template <int kCons, int kUpd, int kStages, int kStagePairs, int kMaxChunks, bool kMulti, int kOpt>
 __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(const PersistParams p) {
   using Smem = PersistSmem<kCons, kUpd, kStages, kStagePairs, kMaxChunks>;
@@ -549,7 +550,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
     load_win(load_id(1), b1, e1, y1);   // window of step t + 1  (stage B)
     int32_t id_next = load_id(2);       // sample id of step t + 2 (stage A)
     for (int64_t t = 0; t < S; ++t) {
-      const int st = (int)(t % kStages);
+      const int st = (int)t & (kStages - 1);
       if (t >= kStages) {
         mbar_wait(&sm.empty[st], (unsigned)(((t / kStages) - 1) & 1), p.abort_flag, p.timeout_cycles);
         if (*(volatile int *)p.abort_flag) return;  // the barrier-synchronised warps gave up (watchdog)
@@ -646,15 +647,21 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
     if (col_act && j_col < p.dim) { wreg[0] = __ldcg(&p.wbuf[0][j_col]); dreg[0] = __ldg(&p.d[j_col]); }
   }
 
+  // rotating buffer indices kept as small integers (64-bit % 3 per warp and step is ~100 instructions on the critical path)
+  int gi_prev = (int)((base + 2) % 3), gi_cur = (int)(base % 3), gi_next = (int)((base + 1) % 3);   // K GPUs: by global step
+  int ti_prev = 2, ti_cur = 0, ti_next = 1;                                                          // by step of this launch
   for (int64_t T = base; T <= base + S; ++T) {
     const int64_t t = T - base;
     const bool first = (t == 0), last = (t == S);
-    const double *Gprev = p.gbuf[(T + 2) % 3];   // g_{T-1}
-    double *Gcur = p.gbuf[T % 3];
-    double *Gzero = p.gbuf[(T + 1) % 3];
-    const unsigned long long *acc_prev = p.acc + (size_t)((t + 2) % 3) * kAccStride;   // partials of W_{T-1}: complete at barrier t-1
-    unsigned long long *acc_cur = p.acc + (size_t)(t % 3) * kAccStride;                // partials of W_T: added before barrier t
-    unsigned long long *acc_next = p.acc + (size_t)((t + 1) % 3) * kAccStride;         // read during interval t-1: zeroed now
+    const double *Gprev = p.gbuf[gi_prev];   // g_{T-1}
+    double *Gcur = p.gbuf[gi_cur];
+    double *Gzero = p.gbuf[gi_next];
+    const unsigned long long *acc_prev = p.acc + (size_t)ti_prev * kAccStride;   // partials of W_{T-1}: complete at barrier t-1
+    unsigned long long *acc_cur = p.acc + (size_t)ti_cur * kAccStride;           // partials of W_T: added before barrier t
+    unsigned long long *acc_next = p.acc + (size_t)ti_next * kAccStride;         // read during interval t-1: zeroed now
+    const double2 *Rprev = p.rec[ti_prev];   // one GPU: {W_{t-1}, g_{t-1}}
+    double2 *Rcur = p.rec[ti_cur];           //          {W_t (written by the updaters), g_t (RED by the consumers)}
+    double2 *Rnext = p.rec[ti_next];         //          its g half is zeroed for step t+1
     const unsigned c_par = (unsigned)((t >> 1) & 1);
     const bool tl_cta = p.tl && t >= kTlFirst && t < kTlFirst + kTlSteps && blockIdx.x < kTlCtas;
     long long *tl_rec = tl_cta ? p.tl + 256 * 16 + ((t - kTlFirst) * kTlCtas + blockIdx.x) * kTlPerCta : nullptr;
@@ -819,9 +826,9 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
       if (warp == 0) DSGD_TL(12);
       publish_partial();
       if (is_cons && !last) {
-        const int st = (int)(t % kStages);
+        const int st = (int)t & (kStages - 1);
         auto &mt = sm.meta[st];
-        mbar_wait(&sm.full[st], (unsigned)((t / kStages) & 1), p.abort_flag, p.timeout_cycles);
+        mbar_wait(&sm.full[st], (unsigned)(((unsigned)t / kStages) & 1u), p.abort_flag, p.timeout_cycles);
         if (warp == 0) DSGD_TL(1);
         FetchLL fetch{LWcur, wtag, p.abort_flag, p.timeout_cycles};
         const unsigned hinge = consume_stage<kCons, kMaxChunks, kOnePass>(mt, &sm.ring[st][0], p.pairs, Gcur, 1, fetch, warp, lane,
@@ -837,14 +844,11 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
       // ---------------------------------------------------------------------------------------------------
       // one GPU
       // ---------------------------------------------------------------------------------------------------
-      const double2 *Rprev = p.rec[(t + 2) % 3];   // {W_{t-1}, g_{t-1}}
-      double2 *Rcur = p.rec[t % 3];                // {W_t (written by the updaters), g_t (RED by the consumers)}
-      double2 *Rnext = p.rec[(t + 1) % 3];         // its g half is zeroed for step t+1
       if (is_cons) {
         if (!last) {
-          const int st = (int)(t % kStages);
+          const int st = (int)t & (kStages - 1);
           auto &mt = sm.meta[st];
-          mbar_wait(&sm.full[st], (unsigned)((t / kStages) & 1), p.abort_flag, p.timeout_cycles);
+          mbar_wait(&sm.full[st], (unsigned)(((unsigned)t / kStages) & 1u), p.abort_flag, p.timeout_cycles);
           if (warp == 0) DSGD_TL(1);
           FetchLocal fetch{Rprev, &sm.c_bar[t & 1], c_par, &sm.c_val[t & 1], p.abort_flag, p.timeout_cycles, p.k_den, lr};
           const unsigned hinge = consume_stage<kCons, kMaxChunks, kOnePass>(mt, &sm.ring[st][0], p.pairs, &Rcur[0].y, 2, fetch, warp,
@@ -921,7 +925,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
       }
       if (tl_rec) tl_rec[0] = global_ns();
       else if (tl_row) tl_row[6] = clock64();
-      bool bar_ok = grid_barrier_arrive_wait(p.bar, phase * (unsigned)G, p.abort_flag, p.timeout_cycles);
+      bool bar_ok = grid_barrier_arrive_wait<(kOpt & 1) == 0>(p.bar, phase * (unsigned)G, p.abort_flag, p.timeout_cycles);
       if (*(volatile int *)&sm.ok == 0) { *(volatile int *)p.abort_flag = 1; bar_ok = false; }
       sm.ok = bar_ok ? 1 : 0;
       if (tl_rec) tl_rec[1] = global_ns();
@@ -929,12 +933,14 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
     }
     named_bar_sync(3, kSyncThreads);
     if (*(volatile int *)&sm.ok == 0) return;
+    { const int a = gi_prev; gi_prev = gi_cur; gi_cur = gi_next; gi_next = a; }
+    { const int a = ti_prev; ti_prev = ti_cur; ti_cur = ti_next; ti_next = a; }
   }
 
   // ---- epilogue: publish W_{base+S} as the resident weights ----------------------------------------------------
   if (blockIdx.x == 0 && warp == kCons && S > 0) {
     double sd, sn;
-    acc_read(p.acc + (size_t)(S % 3) * kAccStride, lane, sd, sn);   // partials of W_S: complete at the last barrier
+    acc_read(p.acc + (size_t)ti_prev * kAccStride, lane, sd, sn);   // partials of W_S: complete at the last barrier
     if (lane == 0) { p.scal[kScalC] = p.lambda * 2.0 * sd; p.scal[kScalNrm2] = sn; }
   }
   if constexpr (kMulti) {
@@ -952,7 +958,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
       atomicAdd(&p.xstats[1], st_bm);
     }
   } else if (is_upd) {
-    const double2 *Rfin = p.rec[S % 3];
+    const double2 *Rfin = p.rec[ti_prev];
 #pragma unroll
     for (int i = 0; i < kUpdCols; ++i) {
       const int j = u0 + i * n_upd;

@@ -37,7 +37,7 @@
 
 namespace dsgd {
 
-constexpr int kStreamThreads = 768;   // 24 warps x 80 registers: room for two groups of loads per lane
+constexpr int kStreamThreads = 1024;
 constexpr int kStreamUnroll = 4;
 constexpr int kHotSlots = 2688;
 constexpr int64_t kHotMaxRows = 1 << 18;   // limb headroom: 2^18 adds of < 2^14 (resp. <= 2^12 in magnitude)
@@ -221,38 +221,33 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
     float dot_mine = 0.f;                             // this lane's row: x.w in fp32 once the row is closed
     int row0 = 0;                                     // rows closed so far (warp-uniform)
 
-    // One GROUP = kStreamUnroll slots of 32 units.  fetch_group(): where rows end inside the group (one or-reduction per
-    // slot), hence the row of each lane's unit, and the 128-bit loads.  Group g + 1 is fetched BEFORE group g is
-    // processed: two groups of loads per lane are in flight at any time (4 KB per warp, 96 KB per SM).
-    auto fetch_group = [&](int v0, int r_begin, unsigned (&ends)[kStreamUnroll], uint4 (&q)[kStreamUnroll]) -> int {
-      const unsigned pos = (unsigned)(my_end - v0);          // < 32 * kStreamUnroll iff the row ends in this group
-      const unsigned bit = 1u << (pos & 31u);
+    // One GROUP = kStreamUnroll slots of 32 units: where rows end inside the group (one or-reduction per slot), hence the
+    // row of each lane's unit, then the 128-bit loads -- all issued before the first is used (64 KB in flight per SM).
+    // (A software-prefetched form -- group g + 1 fetched before group g is processed, 768 threads x 80 registers -- was
+    // measured SLOWER: 118.9 us against 107.4 us per evaluation pass, profiles/r2_streaming.md: the lost warps cost more
+    // latency hiding than the deeper queue bought.)
+    for (int v0 = 0; v0 < total; v0 += 32 * kStreamUnroll) {
+      uint4 q[kStreamUnroll];
+      unsigned ends[kStreamUnroll];   // bit j: a row's LAST unit sits at lane j of this slot
       const bool full = v0 + 32 * kStreamUnroll <= total;
-      int r0 = r_begin;
+      {
+        const unsigned pos = (unsigned)(my_end - v0);          // < 32 * kStreamUnroll iff the row ends in this group
+        const unsigned bit = 1u << (pos & 31u);
+        int r0 = row0;
 #pragma unroll
-      for (int i = 0; i < kStreamUnroll; ++i) {
-        ends[i] = __reduce_or_sync(0xffffffffu, (pos >> 5) == (unsigned)i ? bit : 0u);
-        const int rmy = r0 + __popc(ends[i] & lt_mask);      // row of this lane's unit
-        r0 += __popc(ends[i]);
-        const uint32_t bs = __shfl_sync(0xffffffffu, base, rmy & 31);
-        if (full) {
-          q[i] = __ldg(&p.units[bs + (uint32_t)(v0 + 32 * i + lane)]);
-        } else {
-          q[i] = make_uint4(0u, 0u, 0u, 0u);  // col 0, val +0.0f
-          if (v0 + 32 * i + lane < total) q[i] = __ldg(&p.units[bs + (uint32_t)(v0 + 32 * i + lane)]);
+        for (int i = 0; i < kStreamUnroll; ++i) {
+          ends[i] = __reduce_or_sync(0xffffffffu, (pos >> 5) == (unsigned)i ? bit : 0u);
+          const int rmy = r0 + __popc(ends[i] & lt_mask);      // row of this lane's unit
+          r0 += __popc(ends[i]);
+          const uint32_t bs = __shfl_sync(0xffffffffu, base, rmy & 31);
+          if (full) {
+            q[i] = __ldg(&p.units[bs + (uint32_t)(v0 + 32 * i + lane)]);
+          } else {
+            q[i] = make_uint4(0u, 0u, 0u, 0u);  // col 0, val +0.0f
+            if (v0 + 32 * i + lane < total) q[i] = __ldg(&p.units[bs + (uint32_t)(v0 + 32 * i + lane)]);
+          }
         }
       }
-      return r0;
-    };
-    uint4 q[kStreamUnroll], qn[kStreamUnroll];
-    unsigned ends[kStreamUnroll], endsn[kStreamUnroll];   // bit j: a row's LAST unit sits at lane j of this slot
-    int r_next = 0;
-    if (total > 0) r_next = fetch_group(0, 0, ends, q);
-    for (int v0 = 0; v0 < total; v0 += 32 * kStreamUnroll) {
-      const int v1 = v0 + 32 * kStreamUnroll;
-      const bool more = v1 < total;
-      if (more) r_next = fetch_group(v1, r_next, endsn, qn);
-      const bool full = v1 <= total;
 #pragma unroll
       for (int i = 0; i < kStreamUnroll; ++i) {
         float pp = __fmaf_rn(__uint_as_float(q[i].w), ws[q[i].z], __uint_as_float(q[i].y) * ws[q[i].x]);
@@ -269,10 +264,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
           ++row0;
         }
         acc_p += (rmy == row0) ? pp : 0.f;
-      }
-      if (more) {
-#pragma unroll
-        for (int i = 0; i < kStreamUnroll; ++i) { q[i] = qn[i]; ends[i] = endsn[i]; }
       }
     }
     // ---- 32 rows decided by 32 lanes: inside the rounding band -> exact recomputation; else the sign is certain ----

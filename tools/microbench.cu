@@ -185,6 +185,87 @@ __global__ void k_post_barrier_load(unsigned *bar, const double2 *buf, double *r
   if (blockIdx.x == 0 && threadIdx.x == 0) *out = tot / iters;
 }
 
+// 9. does it matter that the gathered vector was WRITTEN (REDs / partial stores from all SMs) just before the barrier?
+//    WR: 0 = read only, 1 = every thread REDs 4 entries before the barrier, 2 = every thread stores 8 bytes into 4 entries
+template <int WR>
+__global__ void k_rw_then_gather(unsigned *bar, double2 *buf, int n_addr, int iters, long long *out, double *sink) {
+  __shared__ int dummy;
+  unsigned a = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u;
+  long long tot = 0;
+  double acc = 0.0;
+  for (int it = 1; it <= iters; ++it) {
+    if (WR) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a = a * 1664525u + 1013904223u;
+        double *q = &buf[(a >> 8) % n_addr].y;
+        if (WR == 1) asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(q), "d"(1.0) : "memory");
+        else *(volatile double *)q = 1.0;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned target = (unsigned)it * gridDim.x;
+      red_release_gpu_add(bar, 1u); while (ld_relaxed_gpu(bar) < target) {} asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      dummy = it;
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {   // 8 warps x 1 gather per lane
+      const long long t0 = clock64();
+      a = a * 1664525u + 1013904223u;
+      const double2 v = __ldcg(&buf[(a >> 8) % n_addr]);
+      acc += v.x + v.y;
+      if (acc == 12345.678) *sink = acc;
+      tot += clock64() - t0;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out = tot / iters;
+}
+
+// 10. variants of 9: WHO wrote, WHERE, how long ago, and how the gather is issued.
+//   WR 1: all SMs RED before the barrier; 3: only CTA 0 REDs (4 x 448 entries); 4: all SMs RED into the OTHER half of the
+//   vector (gathers go to the half nobody wrote)
+//   RD 0: ld.cg   1: ld.relaxed.gpu   2: atom.add.f64 of 0.0 (performed at L2)   3: ld.cg after spinning 6000 cycles
+template <int WR, int RD>
+__global__ void k_rw_variants(unsigned *bar, double2 *buf, int n_addr, int iters, long long *out, double *sink) {
+  __shared__ int dummy;
+  unsigned a = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u;
+  long long tot = 0;
+  double acc = 0.0;
+  const int half = n_addr / 2;
+  for (int it = 1; it <= iters; ++it) {
+    if (WR == 1 || WR == 4 || (WR == 3 && blockIdx.x == 0)) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a = a * 1664525u + 1013904223u;
+        const int idx = (WR == 4) ? half + (int)((a >> 8) % half) : (int)((a >> 8) % half);
+        asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(&buf[idx].y), "d"(1.0) : "memory");
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned target = (unsigned)it * gridDim.x;
+      red_release_gpu_add(bar, 1u); while (ld_relaxed_gpu(bar) < target) {} asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      dummy = it;
+    }
+    __syncthreads();
+    if (RD == 3) { const long long w0 = clock64(); while (clock64() - w0 < 6000) {} }
+    if (threadIdx.x < 256) {
+      const long long t0 = clock64();
+      a = a * 1664525u + 1013904223u;
+      const double2 *q = &buf[(a >> 8) % half];
+      double2 v;
+      if (RD == 1) asm volatile("ld.relaxed.gpu.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(q) : "memory");
+      else if (RD == 2) { asm volatile("atom.relaxed.gpu.global.add.f64 %0, [%1], %2;" : "=d"(v.x) : "l"(&q->x), "d"(0.0) : "memory"); v.y = 0.0; }
+      else v = __ldcg(q);
+      acc += v.x + v.y;
+      if (acc == 12345.678) *sink = acc;
+      tot += clock64() - t0;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out = tot / iters;
+}
+
 int main() {
   int dev = 0; CK(cudaSetDevice(dev));
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, dev));
@@ -275,6 +356,25 @@ int main() {
       run((void *)k_post_barrier_load<1, 4>, nw, "4 loads/lane, rel/acq barrier:");
       run((void *)k_post_barrier_load<3, 4>, nw, "4 loads/lane, RED + barrier:");
     }
+  }
+  {
+    const int G = prop.multiProcessorCount; int iters = 1000, n_addr = 47236;
+    double2 *rb; CK(cudaMalloc(&rb, sizeof(double2) * n_addr)); CK(cudaMemset(rb, 0, sizeof(double2) * n_addr));
+    auto run = [&](void *fn, const char *name) {
+      CK(cudaMemset(bar, 0, 1024));
+      void *args[] = {&bar, &rb, &n_addr, &iters, &out, &bd};
+      CK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(448), args, 0, 0)); CK(cudaDeviceSynchronize());
+      printf("gather (8 warps x 1 per lane) after the barrier, vector %-36s %lld cyc\n", name, *out);
+    };
+    run((void *)k_rw_then_gather<0>, "read-only:");
+    run((void *)k_rw_then_gather<1>, "RED into by every thread before:");
+    run((void *)k_rw_then_gather<2>, "stored into by every thread before:");
+    run((void *)k_rw_variants<1, 0>, "[half] RED by all, ld.cg:");
+    run((void *)k_rw_variants<3, 0>, "[half] RED by CTA 0 only, ld.cg:");
+    run((void *)k_rw_variants<4, 0>, "[half] RED by all into the OTHER half:");
+    run((void *)k_rw_variants<1, 1>, "[half] RED by all, ld.relaxed.gpu:");
+    run((void *)k_rw_variants<1, 2>, "[half] RED by all, atom.add 0.0:");
+    run((void *)k_rw_variants<1, 3>, "[half] RED by all, 6000 cycles later:");
   }
   for (int csz : {8, 16}) {
     for (int relaxed = 0; relaxed < 2; ++relaxed) {
