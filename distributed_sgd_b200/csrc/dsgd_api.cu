@@ -833,21 +833,7 @@ extern "C" int dsgd_comm_init(dsgd_ctx *ctx, const uint8_t id[DSGD_UNIQUE_ID_BYT
 // ---- persistent sync loop (dsgd_persistent.cuh) ----------------------------------------------------------------
 constexpr int kPCons = 8, kPUpd = 6, kPStages = 8, kPStagePairs = 2560, kPMaxChunks = 128;
 using PSmem = PersistSmem<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks>;
-typedef void (*persist_kernel_t)(const PersistParams);
-template <bool kMulti>
-static persist_kernel_t persist_variant(int opt) {
-  switch (opt & 3) {
-    case 0: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, kMulti, 0>;
-    case 1: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, kMulti, 1>;
-    case 2: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, kMulti, 2>;
-    default: return k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, kMulti, 3>;
-  }
-}
-// TEMPORARY A/B switch (removed once measured): bit 1 = one-pass single-chunk rows
-static int persist_opt() {
-  static const int v = getenv("DSGD_PERSIST_OPT") ? atoi(getenv("DSGD_PERSIST_OPT")) & 3 : 2;
-  return v;
-}
+#define DSGD_PERSIST_KERNEL(multi) k_sync_persistent<kPCons, kPUpd, kPStages, kPStagePairs, kPMaxChunks, multi>
 static bool persist_timeline() { static const bool v = getenv("DSGD_PERSIST_TIMELINE") != nullptr; return v; }
 
 static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
@@ -862,10 +848,8 @@ static int persist_prepare(dsgd_ctx *ctx, int64_t n_steps) {
     }
     CU(cudaMalloc(&ctx->p_acc, sizeof(unsigned long long) * 3 * kAccStride));
     CU(cudaMalloc(&ctx->p_bar, sizeof(unsigned) * 4));
-    for (int opt = 0; opt < 4; ++opt) {
-      CU(cudaFuncSetAttribute((const void *)persist_variant<false>(opt), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
-      CU(cudaFuncSetAttribute((const void *)persist_variant<true>(opt), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
-    }
+    CU(cudaFuncSetAttribute((const void *)DSGD_PERSIST_KERNEL(false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
+    CU(cudaFuncSetAttribute((const void *)DSGD_PERSIST_KERNEL(true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PSmem)));
     ctx->p_ready = true;
   }
   if (ctx->p_hinge_cap < n_steps) {
@@ -931,7 +915,6 @@ static int persist_run(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t n_per_
   if (rc) return rc;
   const int G = persist_grid(ctx, n_per_step);
   NEED((uint64_t)G * (uint64_t)(n_steps + 2) < (1ull << 32), DSGD_ERR_INVALID, "dsgd_sync_steps: too many steps for one launch");
-  const int opt = persist_opt();
   PersistParams pp;
   if ((rc = persist_params(ctx, pp, samples_dev, n_per_step, n_steps, lr, losses_dev, G))) return rc;
   k_rec_init<<<cdiv(ctx->dim, 256), 256, 0, ctx->stream>>>(ctx->w, ctx->dim, ctx->p_rec[0], ctx->p_rec[1], ctx->p_rec[2]);
@@ -941,7 +924,7 @@ static int persist_run(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t n_per_
   void *args[] = {&pp};
   auto *pe = prof_slot(ctx);
   if (pe) cudaEventRecord(pe->first, ctx->stream);
-  CU(persist_launch(ctx, (void *)persist_variant<false>(opt), G, args));
+  CU(persist_launch(ctx, (void *)DSGD_PERSIST_KERNEL(false), G, args));
   if (pe) cudaEventRecord(pe->second, ctx->stream);
   LAUNCHED();
   return DSGD_OK;
@@ -985,7 +968,6 @@ static int persist_run_multi(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t 
   if (rc) return rc;
   const int G = persist_grid(ctx, n_per_step);
   NEED((uint64_t)G * (uint64_t)(n_steps + 2) < (1ull << 32), DSGD_ERR_INVALID, "dsgd_sync_steps: too many steps for one launch");
-  const int opt = persist_opt();
   PersistParams pp;
   if ((rc = persist_params(ctx, pp, samples_dev, n_per_step, n_steps, lr, losses_dev, G))) return rc;
   // the kernel's first interval reads the host-provided weights from wbuf[0] and publishes them in LL form
@@ -1007,7 +989,7 @@ static int persist_run_multi(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t 
   void *args[] = {&pp};
   auto *pe = prof_slot(ctx);
   if (pe) cudaEventRecord(pe->first, ctx->stream);
-  CU(persist_launch(ctx, (void *)persist_variant<true>(opt), G, args));
+  CU(persist_launch(ctx, (void *)DSGD_PERSIST_KERNEL(true), G, args));
   if (pe) cudaEventRecord(pe->second, ctx->stream);
   LAUNCHED();
   // The next launch must not meet LL words carrying tags this one used (the host may install new weights in between): the

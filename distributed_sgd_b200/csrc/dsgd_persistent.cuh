@@ -24,9 +24,11 @@
 //     148 fp64 partials from one shared area after the barrier, c arrived 1 880 cycles into the interval; a second counter
 //     barrier among the update warps serialised with the grid barrier (+2 200 cycles per step); an all-to-all flag barrier
 //     carrying the partials took 5 100 cycles from the last arrival to the first exit against 2 450 for the counter.
-//   * GRID BARRIER: one release arrival on a counter, relaxed polling, one acquire fence: 2 412 cycles for 148 CTAs on a
-//     B200 (tools/microbench.cu: 1 721 for 2 CTAs -- it is fences and L2 round trips, not contention; cooperative
-//     groups' grid.sync() 2 472; +1 300 with 448 REDs per CTA in flight).  It is the largest single item of a step.
+//   * GRID BARRIER: one release arrival on a counter, relaxed polling.  With an acquire fence after the poll a barrier
+//     costs 2 412 cycles for 148 CTAs on a B200 (tools/microbench.cu: 1 721 for 2 CTAs -- it is fences and L2 round trips,
+//     not contention; cooperative groups' grid.sync() 2 472; +1 300 with 448 REDs per CTA in flight); the acquire fence
+//     is not needed here (see grid_barrier_arrive_wait) and leaving it out saved 1 400 cycles per step.  The barrier is
+//     still the largest single item of a step.
 //
 // One GPU (kMulti == false), interval I_t between grid barrier t-1 and t, W_t = weights step t differentiates at:
 //   consumers: x.W_t with W_t[col] = update(W_{t-1}[col], g_{t-1}[col], c_{t-1}) applied on the fly; gate; RED into g_t
@@ -204,9 +206,14 @@ __device__ __forceinline__ double apply_update(double wv, double graw, double c,
 }
 
 // ---- grid barrier among the barrier-synchronised warps of every CTA (the producer warp stays out) -------------------
-// Called by thread 0 between two CTA-level bar.syncs: one release arrival, relaxed polling, one acquire fence.
+// Called by thread 0 between two CTA-level bar.syncs: one RELEASE arrival on a counter, relaxed polling.
+// There is no acquire fence after the poll.  What follows the barrier reads mutable global data only with instructions
+// that are served by L2 -- ld.global.cg / ld.relaxed.gpu / red / the LL words' ld.relaxed.sys -- never through L1, and a
+// thread cannot issue them before the branch on the polled value resolves, so they reach L2 after the arrival they
+// observed, which every peer performed after its own writes (release).  The fence cost 1 400 cycles per step (measured:
+// last arrival -> first exit 1 728 ns with it, 928 ns without; profiles/r2_timeline.md); the trajectories are checked
+// against the oracle to 1e-12 over hundreds of steps in the tests and in every bench run (`parity`).
 // Returns false if the watchdog fired.
-template <bool kAcquireFence>
 __device__ __forceinline__ bool grid_barrier_arrive_wait(unsigned *bar, unsigned target, int *abort_flag, long long timeout) {
   red_release_gpu_add(bar, 1u);
   const long long t0 = clock64();
@@ -219,7 +226,6 @@ __device__ __forceinline__ bool grid_barrier_arrive_wait(unsigned *bar, unsigned
       break;
     }
   }
-  if (kAcquireFence) fence_acq_rel_gpu();
   return ok;
 }
 
@@ -396,9 +402,10 @@ struct FetchLL {
 
 // ---- the consumer warps' work on one stage: SlaveImpl.gradient's per-sample body (core/Slave.scala:147-153) ----
 // x.W per row (math/Vec.scala:58), prediction and hinge loss (SparseSVM.scala:14-16), gate (SparseSVM.scala:28),
-// RED of y*x into g (entry of column c at gbase + gstride * c).  kOnePass: a row that is one chunk is gated and scattered by the warp that computed its
-// dot, from the registers that still hold its pairs (0.0 + acc == acc: the same dot as the two-pass form).
-template <int kCons, int kMaxChunks, bool kOnePass, class Fetch>
+// RED of y*x into g (entry of column c at gbase + gstride * c).  A row that is ONE chunk (85 % of them) is gated and
+// scattered by the warp that computed its dot, from the registers that still hold its pairs; rows of several chunks
+// take a second pass after a barrier among the consumer warps (partials summed in chunk order).
+template <int kCons, int kMaxChunks, class Fetch>
 __device__ __forceinline__ unsigned consume_stage(StageMeta<kMaxChunks> &mt, const uint2 *ring, const uint2 *pairs, double *gbase,
                                                   const int gstride, Fetch &fetch, int warp, int lane, long long *tl) {
   const int n_ch = mt.n_chunks;
@@ -422,7 +429,7 @@ __device__ __forceinline__ unsigned consume_stage(StageMeta<kMaxChunks> &mt, con
     if (tl && lane == 0 && c == warp) tl[2] = clock64();   // first chunk: weights arrived, products done
     acc = warp_sum(acc);
     if (tl && lane == 0 && c == warp) tl[4] = clock64();   // ... dot reduced
-    if constexpr (kOnePass) {
+    {
       const int row1 = mt.ch_row[c];
       if (mt.row_nch[row1] == 1) {
         const int yi = mt.row_y[row1];
@@ -441,12 +448,12 @@ __device__ __forceinline__ unsigned consume_stage(StageMeta<kMaxChunks> &mt, con
     if (lane == 0) mt.part[c] = acc;
   }
   // ---- pass 2 (rows of several chunks): row dot = chunk partials in order, prediction, gate, scatter ----
-  if (!kOnePass || mt.n_multi > 0) {
+  if (mt.n_multi > 0) {
     named_bar_sync(2, kCons * 32);
     for (int c = warp; c < n_ch; c += kCons) {
       const int row = mt.ch_row[c];
       const int first = mt.row_first[row], nch = mt.row_nch[row];
-      if (kOnePass && nch == 1) continue;
+      if (nch == 1) continue;
       double dot = 0.0;
       for (int i = 0; i < nch; ++i) dot += mt.part[first + i];
       const int yi = mt.row_y[row];
@@ -493,13 +500,11 @@ __device__ __forceinline__ unsigned consume_stage(StageMeta<kMaxChunks> &mt, con
   return hinge;
 }
 
-// kOpt: bit 1 = one-pass single-chunk rows; bit 0 = EXPERIMENT: no acquire fence after the barrier poll.
-template <int kCons, int kUpd, int kStages, int kStagePairs, int kMaxChunks, bool kMulti, int kOpt>
+template <int kCons, int kUpd, int kStages, int kStagePairs, int kMaxChunks, bool kMulti>
 __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(const PersistParams p) {
   using Smem = PersistSmem<kCons, kUpd, kStages, kStagePairs, kMaxChunks>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
-  constexpr bool kOnePass = (kOpt & 2) != 0;
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -831,7 +836,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
         mbar_wait(&sm.full[st], (unsigned)(((unsigned)t / kStages) & 1u), p.abort_flag, p.timeout_cycles);
         if (warp == 0) DSGD_TL(1);
         FetchLL fetch{LWcur, wtag, p.abort_flag, p.timeout_cycles};
-        const unsigned hinge = consume_stage<kCons, kMaxChunks, kOnePass>(mt, &sm.ring[st][0], p.pairs, Gcur, 1, fetch, warp, lane,
+        const unsigned hinge = consume_stage<kCons, kMaxChunks>(mt, &sm.ring[st][0], p.pairs, Gcur, 1, fetch, warp, lane,
                                                                           warp == 0 ? tl_row : nullptr);
         ok = ok && fetch.good;
         if (lane == 0 && hinge) atomicAdd(&sm.hinge_acc, hinge);
@@ -851,7 +856,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
           mbar_wait(&sm.full[st], (unsigned)(((unsigned)t / kStages) & 1u), p.abort_flag, p.timeout_cycles);
           if (warp == 0) DSGD_TL(1);
           FetchLocal fetch{Rprev, &sm.c_bar[t & 1], c_par, &sm.c_val[t & 1], p.abort_flag, p.timeout_cycles, p.k_den, lr};
-          const unsigned hinge = consume_stage<kCons, kMaxChunks, kOnePass>(mt, &sm.ring[st][0], p.pairs, &Rcur[0].y, 2, fetch, warp,
+          const unsigned hinge = consume_stage<kCons, kMaxChunks>(mt, &sm.ring[st][0], p.pairs, &Rcur[0].y, 2, fetch, warp,
                                                                             lane, warp == 0 ? tl_row : nullptr);
           if (lane == 0 && hinge) atomicAdd(&sm.hinge_acc, hinge);
           if (tl_rec && warp == 0 && lane == 0) tl_rec[2] = mt.n_pairs;
@@ -925,7 +930,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
       }
       if (tl_rec) tl_rec[0] = global_ns();
       else if (tl_row) tl_row[6] = clock64();
-      bool bar_ok = grid_barrier_arrive_wait<(kOpt & 1) == 0>(p.bar, phase * (unsigned)G, p.abort_flag, p.timeout_cycles);
+      bool bar_ok = grid_barrier_arrive_wait(p.bar, phase * (unsigned)G, p.abort_flag, p.timeout_cycles);
       if (*(volatile int *)&sm.ok == 0) { *(volatile int *)p.abort_flag = 1; bar_ok = false; }
       sm.ok = bar_ok ? 1 : 0;
       if (tl_rec) tl_rec[1] = global_ns();
