@@ -16,7 +16,6 @@
 #include "dsgd_kernels.cuh"
 #include "dsgd_persistent.cuh"
 #include "dsgd_stream.cuh"
-#include "dsgd_stream_v1.cuh"
 #include "dsgd_async.cuh"
 #include <cstdlib>
 
@@ -76,10 +75,6 @@ struct dsgd_ctx {
   unsigned *p_hinge = nullptr;
   int64_t p_hinge_cap = 0;
   unsigned *p_bar = nullptr;   // [0]: grid barrier counter, [1]: abort flag
-  uint32_t *hot_bits = nullptr;     // hot-column bitmap / slot prefix / slot -> column of the streaming scatter (dsgd_stream.cuh)
-  uint16_t *hot_prefix = nullptr;
-  int32_t *hot_cols = nullptr;
-  int n_hot = 0;
   bool p_ready = false;
   long long *p_tl = nullptr;   // debug timeline (DSGD_PERSIST_TIMELINE)
 
@@ -289,7 +284,7 @@ extern "C" int dsgd_destroy(dsgd_ctx *ctx) {
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   void *ptrs[] = {ctx->rp16, ctx->pairs, ctx->label, ctx->yabs, ctx->w, ctx->g, ctx->d, ctx->w_req, ctx->w32, ctx->w32_req, ctx->n_exact, ctx->scal,
                   ctx->cnt, ctx->partial, ctx->out2, ctx->gsum, ctx->p_wbuf[0], ctx->p_wbuf[1], ctx->p_gbuf[0],
-                  ctx->p_gbuf[1], ctx->p_gbuf[2], ctx->p_rec[0], ctx->p_rec[1], ctx->p_rec[2], ctx->p_acc, ctx->p_hinge, ctx->p_bar, ctx->x_stats, ctx->hot_bits, ctx->hot_prefix, ctx->hot_cols, ctx->samples,
+                  ctx->p_gbuf[1], ctx->p_gbuf[2], ctx->p_rec[0], ctx->p_rec[1], ctx->p_rec[2], ctx->p_acc, ctx->p_hinge, ctx->p_bar, ctx->x_stats, ctx->samples,
                   ctx->losses, ctx->preds};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -577,122 +572,38 @@ static inline int rows_grid(const dsgd_ctx *ctx, int64_t n) {
 constexpr int64_t kStreamMinRows = 2048;
 
 static bool stream_eligible(const dsgd_ctx *ctx, int64_t n) {
-  return n >= kStreamMinRows && stream_smem_bytes(ctx->dim, false) + 1024 <= 227u * 1024u;
-}
-
-// TEMPORARY A/B switches of round 2's first GPU session (removed once measured): DSGD_STREAM_V1=1 runs round 1's kernel,
-// DSGD_STREAM_HOT=1 turns the hot-column accumulators of the scatter on.
-static bool stream_use_v1() { static const bool v = getenv("DSGD_STREAM_V1") != nullptr; return v; }
-static bool stream_use_hot() { static const bool v = getenv("DSGD_STREAM_HOT") && atoi(getenv("DSGD_STREAM_HOT")) != 0; return v; }
-
-// the kHotSlots most frequent columns (over all loaded rows) get a shared-memory slot: bitmap, per-word slot prefix and
-// slot -> column list, built once on the host from the column histogram
-static int stream_hot_prepare(dsgd_ctx *ctx) {
-  if (ctx->hot_bits) return DSGD_OK;
-  unsigned *df = nullptr;
-  CU(cudaMalloc(&df, sizeof(unsigned) * (size_t)ctx->dim));
-  CU(cudaMemsetAsync(df, 0, sizeof(unsigned) * (size_t)ctx->dim, ctx->stream));
-  if (ctx->n_pairs > 0) {
-    const int blocks = (int)std::min<int64_t>(cdiv(ctx->n_pairs, 256), (int64_t)ctx->sm_count * 16);
-    k_col_hist<<<blocks, 256, 0, ctx->stream>>>(ctx->pairs, ctx->n_pairs, df);
-    LAUNCHED();
-  }
-  std::vector<unsigned> hist((size_t)ctx->dim);
-  CU(cudaMemcpyAsync(hist.data(), df, sizeof(unsigned) * (size_t)ctx->dim, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaFree(df));
-  std::vector<int32_t> order((size_t)ctx->dim);
-  for (int j = 0; j < ctx->dim; ++j) order[(size_t)j] = j;
-  const size_t n_hot = std::min<size_t>((size_t)kHotSlots, (size_t)ctx->dim);
-  std::partial_sort(order.begin(), order.begin() + (ptrdiff_t)n_hot, order.end(),
-                    [&](int32_t a, int32_t b) { return hist[(size_t)a] != hist[(size_t)b] ? hist[(size_t)a] > hist[(size_t)b] : a < b; });
-  const size_t words = ((size_t)ctx->dim + 31) / 32;
-  std::vector<uint32_t> bits(words, 0u);
-  for (size_t i = 0; i < n_hot; ++i)
-    if (hist[(size_t)order[i]] > 0) bits[(size_t)order[i] >> 5] |= 1u << (order[i] & 31);
-  std::vector<uint16_t> prefix(words);
-  std::vector<int32_t> cols;
-  for (size_t wd = 0; wd < words; ++wd) {
-    prefix[wd] = (uint16_t)cols.size();
-    for (int b = 0; b < 32; ++b)
-      if (bits[wd] >> b & 1u) cols.push_back((int32_t)(wd * 32 + (size_t)b));   // slot order = column order
-  }
-  const int n = (int)cols.size();
-  if (cols.empty()) cols.push_back(0);
-  CU(cudaMalloc(&ctx->hot_bits, sizeof(uint32_t) * words));
-  CU(cudaMalloc(&ctx->hot_prefix, sizeof(uint16_t) * words));
-  CU(cudaMalloc(&ctx->hot_cols, sizeof(int32_t) * cols.size()));
-  CU(cudaMemcpy(ctx->hot_bits, bits.data(), sizeof(uint32_t) * words, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(ctx->hot_prefix, prefix.data(), sizeof(uint16_t) * words, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(ctx->hot_cols, cols.data(), sizeof(int32_t) * cols.size(), cudaMemcpyHostToDevice));
-  ctx->n_hot = n;
-  return DSGD_OK;
-}
-
-template <bool kScatter, bool kPreds>
-static int stream_launch_v1(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t row_begin, int64_t n, const double *w_dev,
-                            const float *w32_dev, double *g, double *preds) {
-  const size_t smem = (size_t)ctx->dim * sizeof(float);
-  CU(cudaFuncSetAttribute(k_stream_rows_v1<kScatter, kPreds>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  StreamParamsV1 sp;
-  sp.rp16 = ctx->rp16; sp.units = reinterpret_cast<const uint4 *>(ctx->pairs); sp.label = ctx->label;
-  sp.samples = samples_dev; sp.row_begin = row_begin; sp.n = n; sp.w = w_dev; sp.w32 = w32_dev; sp.dim = ctx->dim;
-  sp.g = g; sp.preds = preds; sp.cnt = ctx->cnt; sp.n_exact = ctx->n_exact; sp.next_block = ctx->n_exact + 1;
-  CU(cudaMemsetAsync(ctx->n_exact + 1, 0, sizeof(unsigned long long), ctx->stream));
-  const int64_t blocks32 = (n + 31) / 32;
-  const int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, cdiv(blocks32, kStreamThreadsV1 / 32)));
-  auto *pe = prof_slot(ctx);
-  if (pe) cudaEventRecord(pe->first, ctx->stream);
-  k_stream_rows_v1<kScatter, kPreds><<<grid, kStreamThreadsV1, smem, ctx->stream>>>(sp);
-  if (pe) cudaEventRecord(pe->second, ctx->stream);
-  LAUNCHED();
-  CU(cudaGetLastError());
-  return DSGD_OK;
+  return n >= kStreamMinRows && stream_smem_bytes(ctx->dim) + 1024 <= 227u * 1024u;
 }
 
 template <bool kScatter, bool kPreds>
 static int stream_launch(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t row_begin, int64_t n, const double *w_dev,
                          const float *w32_dev, double *g, double *preds) {
-  if (stream_use_v1()) return stream_launch_v1<kScatter, kPreds>(ctx, samples_dev, row_begin, n, w_dev, w32_dev, g, preds);
-  const bool hot = kScatter && stream_use_hot() && stream_smem_bytes(ctx->dim, true) + 256 <= 227u * 1024u;
+  const size_t smem = stream_smem_bytes(ctx->dim);
   if (!ctx->stream_ready) {
-    CU(cudaFuncSetAttribute(k_stream_rows<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem_bytes(ctx->dim, false)));
-    CU(cudaFuncSetAttribute(k_stream_rows<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem_bytes(ctx->dim, false)));
-    CU(cudaFuncSetAttribute(k_stream_rows<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem_bytes(ctx->dim, false)));
-    if (stream_smem_bytes(ctx->dim, true) + 256 <= 227u * 1024u)
-      CU(cudaFuncSetAttribute(k_stream_rows<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem_bytes(ctx->dim, true)));
+    CU(cudaFuncSetAttribute(k_stream_rows<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k_stream_rows<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k_stream_rows<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ctx->stream_ready = true;
   }
-  if (hot) {
-    int rc = stream_hot_prepare(ctx);
-    if (rc) return rc;
-  }
-  // a launch of the hot-column variant covers at most kHotMaxRows rows (limb headroom of the fixed-point slots)
-  const int64_t max_rows = hot ? kHotMaxRows : n;
-  for (int64_t off = 0; off < n; off += max_rows) {
-    const int64_t m = std::min<int64_t>(max_rows, n - off);
-    StreamParams sp;
-    memset(&sp, 0, sizeof sp);
-    sp.rp16 = ctx->rp16; sp.units = reinterpret_cast<const uint4 *>(ctx->pairs); sp.yabs = ctx->yabs;
-    sp.samples = samples_dev ? samples_dev + off : nullptr; sp.row_begin = row_begin + off; sp.n = m;
-    sp.w = w_dev; sp.w32 = w32_dev; sp.dim = ctx->dim;
-    sp.g = g; sp.preds = preds ? preds + off : nullptr; sp.cnt = ctx->cnt; sp.n_exact = ctx->n_exact; sp.next_block = ctx->n_exact + 1;
-    sp.hot_bits = ctx->hot_bits; sp.hot_prefix = ctx->hot_prefix; sp.hot_cols = ctx->hot_cols; sp.n_hot = ctx->n_hot;
-    CU(cudaMemsetAsync(ctx->n_exact + 1, 0, sizeof(unsigned long long), ctx->stream));
-    // rows per block (the unit of the dynamic work distribution): 32, or fewer when that leaves a warp fewer than ~6 blocks
-    const int64_t n_warps_all = (int64_t)ctx->sm_count * (kStreamThreads / 32);
-    sp.rows_log2 = 5;
-    while (sp.rows_log2 > 3 && ((m + (1 << sp.rows_log2) - 1) >> sp.rows_log2) < 6 * n_warps_all) --sp.rows_log2;
-    const int64_t n_blk = (m + (1 << sp.rows_log2) - 1) >> sp.rows_log2;
-    const int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, cdiv(n_blk, kStreamThreads / 32)));
-    auto *pe = prof_slot(ctx);
-    if (pe) cudaEventRecord(pe->first, ctx->stream);
-    if (kScatter && hot) k_stream_rows<kScatter, kPreds, kScatter><<<grid, kStreamThreads, stream_smem_bytes(ctx->dim, true), ctx->stream>>>(sp);
-    else k_stream_rows<kScatter, kPreds, false><<<grid, kStreamThreads, stream_smem_bytes(ctx->dim, false), ctx->stream>>>(sp);
-    if (pe) cudaEventRecord(pe->second, ctx->stream);
-    LAUNCHED();
-    CU(cudaGetLastError());
-  }
+  StreamParams sp;
+  memset(&sp, 0, sizeof sp);
+  sp.rp16 = ctx->rp16; sp.units = reinterpret_cast<const uint4 *>(ctx->pairs); sp.yabs = ctx->yabs;
+  sp.samples = samples_dev; sp.row_begin = row_begin; sp.n = n;
+  sp.w = w_dev; sp.w32 = w32_dev; sp.dim = ctx->dim;
+  sp.g = g; sp.preds = preds; sp.cnt = ctx->cnt; sp.n_exact = ctx->n_exact; sp.next_block = ctx->n_exact + 1;
+  CU(cudaMemsetAsync(ctx->n_exact + 1, 0, sizeof(unsigned long long), ctx->stream));
+  // rows per block (the unit of the dynamic work distribution): 32, or fewer when that leaves a warp fewer than ~6 blocks
+  const int64_t n_warps_all = (int64_t)ctx->sm_count * (kStreamThreads / 32);
+  sp.rows_log2 = 5;
+  while (sp.rows_log2 > 3 && ((n + (1 << sp.rows_log2) - 1) >> sp.rows_log2) < 6 * n_warps_all) --sp.rows_log2;
+  const int64_t n_blk = (n + (1 << sp.rows_log2) - 1) >> sp.rows_log2;
+  const int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, cdiv(n_blk, kStreamThreads / 32)));
+  auto *pe = prof_slot(ctx);
+  if (pe) cudaEventRecord(pe->first, ctx->stream);
+  k_stream_rows<kScatter, kPreds><<<grid, kStreamThreads, smem, ctx->stream>>>(sp);
+  if (pe) cudaEventRecord(pe->second, ctx->stream);
+  LAUNCHED();
+  CU(cudaGetLastError());
   return DSGD_OK;
 }
 

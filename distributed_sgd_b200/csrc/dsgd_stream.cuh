@@ -25,10 +25,11 @@
 //     recomputed with the fp64 weights from L2 after the block's stream, so every prediction and gate decision is
 //     that of the fp64 arithmetic (tests/test_gpu_parity.py::test_streaming_exact_fallback_decides_like_fp64).
 //   * Scatter (gradient): rows that pass the gate are re-walked after the block's stream (their units are in
-//     L1/L2) and y*x goes to g with fp64 REDs.  kHot: the kHotSlots most frequent columns get a per-CTA exact
-//     fixed-point accumulator in the shared memory left beside the weights (three 32-bit limbs of g * 2^40; shared
-//     memory has native 32-bit atomics only), flushed with one RED per touched slot: the RED rate at L2
-//     (0.48 per SM-cycle, tools/microbench.cu) is what bounds a large-batch gradient on untrained weights.
+//     L1/L2) and y*x goes to g with fp64 REDs.  On trained weights few rows pass (the misclassified ones) and the pass
+//     runs at the streaming rate; on untrained weights every row passes and the fp64 RED rate at L2 bounds it
+//     (0.45 per SM-cycle, tools/microbench.cu).  Per-CTA fixed-point accumulators in shared memory for the most
+//     frequent columns were measured and dropped: 162 -> 160 us on 262 144 rows, 58 -> 64 us on 65 536
+//     (profiles/r2_streaming.md).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -39,8 +40,6 @@ namespace dsgd {
 
 constexpr int kStreamThreads = 1024;
 constexpr int kStreamUnroll = 4;
-constexpr int kHotSlots = 2688;
-constexpr int64_t kHotMaxRows = 1 << 18;   // limb headroom: 2^18 adds of < 2^14 (resp. <= 2^12 in magnitude)
 
 struct StreamParams {
   const uint32_t *rp16;
@@ -58,19 +57,11 @@ struct StreamParams {
   unsigned long long *next_block;  // work counter (zero on entry): blocks beyond the first wave are claimed dynamically
   int rows_log2;               // rows per block = 1 << rows_log2 (5, 4 or 3): the host picks it so that every warp gets
                                // several blocks (a block is the unit of the dynamic work distribution)
-  const uint32_t *hot_bits;    // kHot: bit c set = column c has a shared-memory accumulator slot
-  const uint16_t *hot_prefix;  //       slots before word c >> 5 (slot = prefix + popc of the lower bits of the word)
-  const int32_t *hot_cols;     //       slot -> column
-  int n_hot;                   //       slots in use (<= kHotSlots)
 };
 
-__host__ __device__ constexpr size_t stream_smem_bytes(int dim, bool hot) {
-  const size_t ws = (((size_t)dim + 3) & ~(size_t)3) * sizeof(float);
-  const size_t words = ((size_t)dim + 31) / 32;
-  return hot ? ws + (size_t)kHotSlots * 12 + words * 4 + ((words * 2 + 15) & ~(size_t)15) : ws;
-}
+__host__ __device__ constexpr size_t stream_smem_bytes(int dim) { return (((size_t)dim + 3) & ~(size_t)3) * sizeof(float); }
 
-template <bool kScatter, bool kPreds, bool kHot>
+template <bool kScatter, bool kPreds>
 __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *ws = reinterpret_cast<float *>(smem_raw);
@@ -99,50 +90,15 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
     for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
     if (lane == 0) s_wmax[warp] = wmax;
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0ull;
-    if constexpr (kHot) {
-      const int words = (p.dim + 31) >> 5;
-      uint32_t *acc = reinterpret_cast<uint32_t *>(ws + ((p.dim + 3) & ~3));
-      uint32_t *hb = acc + 3 * kHotSlots;
-      uint16_t *hp = reinterpret_cast<uint16_t *>(hb + words);
-      for (int i = threadIdx.x; i < 3 * kHotSlots; i += kStreamThreads) acc[i] = 0u;
-      for (int i = threadIdx.x; i < words; i += kStreamThreads) { hb[i] = __ldg(&p.hot_bits[i]); hp[i] = __ldg(&p.hot_prefix[i]); }
-    }
     __syncthreads();
     wmax = 0.f;
 #pragma unroll
     for (int i = 0; i < kStreamThreads / 32; ++i) wmax = fmaxf(wmax, s_wmax[i]);
   }
   const float band_scale = 1.5f * 5.9604645e-8f * wmax;   // 1.5 * 2^-24 * max|w|
-  uint32_t *hot_acc = nullptr;
-  const uint32_t *hot_bits = nullptr;
-  const uint16_t *hot_prefix = nullptr;
-  if constexpr (kHot) {
-    hot_acc = reinterpret_cast<uint32_t *>(ws + ((p.dim + 3) & ~3));
-    hot_bits = hot_acc + 3 * kHotSlots;
-    hot_prefix = reinterpret_cast<const uint16_t *>(hot_bits + ((p.dim + 31) >> 5));
-  }
-  // one gradient entry: into the CTA's fixed-point slot if the column has one and the value is exactly representable
+  // one gradient entry (SparseSVM.scala:26-29): a reduction without a return value
   auto scatter_one = [&](uint32_t col, double gv) {
-    if (gv == 0.0) return;
-    if constexpr (kHot) {
-      const uint32_t bits = hot_bits[col >> 5], bit = 1u << (col & 31);
-      if (bits & bit) {
-        const double sv = gv * 1099511627776.0;  // 2^40: exact scaling
-        if (fabs(sv) <= 1099511627776.0) {
-          const long long iv = __double2ll_rn(sv);
-          if ((double)iv == sv) {
-            const uint32_t slot = (uint32_t)hot_prefix[col >> 5] + (uint32_t)__popc(bits & (bit - 1u));
-            const int l2 = (int)(iv >> 28);                                  // signed rest, |l2| <= 2^12
-            const uint32_t rem = (uint32_t)(iv - ((long long)l2 << 28));     // in [0, 2^28)
-            atomicAdd(&hot_acc[3 * slot], rem & 0x3fffu);
-            atomicAdd(&hot_acc[3 * slot + 1], rem >> 14);
-            atomicAdd(&hot_acc[3 * slot + 2], (uint32_t)l2);
-            return;
-          }
-        }
-      }
-    }
-    atomicAdd(&p.g[col], gv);
+    if (gv != 0.0) red_add_f64(&p.g[col], gv);
   };
 
   const int rlog = p.rows_log2, rows_per_block = 1 << rlog;
@@ -335,23 +291,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
   if (threadIdx.x == 0) {
     if (s_cnt[0]) atomicAdd(&p.cnt[kCntHinge], s_cnt[0]);
     if (s_cnt[1]) atomicAdd(&p.cnt[kCntCorrect], s_cnt[1]);
-  }
-  if constexpr (kHot) {
-    // every warp is past its last scatter (the barrier above): flush the touched slots, one RED each
-    for (int slot = threadIdx.x; slot < p.n_hot; slot += kStreamThreads) {
-      const long long tot = (long long)hot_acc[3 * slot] + ((long long)hot_acc[3 * slot + 1] << 14) +
-                            ((long long)(int)hot_acc[3 * slot + 2] << 28);
-      if (tot != 0) {
-        double *dst = &p.g[__ldg(&p.hot_cols[slot])];
-        if (tot > -(1ll << 53) && tot < (1ll << 53)) {
-          atomicAdd(dst, (double)tot * 0x1p-40);             // the conversion is exact
-        } else {
-          const long long hi = tot >> 30, lo = tot - (hi << 30);             // both convert exactly
-          atomicAdd(dst, (double)hi * 0x1p-10);
-          atomicAdd(dst, (double)lo * 0x1p-40);
-        }
-      }
-    }
   }
 }
 

@@ -266,6 +266,47 @@ __global__ void k_rw_variants(unsigned *bar, double2 *buf, int n_addr, int iters
   if (blockIdx.x == 0 && threadIdx.x == 0) *out = tot / iters;
 }
 
+// 11. how the WRITER stores decides what the readers pay?  ST 0: st.volatile (as 9/WR 2)  1: st.global.cg  2: st.relaxed.gpu
+//     3: st.global.wt  4: atom.exch.b64  5: red.global.add.f64 (reference)  6: st.relaxed.sys.v2 16 bytes (the LL word)
+template <int ST>
+__global__ void k_store_kinds(unsigned *bar, double2 *buf, int n_addr, int iters, long long *out, double *sink) {
+  __shared__ int dummy;
+  unsigned a = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u;
+  long long tot = 0;
+  double acc = 0.0;
+  for (int it = 1; it <= iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      a = a * 1664525u + 1013904223u;
+      double *q = &buf[(a >> 8) % n_addr].y;
+      const double v = (double)it;
+      if (ST == 0) *(volatile double *)q = v;
+      else if (ST == 1) asm volatile("st.global.cg.f64 [%0], %1;" ::"l"(q), "d"(v) : "memory");
+      else if (ST == 2) asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(q), "d"(v) : "memory");
+      else if (ST == 3) asm volatile("st.global.wt.f64 [%0], %1;" ::"l"(q), "d"(v) : "memory");
+      else if (ST == 4) { unsigned long long o; asm volatile("atom.relaxed.gpu.global.exch.b64 %0, [%1], %2;" : "=l"(o) : "l"(q), "l"(__double_as_longlong(v)) : "memory"); if (o == 12345ull) *sink = 1.0; }
+      else if (ST == 5) asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(q), "d"(1.0) : "memory");
+      else asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(q - 1), "l"((unsigned long long)it), "l"((unsigned long long)it) : "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned target = (unsigned)it * gridDim.x;
+      red_release_gpu_add(bar, 1u); while (ld_relaxed_gpu(bar) < target) {}
+      dummy = it;
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {
+      const long long t0 = clock64();
+      a = a * 1664525u + 1013904223u;
+      const double2 v = __ldcg(&buf[(a >> 8) % n_addr]);
+      acc += v.x + v.y;
+      if (acc == 12345.678) *sink = acc;
+      tot += clock64() - t0;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out = tot / iters;
+}
+
 int main() {
   int dev = 0; CK(cudaSetDevice(dev));
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, dev));
@@ -369,6 +410,13 @@ int main() {
     run((void *)k_rw_then_gather<0>, "read-only:");
     run((void *)k_rw_then_gather<1>, "RED into by every thread before:");
     run((void *)k_rw_then_gather<2>, "stored into by every thread before:");
+    run((void *)k_store_kinds<0>, "st.volatile by all:");
+    run((void *)k_store_kinds<1>, "st.global.cg by all:");
+    run((void *)k_store_kinds<2>, "st.relaxed.gpu by all:");
+    run((void *)k_store_kinds<3>, "st.global.wt by all:");
+    run((void *)k_store_kinds<4>, "atom.exch.b64 by all:");
+    run((void *)k_store_kinds<5>, "red.add.f64 by all:");
+    run((void *)k_store_kinds<6>, "st.relaxed.sys.v2 (LL word) by all:");
     run((void *)k_rw_variants<1, 0>, "[half] RED by all, ld.cg:");
     run((void *)k_rw_variants<3, 0>, "[half] RED by CTA 0 only, ld.cg:");
     run((void *)k_rw_variants<4, 0>, "[half] RED by all into the OTHER half:");
