@@ -382,16 +382,26 @@ struct FetchLL {
     }
   }
   __device__ __forceinline__ void get4(const uint2 (&pr)[4], double (&wv)[4]) {
-    bool got[4];
+    unsigned pend = 0;   // bit u: word of pair u not published yet; all pending words are re-requested together
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       wv[u] = 0.0;
-      got[u] = true;
-      if (pr[u].y << 1) got[u] = ll_try_load(LW + 2 * (size_t)pr[u].x, tag, wv[u]);
+      if (pr[u].y << 1) pend |= 1u << u;
     }
+    unsigned spins = 0;
+    const long long t0 = clock64();
+    while (pend) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (!got[u]) spin(LW + 2 * (size_t)pr[u].x, wv[u]);
+      for (int u = 0; u < 4; ++u)
+        if (pend & (1u << u)) {
+          if (ll_try_load(LW + 2 * (size_t)pr[u].x, tag, wv[u])) pend &= ~(1u << u);
+        }
+      if (pend && (++spins & 63u) == 0u && (clock64() - t0 > timeout || *(volatile int *)abort_flag)) {
+        *(volatile int *)abort_flag = 1;
+        good = false;
+        pend = 0;
+      }
+    }
   }
   __device__ __forceinline__ double get1(uint32_t col) {
     double v;
@@ -764,39 +774,65 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
             double wn = wreg[0];                 // W_{T-1}[j_col]: this thread computed it one interval ago
             const unsigned long long *bm0 = p.xbm[me] + (size_t)parp * p.xwords + (size_t)col_word;
             const unsigned long long *vl0 = p.xval[me] + 2 * ((size_t)parp * p.xstride + (size_t)j_col);
+            // All K-1 bitmap words are requested together and re-requested together until every one carries this step's
+            // tag: the wait is the LATEST peer plus one poll, not a poll per peer in turn (with one peer polled after the
+            // other the 8-GPU step spent 13 600 cycles here, profiles/r2_multi_gpu.md).
+            unsigned bits[kMaxWorld];
+            unsigned pend = 0;   // bit k: bitmap word of peer k not here yet
 #pragma unroll
             for (int k = 0; k < kMaxWorld; ++k) {
               raw[k] = (k == me) ? own : 0.0;
-              if (k < K && k != me) {
-                const unsigned long long *bsrc = bm0 + (size_t)k * 2 * p.xwords;
-                unsigned bits;
-                if (!ll_try_load32(bsrc, gtag, bits)) {
-                  unsigned spins = 0;
-                  const long long t0 = clock64();
-                  while (!ll_try_load32(bsrc, gtag, bits)) {
-                    if ((++spins & 255u) == 0u && (clock64() - t0 > p.timeout_cycles || *(volatile int *)p.abort_flag)) {
-                      *(volatile int *)p.abort_flag = 1;
-                      ok = false;
-                      bits = 0u;
-                      break;
-                    }
+              bits[k] = 0u;
+              if (k < K && k != me) pend |= 1u << k;
+            }
+            {
+              unsigned spins = 0;
+              const long long t0 = clock64();
+              while (pend) {
+#pragma unroll
+                for (int k = 0; k < kMaxWorld; ++k)
+                  if (pend & (1u << k)) {
+                    if (ll_try_load32(bm0 + (size_t)k * 2 * p.xwords, gtag, bits[k])) pend &= ~(1u << k);
                   }
-                }
-                if ((bits >> lane) & 1u) {
-                  if (!ll_try_load(vl0 + 2 * (size_t)k * 2 * p.xstride, gtag, raw[k])) need |= 1u << k;
+                if (pend && (++spins & 63u) == 0u && (clock64() - t0 > p.timeout_cycles || *(volatile int *)p.abort_flag)) {
+                  *(volatile int *)p.abort_flag = 1;
+                  ok = false;
+#pragma unroll
+                  for (int k = 0; k < kMaxWorld; ++k)
+                    if (pend & (1u << k)) bits[k] = 0u;
+                  pend = 0;
                 }
               }
             }
+#pragma unroll
+            for (int k = 0; k < kMaxWorld; ++k)
+              if (k < K && k != me && ((bits[k] >> lane) & 1u)) {
+                if (!ll_try_load(vl0 + 2 * (size_t)k * 2 * p.xstride, gtag, raw[k])) need |= 1u << k;
+              }
             mbar_wait(&sm.c_bar[t & 1], c_par, p.abort_flag, p.timeout_cycles);
             const double c_prev = *(volatile double *)&sm.c_val[t & 1];
             const bool add_c = (c_prev != 0.0) && (fabs(c_prev) > kEps);
             if (col_act) {
-              FetchLL sp{nullptr, gtag, p.abort_flag, p.timeout_cycles};
+              {
+                unsigned spins = 0;
+                const long long t0 = clock64();
+                while (need) {
+#pragma unroll
+                  for (int k = 0; k < kMaxWorld; ++k)
+                    if (need & (1u << k)) {
+                      if (ll_try_load(vl0 + 2 * (size_t)k * 2 * p.xstride, gtag, raw[k])) need &= ~(1u << k);
+                    }
+                  if (need && (++spins & 63u) == 0u && (clock64() - t0 > p.timeout_cycles || *(volatile int *)p.abort_flag)) {
+                    *(volatile int *)p.abort_flag = 1;
+                    ok = false;
+                    need = 0;
+                  }
+                }
+              }
               double s = 0.0;
 #pragma unroll
               for (int k = 0; k < kMaxWorld; ++k) {
                 if (k < K) {
-                  if (need & (1u << k)) sp.spin(vl0 + 2 * (size_t)k * 2 * p.xstride, raw[k]);
                   if (j_col == p.dim) {
                     s += raw[k];                                // packed counters: plain sum
                   } else {
@@ -806,7 +842,6 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
                   }
                 }
               }
-              ok = ok && sp.good;
               if (j_col == p.dim) {
                 if (p.losses) {  // loss of step T-1 on W_{T-1}: lambda*||W||^2 + (all ranks' hinge) / (all ranks' samples)
                   const double ns = floor(s / 4294967296.0);
