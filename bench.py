@@ -294,14 +294,15 @@ def async_record(args, group, data, n_train, rank, local_rank, world, hbm_peak):
     group.barrier()
     mean_bytes = data.algorithmic_bytes() / data.n_rows
     out = []
-    for lanes, U in ((1, 60000), (256, 1500000)):
+    # (batch, lanes, updates per GPU): configs[3] = batch 1; configs[4] sweeps batch 64 / 256 / 1024 in async mode too
+    for B_a, lanes, U in ((1, 1, 60000), (1, 256, 1500000), (64, 64, 12000), (256, 64, 4000), (1024, 64, 1200)):
         actx.set_weights(w0)
         if rank == 0:
             actx.async_host_master(w0)
         group.barrier()
 
         def run(seed, n_upd):
-            actx.start_async(None, assigned, 1, LR, concurrency=lanes, max_updates=n_upd, seed=seed)
+            actx.start_async(None, assigned, B_a, LR, concurrency=lanes, max_updates=n_upd, seed=seed)
             while actx.async_running():
                 time.sleep(0.0002)
             actx.stop_async()
@@ -316,12 +317,12 @@ def async_record(args, group, data, n_train, rank, local_rank, world, hbm_peak):
         group.barrier()
         w_self = actx.get_weights()
         blobs = group.all_gather_bytes(w_self.tobytes())
-        rec = {"mode": "async", "batch": 1, "lanes_per_gpu": lanes, "n_gpus": world, "updates_per_gpu": U, "lr": LR,
-               "value": U * world / (ms * 1e-3), "e2e_value": U * world / wall, "unit": UNIT,
+        rec = {"mode": "async", "batch": B_a, "lanes_per_gpu": lanes, "n_gpus": world, "updates_per_gpu": U, "lr": LR,
+               "value": U * B_a * world / (ms * 1e-3), "e2e_value": U * B_a * world / wall, "unit": UNIT,
                "us_per_update_per_lane": ms * 1e3 * lanes / U,
-               "roofline_frac": U * mean_bytes / (ms * 1e-3) / 1e9 / hbm_peak,
+               "roofline_frac": U * B_a * mean_bytes / (ms * 1e-3) / 1e9 / hbm_peak,
                "label": ("one worker per GPU, sequential loop: the reference's Slave.asyncTask" if lanes == 1 else
-                         "EXTENSION: 256 Hogwild lanes per GPU on the GPU's replica (the reference runs one loop per slave)")}
+                         f"EXTENSION: {lanes} Hogwild lanes per GPU on the GPU's replica (the reference runs one loop per slave)")}
         if rank == 0:
             ws = [np.frombuffer(b, dtype=np.float64) for b in blobs]
             w_master = actx.async_master_weights()
