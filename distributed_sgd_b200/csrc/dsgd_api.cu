@@ -575,16 +575,17 @@ static bool stream_eligible(const dsgd_ctx *ctx, int64_t n) {
   return n >= kStreamMinRows && stream_smem_bytes(ctx->dim) + 1024 <= 227u * 1024u;
 }
 
-template <bool kScatter, bool kPreds>
+template <bool kScatter, bool kPreds, bool kContig>
 static int stream_launch(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t row_begin, int64_t n, const double *w_dev,
                          const float *w32_dev, double *g, double *preds) {
   const size_t smem = stream_smem_bytes(ctx->dim);
   if (!ctx->stream_ready) {
-    CU(cudaFuncSetAttribute(k_stream_rows<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaFuncSetAttribute(k_stream_rows<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaFuncSetAttribute(k_stream_rows<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k_stream_rows<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k_stream_rows<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k_stream_rows<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ctx->stream_ready = true;
   }
+  NEED(kContig == (samples_dev == nullptr), DSGD_ERR_INVALID, "stream_launch: sample list / row range mismatch");
   StreamParams sp;
   memset(&sp, 0, sizeof sp);
   sp.rp16 = ctx->rp16; sp.units = reinterpret_cast<const uint4 *>(ctx->pairs); sp.yabs = ctx->yabs;
@@ -596,11 +597,15 @@ static int stream_launch(dsgd_ctx *ctx, const int32_t *samples_dev, int64_t row_
   const int64_t n_warps_all = (int64_t)ctx->sm_count * (kStreamThreads / 32);
   sp.rows_log2 = 5;
   while (sp.rows_log2 > 3 && ((n + (1 << sp.rows_log2) - 1) >> sp.rows_log2) < 6 * n_warps_all) --sp.rows_log2;
-  const int64_t n_blk = (n + (1 << sp.rows_log2) - 1) >> sp.rows_log2;
+  // the last fifth of the pass goes out in blocks of half the size (not below 8 rows): warps end closer together.
+  // (Measured r2q: 2 to 6 blocks per warp and a tail of 0 to 35 % all land within 1 % of each other, profiles/r2_streaming.md.)
+  sp.tail_log2 = std::max(3, sp.rows_log2 - 1);
+  sp.n_big = sp.tail_log2 < sp.rows_log2 ? ((n - n / 5) >> sp.rows_log2) : ((n + (1 << sp.rows_log2) - 1) >> sp.rows_log2);
+  const int64_t n_blk = sp.n_big + cdiv(std::max<int64_t>(0, n - (sp.n_big << sp.rows_log2)), (int64_t)1 << sp.tail_log2);
   const int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, cdiv(n_blk, kStreamThreads / 32)));
   auto *pe = prof_slot(ctx);
   if (pe) cudaEventRecord(pe->first, ctx->stream);
-  k_stream_rows<kScatter, kPreds><<<grid, kStreamThreads, smem, ctx->stream>>>(sp);
+  k_stream_rows<kScatter, kPreds, kContig><<<grid, kStreamThreads, smem, ctx->stream>>>(sp);
   if (pe) cudaEventRecord(pe->second, ctx->stream);
   LAUNCHED();
   CU(cudaGetLastError());
@@ -621,7 +626,7 @@ extern "C" int dsgd_forward(dsgd_ctx *ctx, const double *w, const int32_t *sampl
   const float *w32d;
   if ((rc = request_weights(ctx, w, &wd, &cd, &nd, &w32d))) return rc;
   if (stream_eligible(ctx, n)) {
-    if ((rc = stream_launch<false, true>(ctx, ctx->samples, 0, n, wd, w32d, nullptr, ctx->preds))) return rc;
+    if ((rc = stream_launch<false, true, false>(ctx, ctx->samples, 0, n, wd, w32d, nullptr, ctx->preds))) return rc;
   } else {
     k_rows<false, true><<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(ctx->rp16, ctx->pairs, ctx->label, ctx->samples, 0, n,
                                                                     wd, nullptr, ctx->preds, ctx->cnt);
@@ -647,7 +652,7 @@ extern "C" int dsgd_gradient(dsgd_ctx *ctx, const double *w, const int32_t *samp
   const float *w32d;
   if ((rc = request_weights(ctx, w, &wd, &cd, &nd, &w32d))) return rc;
   if (stream_eligible(ctx, n)) {
-    if ((rc = stream_launch<true, false>(ctx, ctx->samples, 0, n, wd, w32d, ctx->g, nullptr))) return rc;
+    if ((rc = stream_launch<true, false, false>(ctx, ctx->samples, 0, n, wd, w32d, ctx->g, nullptr))) return rc;
   } else {
     k_rows<true, false><<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(ctx->rp16, ctx->pairs, ctx->label, ctx->samples, 0, n,
                                                                     wd, ctx->g, nullptr, ctx->cnt);
@@ -679,7 +684,7 @@ static int eval_impl(dsgd_ctx *ctx, const double *w, int64_t row_begin, int64_t 
   int rc;
   if ((rc = request_weights(ctx, w, &wd, &cd, &nd, &w32d))) return rc;
   if (stream_eligible(ctx, n)) {
-    if ((rc = stream_launch<false, false>(ctx, nullptr, row_begin, n, wd, w32d, nullptr, nullptr))) return rc;
+    if ((rc = stream_launch<false, false, true>(ctx, nullptr, row_begin, n, wd, w32d, nullptr, nullptr))) return rc;
   } else {
     k_rows<false, false><<<rows_grid(ctx, n), 256, 0, ctx->stream>>>(ctx->rp16, ctx->pairs, ctx->label, nullptr, row_begin, n,
                                                                      wd, nullptr, nullptr, ctx->cnt);

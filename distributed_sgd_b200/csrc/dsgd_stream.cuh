@@ -15,9 +15,13 @@
 //     busy).  A lane accumulates its units of the open row; the warp reduces once per ROW END (one 5-step butterfly
 //     of ONE float), not per load, and the row's lane just keeps the sum: predictions, counters and gates of the 32
 //     rows are worked out by 32 lanes in parallel after the block's stream.  The kernel is ISSUE-bound before it is
-//     HBM-bound (ncu, round 2 first cut: 108 warp instructions per 64 pairs = 131 us per pass; this form: see
-//     profiles/), so every per-slot instruction counts: no bounds predicates except in a block's last group, row ends
-//     located once per 4 slots.
+//     HBM-bound (ncu: round 2's first cut 108 warp instructions per 64 pairs = 131 us per evaluation pass; 100.8 us at
+//     70; 88.7 us at ~55, profiles/r2_streaming.md), so every per-slot instruction counts: groups that lie inside the block
+//     carry no bounds predicates (only a block's last group does), a slot without a row end adds its products with one
+//     FADD, and a pass over CONSECUTIVE rows (kContig: evaluation) needs no row lookup for its loads at all -- the windows
+//     are back to back in the pair array -- so its four loads leave before the row-end masks are even computed.
+//   * Blocks are dealt dynamically (one atomic per block, requested a block ahead); the last fifth of a pass goes out in
+//     blocks of half the size so the warps run dry together.
 //   * Exactness against the fp64 arithmetic of the reference: the fp32 result differs from x.w by at most
 //       (D + 1) * 2^-24 * max|w| * sum|x|,   D = units/32 + 9 roundings on the longest add chain, + 1 for rounding w
 //     (first-order bound, 1.5x slack); sum|x| per row is computed once when the rows are loaded (k_repack, rounded
@@ -38,6 +42,9 @@
 
 namespace dsgd {
 
+struct TrueTag { static constexpr bool value = true; };
+struct FalseTag { static constexpr bool value = false; };
+
 constexpr int kStreamThreads = 1024;
 constexpr int kStreamUnroll = 4;
 
@@ -57,11 +64,16 @@ struct StreamParams {
   unsigned long long *next_block;  // work counter (zero on entry): blocks beyond the first wave are claimed dynamically
   int rows_log2;               // rows per block = 1 << rows_log2 (5, 4 or 3): the host picks it so that every warp gets
                                // several blocks (a block is the unit of the dynamic work distribution)
+  int64_t n_big;               // blocks [0, n_big) have 1 << rows_log2 rows, the blocks after them 1 << tail_log2: the
+  int tail_log2;               // last part of a pass is dealt in smaller pieces, so the warps run dry together
 };
 
 __host__ __device__ constexpr size_t stream_smem_bytes(int dim) { return (((size_t)dim + 3) & ~(size_t)3) * sizeof(float); }
 
-template <bool kScatter, bool kPreds>
+// kContig: the rows of the pass are consecutive (samples == nullptr), hence so are their windows in the pair array: unit v
+// of a block sits at (first window) + v and the loads need no row lookup (5 instructions per slot less, and the row-end
+// masks are worked out while the loads are in flight).
+template <bool kScatter, bool kPreds, bool kContig>
 __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *ws = reinterpret_cast<float *>(smem_raw);
@@ -70,6 +82,41 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
+  const int rlog = p.rows_log2, tlog = p.tail_log2;
+  const int64_t tail_row0 = p.n_big << rlog;   // first row of the smaller tail blocks
+  const int64_t n_blocks = p.n_big + ((p.n - tail_row0 + (1 << tlog) - 1) >> tlog);
+  const int64_t warp_global = (int64_t)blockIdx.x * (kStreamThreads / 32) + warp;
+  const int64_t n_warps = (int64_t)gridDim.x * (kStreamThreads / 32);
+  unsigned hinge = 0, correct = 0, n_exact = 0;
+
+  // bounds of the block being processed / the next one: lane l holds row l of the block
+  auto load_block = [&](int64_t blk, int64_t &first, uint32_t &b, uint32_t &e, float &ya, bool &valid) {
+    const bool big = blk < p.n_big;
+    first = big ? (blk << rlog) : tail_row0 + ((blk - p.n_big) << tlog);
+    const int64_t i = first + lane;
+    b = 0u; e = 0u; ya = 0.f;
+    valid = blk < n_blocks && lane < (1 << (big ? rlog : tlog)) && i < p.n;
+    if (valid) {
+      const int64_t rid = (!kContig && p.samples) ? (int64_t)__ldg(&p.samples[i]) : p.row_begin + i;
+      b = __ldg(&p.rp16[rid]);
+      e = __ldg(&p.rp16[rid + 1]);
+      ya = __ldg(&p.yabs[rid]);
+    }
+  };
+  // Work distribution: the first wave is static (block = warp id), later blocks are claimed from a global counter one
+  // step ahead; the ticket (an atomic with a return value) is requested when a block starts and read when it ends, the
+  // next block's bounds were prefetched a block earlier.
+  unsigned long long ticket = 0;   // lane 0: the pending claim
+  auto claim_issue = [&]() {
+    if (lane == 0) ticket = atomicAdd(p.next_block, 1ull);
+  };
+  auto claim_get = [&]() -> int64_t { return (int64_t)__shfl_sync(0xffffffffu, ticket, 0) + n_warps; };
+  uint32_t nb, ne; float nya; bool nvalid; int64_t nfirst;
+  int64_t blk = warp_global;
+  int64_t blk_next = n_blocks;
+  if (blk < n_blocks) claim_issue();
+  load_block(blk, nfirst, nb, ne, nya, nvalid);   // (requested before the weights are staged: latency off the path)
+
   // ---- stage the fp32 weights, find max|w| ----
   float wmax = 0.f;
   {
@@ -101,52 +148,20 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
     if (gv != 0.0) red_add_f64(&p.g[col], gv);
   };
 
-  const int rlog = p.rows_log2, rows_per_block = 1 << rlog;
-  const int64_t n_blocks = (p.n + rows_per_block - 1) >> rlog;
-  const int64_t warp_global = (int64_t)blockIdx.x * (kStreamThreads / 32) + warp;
-  const int64_t n_warps = (int64_t)gridDim.x * (kStreamThreads / 32);
-  unsigned hinge = 0, correct = 0, n_exact = 0;
-
-  // bounds of the block being processed / the next one: lane l holds row l of the block
-  auto load_block = [&](int64_t blk, uint32_t &b, uint32_t &e, float &ya, bool &valid) {
-    const int64_t i = (blk << rlog) + lane;
-    b = 0u; e = 0u; ya = 0.f;
-    valid = blk < n_blocks && lane < rows_per_block && i < p.n;
-    if (valid) {
-      const int64_t rid = p.samples ? (int64_t)__ldg(&p.samples[i]) : p.row_begin + i;
-      b = __ldg(&p.rp16[rid]);
-      e = __ldg(&p.rp16[rid + 1]);
-      ya = __ldg(&p.yabs[rid]);
-    }
-  };
-  // Work distribution: the first wave is static (block = warp id), later blocks are claimed from a global counter one
-  // step ahead; the ticket (an atomic with a return value) is requested when a block starts and read when it ends, the
-  // next block's bounds were prefetched a block earlier.
-  unsigned long long ticket = 0;   // lane 0: the pending claim
-  auto claim_issue = [&]() {
-    if (lane == 0) ticket = atomicAdd(p.next_block, 1ull);
-  };
-  auto claim_get = [&]() -> int64_t { return (int64_t)__shfl_sync(0xffffffffu, ticket, 0) + n_warps; };
-  uint32_t nb, ne; float nya; bool nvalid;
-  int64_t blk = warp_global;
-  int64_t blk_next = n_blocks;
-  if (blk < n_blocks) {
-    claim_issue();
-    blk_next = claim_get();
-  }
-  load_block(blk, nb, ne, nya, nvalid);
+  if (blk < n_blocks) blk_next = claim_get();
   for (; blk < n_blocks;) {
     uint32_t b = nb;
     int len = (int)(ne - nb);   // units
     float ya = nya;
     bool valid = nvalid;
-    load_block(blk_next, nb, ne, nya, nvalid);
+    const int64_t first = nfirst;   // first row (position in the pass) of this block
+    load_block(blk_next, nfirst, nb, ne, nya, nvalid);
     if (blk_next < n_blocks) claim_issue();   // for the block after next: read at the end of this block
     int opos = lane;            // position of this lane's row inside the block (before compaction)
     // empty rows: dot 0 -> prediction 0, hinge 1, never correct, nothing to scatter (SparseSVM.scala:14-16)
     if (valid && len == 0) {
       hinge += 1u;
-      if (kPreds) p.preds[(blk << rlog) + lane] = 0.0;
+      if (kPreds) p.preds[first + lane] = 0.0;
     }
     const unsigned ne_mask = __ballot_sync(0xffffffffu, valid && len > 0);
     if (ne_mask != 0xffffffffu) {   // compact the non-empty rows to lanes 0 .. n-1 (order kept)
@@ -172,6 +187,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
     }
     const int total = __shfl_sync(0xffffffffu, P, 31);
     const uint32_t base = b - (uint32_t)(P - len);   // unit address of virtual unit v of this row = base + v (mod 2^32)
+    const uint32_t base0 = __shfl_sync(0xffffffffu, base, 0);   // kContig: the same for every row of the block
     const int my_end = len > 0 ? P - 1 : -1;          // virtual position of this row's LAST unit
     float acc_p = 0.f;                                // this lane's share of the OPEN row: sum x*w
     float dot_mine = 0.f;                             // this lane's row: x.w in fp32 once the row is closed
@@ -179,16 +195,26 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
 
     // One GROUP = kStreamUnroll slots of 32 units: where rows end inside the group (one or-reduction per slot), hence the
     // row of each lane's unit, then the 128-bit loads -- all issued before the first is used (64 KB in flight per SM).
+    // Groups that lie entirely inside the block (kFull) carry no bounds predicates; the block's last group does.
     // (A software-prefetched form -- group g + 1 fetched before group g is processed, 768 threads x 80 registers -- was
     // measured SLOWER: 118.9 us against 107.4 us per evaluation pass, profiles/r2_streaming.md: the lost warps cost more
     // latency hiding than the deeper queue bought.)
-    for (int v0 = 0; v0 < total; v0 += 32 * kStreamUnroll) {
+    auto do_group = [&](auto full_tag, const int v0) {
+      constexpr bool kFull = decltype(full_tag)::value;
       uint4 q[kStreamUnroll];
       unsigned ends[kStreamUnroll];   // bit j: a row's LAST unit sits at lane j of this slot
-      const bool full = v0 + 32 * kStreamUnroll <= total;
-      {
-        const unsigned pos = (unsigned)(my_end - v0);          // < 32 * kStreamUnroll iff the row ends in this group
-        const unsigned bit = 1u << (pos & 31u);
+      const unsigned pos = (unsigned)(my_end - v0);          // < 32 * kStreamUnroll iff the row ends in this group
+      const unsigned bit = 1u << (pos & 31u);
+      if constexpr (kContig) {
+#pragma unroll
+        for (int i = 0; i < kStreamUnroll; ++i) {
+          if (kFull || v0 + 32 * i + lane < total) q[i] = __ldg(&p.units[base0 + (uint32_t)(v0 + 32 * i + lane)]);
+          else q[i] = make_uint4(0u, 0u, 0u, 0u);  // col 0, val +0.0f
+        }
+#pragma unroll
+        for (int i = 0; i < kStreamUnroll; ++i)
+          ends[i] = __reduce_or_sync(0xffffffffu, (pos >> 5) == (unsigned)i ? bit : 0u);
+      } else {
         int r0 = row0;
 #pragma unroll
         for (int i = 0; i < kStreamUnroll; ++i) {
@@ -196,31 +222,36 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
           const int rmy = r0 + __popc(ends[i] & lt_mask);      // row of this lane's unit
           r0 += __popc(ends[i]);
           const uint32_t bs = __shfl_sync(0xffffffffu, base, rmy & 31);
-          if (full) {
-            q[i] = __ldg(&p.units[bs + (uint32_t)(v0 + 32 * i + lane)]);
-          } else {
-            q[i] = make_uint4(0u, 0u, 0u, 0u);  // col 0, val +0.0f
-            if (v0 + 32 * i + lane < total) q[i] = __ldg(&p.units[bs + (uint32_t)(v0 + 32 * i + lane)]);
-          }
+          if (kFull || v0 + 32 * i + lane < total) q[i] = __ldg(&p.units[bs + (uint32_t)(v0 + 32 * i + lane)]);
+          else q[i] = make_uint4(0u, 0u, 0u, 0u);
         }
       }
 #pragma unroll
       for (int i = 0; i < kStreamUnroll; ++i) {
         float pp = __fmaf_rn(__uint_as_float(q[i].w), ws[q[i].z], __uint_as_float(q[i].y) * ws[q[i].x]);
-        if (!full && !(v0 + 32 * i + lane < total)) pp = 0.f;   // a masked unit reads ws[0]: keep a NaN / inf weight out
-        const int rmy = row0 + __popc(ends[i] & lt_mask);       // row0 == rows closed before this slot
+        if (!kFull && !(v0 + 32 * i + lane < total)) pp = 0.f;   // a masked unit reads ws[0]: keep a NaN / inf weight out
         unsigned m = ends[i];
-        while (m) {   // warp-uniform: close the rows that end inside this slot, in order
-          m &= m - 1u;
-          float sp = acc_p + (rmy == row0 ? pp : 0.f);
+        if (m == 0u) {   // warp-uniform: no row ends inside this slot
+          acc_p += pp;
+        } else {
+          const int rmy = row0 + __popc(m & lt_mask);           // row0 == rows closed before this slot
+          do {   // close the rows that end inside this slot, in order
+            m &= m - 1u;
+            float sp = acc_p + (rmy == row0 ? pp : 0.f);
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) sp += __shfl_xor_sync(0xffffffffu, sp, o);
-          if (lane == row0) dot_mine = sp;
-          acc_p = 0.f;
-          ++row0;
+            for (int o = 16; o > 0; o >>= 1) sp += __shfl_xor_sync(0xffffffffu, sp, o);
+            if (lane == row0) dot_mine = sp;
+            acc_p = 0.f;
+            ++row0;
+          } while (m);
+          acc_p = (rmy == row0) ? pp : 0.f;
         }
-        acc_p += (rmy == row0) ? pp : 0.f;
       }
+    };
+    {
+      int v0 = 0;
+      for (; v0 + 32 * kStreamUnroll <= total; v0 += 32 * kStreamUnroll) do_group(TrueTag{}, v0);
+      if (v0 < total) do_group(FalseTag{}, v0);
     }
     // ---- 32 rows decided by 32 lanes: inside the rounding band -> exact recomputation; else the sign is certain ----
     bool need_exact = false, do_scatter = false;
@@ -257,7 +288,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream_rows(const StreamP
       }
     }
     if (kPreds) {
-      if (valid) p.preds[(blk << rlog) + opos] = (double)pred_mine;
+      if (valid) p.preds[first + opos] = (double)pred_mine;
     }
     // ---- scatter y*x of the rows that passed the gate (SparseSVM.scala:28) ----
     if (kScatter) {
