@@ -101,19 +101,34 @@ def ncu_traffic(kernel_key: str):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md's clocks line), read every 25 ms from NVML
+    in this process -- the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints, without a
+    looping nvidia-smi process next to the launching rank (whose peers spin for it inside the fused multi-GPU kernel).
+    `nvidia-smi -lms 20` remains the fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device: int):
         self.device, self.rows, self.proc, self.first = device, [], None, 0
+        self.nvml, self.handle, self.run, self.thread = None, None, False, None
 
     def mark(self):
-        """Samples before this call (GPU idle while nvidia-smi starts) are not used."""
+        """Samples before this call (GPU idle while the sampler starts) are not used."""
         self.first = len(self.rows)
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml, self.run = pynvml, True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "20", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
@@ -121,15 +136,37 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        names = (("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap))
+        try:
+            mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        while self.run:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                self.rows.append([str(self.device), str(sm), str(mx), ""] + ["Active" if mask & bit else "Not Active" for _, bit in names])
+            except Exception:
+                pass
+            time.sleep(0.025)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.nvml is not None:
+            time.sleep(0.03)
+            self.run = False
+            self.thread.join(timeout=1.0)
+        elif self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source: NVML and nvidia-smi unavailable"]}
         sm, mx, reasons = [], [], set()
         for r in self.rows[self.first:]:
             try:
@@ -140,7 +177,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "source": "NVML, every 25 ms during warm-up + timed region" if self.nvml is not None else "nvidia-smi -lms 20"}
 
 
 def nvlink_counters(device: int):
@@ -571,10 +609,13 @@ def main():
         clocks.mark()
     for i in range(args.warmup):
         ctx.sync_steps_staged(i * S * B, B, S, LR, want_losses=True)
-    barrier()
+    ctx.synchronize()
+    # (read BEFORE the barrier: the first NVML query takes tens of ms on rank 0 alone, and a rank that starts its timed
+    #  launches late keeps its peers spinning inside theirs -- with the query after the barrier `value` fell below `e2e`)
     nvl0 = nvlink_counters(local_rank) if (rank == 0 and world > 1) else None
     xs0 = ctx.xchg_stats() if world > 1 else None
     launches0 = ctx.launch_count()
+    barrier()
     ctx.timer_start()
     for i in range(args.warmup, total_steps):
         ctx.sync_steps_staged(i * S * B, B, S, LR, want_losses=True)
