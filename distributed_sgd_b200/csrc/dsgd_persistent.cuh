@@ -760,9 +760,8 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
             const size_t bslot = ((size_t)me * 2 + parp) * p.xwords + (size_t)col_word;
             for (int k = 0; k < K; ++k) {
               if (k == me) continue;
-              if (own != 0.0) ll_store(p.xval[k] + vslot, own, gtag);
-              __syncwarp();   // the warp's value words leave before its bitmap word
               if (lane == 0) ll_store32(p.xbm[k] + bslot, my_bits, gtag);
+              if (own != 0.0) ll_store(p.xval[k] + vslot, own, gtag);
             }
             if (lane == 0) { st_bm += 1; st_val += (unsigned)__popc(my_bits); }
           }
@@ -777,10 +776,12 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
             const unsigned long long *vl0 = p.xval[me] + 2 * ((size_t)parp * p.xstride + (size_t)j_col);
             // All K-1 bitmap words are requested together and re-requested together until every one carries this step's
             // tag: the wait is the LATEST peer plus one poll, not a poll per peer in turn (with one peer polled after the
-            // other the 8-GPU step spent 13 600 cycles here, profiles/r2_multi_gpu.md).
+            // other the 8-GPU step spent 13 600 cycles here, profiles/r2_multi_gpu.md).  Polling HARDER does not pay:
+            // a second request set half a round trip behind the first made the 2-GPU step 8.6 -> 13.5 us, and requesting
+            // every thread's value word along with the bitmap word (66 000 more requests per round) 8.5 -> 8.6 us --
+            // the polled lines are the ones the NVLink writes are landing in.
             unsigned bits[kMaxWorld];
             unsigned pend = 0;   // bit k: bitmap word of peer k not here yet
-            unsigned have = 0;   // bit k: value word of peer k read with this step's tag
 #pragma unroll
             for (int k = 0; k < kMaxWorld; ++k) {
               raw[k] = (k == me) ? own : 0.0;
@@ -788,18 +789,12 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
               if (k < K && k != me) pend |= 1u << k;
             }
             {
-              // The value word of this thread's column is requested WITH the peer's bitmap word, not after it: a word
-              // that carries this step's tag is this step's entry (the sender stores it before the bitmap word), so a
-              // touched column costs no second dependent round trip; an untouched one reads a stale tag and is decided
-              // by the bitmap.
               unsigned spins = 0;
               const long long t0 = clock64();
               while (pend) {
 #pragma unroll
                 for (int k = 0; k < kMaxWorld; ++k)
                   if (pend & (1u << k)) {
-                    if (col_act && !(have & (1u << k)) && ll_try_load(vl0 + 2 * (size_t)k * 2 * p.xstride, gtag, raw[k]))
-                      have |= 1u << k;
                     if (ll_try_load32(bm0 + (size_t)k * 2 * p.xwords, gtag, bits[k])) pend &= ~(1u << k);
                   }
                 if (pend && (++spins & 63u) == 0u && (clock64() - t0 > p.timeout_cycles || *(volatile int *)p.abort_flag)) {
@@ -814,12 +809,8 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
             }
 #pragma unroll
             for (int k = 0; k < kMaxWorld; ++k)
-              if (k < K && k != me) {
-                if ((bits[k] >> lane) & 1u) {
-                  if (!(have & (1u << k))) need |= 1u << k;
-                } else {
-                  raw[k] = 0.0;   // not sent this step
-                }
+              if (k < K && k != me && ((bits[k] >> lane) & 1u)) {
+                if (!ll_try_load(vl0 + 2 * (size_t)k * 2 * p.xstride, gtag, raw[k])) need |= 1u << k;
               }
             mbar_wait(&sm.c_bar[t & 1], c_par, p.abort_flag, p.timeout_cycles);
             const double c_prev = *(volatile double *)&sm.c_val[t & 1];
