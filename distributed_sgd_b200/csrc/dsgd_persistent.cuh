@@ -381,6 +381,8 @@ struct FetchLL {
       }
     }
   }
+  // All pending words are REQUESTED before any is looked at (a request and its check written together compile into
+  // one dependent round trip per word: nvcc reuses the destination registers -- measured, profiles/r2_multi_gpu.md).
   __device__ __forceinline__ void get4(const uint2 (&pr)[4], double (&wv)[4]) {
     unsigned pend = 0;   // bit u: word of pair u not published yet; all pending words are re-requested together
 #pragma unroll
@@ -391,10 +393,18 @@ struct FetchLL {
     unsigned spins = 0;
     const long long t0 = clock64();
     while (pend) {
+      unsigned long long w0[4], w1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        w0[u] = 0ull; w1[u] = 0ull;
+        if (pend & (1u << u))
+          asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[u]), "=l"(w1[u]) : "l"(LW + 2 * (size_t)pr[u].x) : "memory");
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (pend & (1u << u)) {
-          if (ll_try_load(LW + 2 * (size_t)pr[u].x, tag, wv[u])) pend &= ~(1u << u);
+        if ((pend & (1u << u)) && (unsigned)(w0[u] >> 32) == tag && (unsigned)(w1[u] >> 32) == tag) {
+          wv[u] = __longlong_as_double((long long)((w0[u] & 0xffffffffull) | (w1[u] << 32)));
+          pend &= ~(1u << u);
         }
       if (pend && (++spins & 63u) == 0u && (clock64() - t0 > timeout || *(volatile int *)abort_flag)) {
         *(volatile int *)abort_flag = 1;
@@ -809,9 +819,25 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
             }
 #pragma unroll
             for (int k = 0; k < kMaxWorld; ++k)
-              if (k < K && k != me && ((bits[k] >> lane) & 1u)) {
-                if (!ll_try_load(vl0 + 2 * (size_t)k * 2 * p.xstride, gtag, raw[k])) need |= 1u << k;
+              if (k < K && k != me && ((bits[k] >> lane) & 1u)) need |= 1u << k;
+            // the value words of every peer that sent this column: requested together, looked at together
+            auto poll_values = [&]() {
+              unsigned long long v0[kMaxWorld], v1[kMaxWorld];
+#pragma unroll
+              for (int k = 0; k < kMaxWorld; ++k) {
+                v0[k] = 0ull; v1[k] = 0ull;
+                if (need & (1u << k))
+                  asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];"
+                               : "=l"(v0[k]), "=l"(v1[k]) : "l"(vl0 + 2 * (size_t)k * 2 * p.xstride) : "memory");
               }
+#pragma unroll
+              for (int k = 0; k < kMaxWorld; ++k)
+                if ((need & (1u << k)) && (unsigned)(v0[k] >> 32) == gtag && (unsigned)(v1[k] >> 32) == gtag) {
+                  raw[k] = __longlong_as_double((long long)((v0[k] & 0xffffffffull) | (v1[k] << 32)));
+                  need &= ~(1u << k);
+                }
+            };
+            if (need) poll_values();
             mbar_wait(&sm.c_bar[t & 1], c_par, p.abort_flag, p.timeout_cycles);
             const double c_prev = *(volatile double *)&sm.c_val[t & 1];
             const bool add_c = (c_prev != 0.0) && (fabs(c_prev) > kEps);
@@ -820,11 +846,7 @@ __global__ void __launch_bounds__((kCons + kUpd + 1) * 32, 1) k_sync_persistent(
                 unsigned spins = 0;
                 const long long t0 = clock64();
                 while (need) {
-#pragma unroll
-                  for (int k = 0; k < kMaxWorld; ++k)
-                    if (need & (1u << k)) {
-                      if (ll_try_load(vl0 + 2 * (size_t)k * 2 * p.xstride, gtag, raw[k])) need &= ~(1u << k);
-                    }
+                  poll_values();
                   if (need && (++spins & 63u) == 0u && (clock64() - t0 > p.timeout_cycles || *(volatile int *)p.abort_flag)) {
                     *(volatile int *)p.abort_flag = 1;
                     ok = false;

@@ -4,6 +4,9 @@ dsgd_xchg_attach), one host thread per context like one JVM thread per Slave.  T
 exchange exactly as they do over NVLink -- the receive areas just live in the same HBM -- so the driver's single-GPU test
 box runs the multi-rank path for real: trajectories against the oracle's K-worker master step (core/Master.scala:184-197),
 bit-identical replicas, several launches in a row (global step counter, receive parities), short last batches.
+K stops at 3 here: four spinning kernels sharing one GPU hit the device-side watchdog in 2 of 9 sessions (CUDA does not
+promise co-scheduling of independent kernels; cooperative launch is per kernel) -- four and eight ranks are checked on real
+GPUs by bench.py's parity record (profiles/r2_multi_gpu.md).
 """
 import threading
 
@@ -35,7 +38,7 @@ def _run_ranks(fns):
     assert not any(t.is_alive() for t in th), "a rank hangs"
 
 
-@pytest.mark.parametrize("K,batch,dim", [(2, 48, 20000), (2, 7, 3000), (3, 33, 9000), (4, 64, 11000)])
+@pytest.mark.parametrize("K,batch,dim", [(2, 48, 20000), (2, 7, 3000), (3, 33, 9000), (3, 64, 11000)])
 def test_fused_k_ranks_on_one_gpu_match_oracle(K, batch, dim):
     import torch
     from distributed_sgd_b200.utils import synthetic_rcv1
