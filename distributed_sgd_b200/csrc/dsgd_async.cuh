@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "dsgd_feistel.h"
 #include "dsgd_kernels.cuh"
 
 namespace dsgd {
@@ -58,6 +59,34 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long &s) {
   return z ^ (z >> 31);
 }
 
+// `Random.shuffle(indices) take batchSize` (core/Slave.scala:86-88): the first B images of a keyed pseudo-random permutation
+// of [0, n) (dsgd_feistel.h).  The rejection loop of round 1 compared each candidate with all earlier ones on one lane:
+// 1.9 ms per batch of 256, 10 ms per batch of 1024 (profiles/r2_sweep.md).
+// One row of a batch, requested one row ahead of its use: window bounds, label and the first 128 pairs.
+struct AsyncBatchRow {
+  int64_t s0, s1;
+  double y;
+  uint2 pre[4];
+};
+__device__ __forceinline__ AsyncBatchRow async_fetch_batch_row(const AsyncParams &p, const int32_t *rows, int b, int B, int lane) {
+  AsyncBatchRow row;
+  row.s0 = row.s1 = 0;
+  row.y = 0.0;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) row.pre[u] = make_uint2(0u, 0u);
+  if (b >= B) return row;
+  const int32_t r = rows[b];
+  row.s0 = (int64_t)__ldg(&p.rp16[r]) * 2;
+  row.s1 = (int64_t)__ldg(&p.rp16[r + 1]) * 2;
+  row.y = (double)__ldg(&p.label[r]);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int64_t k = row.s0 + lane + 32 * u;
+    if (k < row.s1) row.pre[u] = __ldg(&p.pairs[k]);
+  }
+  return row;
+}
+
 __global__ void __launch_bounds__(128) k_async_worker(const AsyncParams p) {
   const int lane = threadIdx.x & 31;
   const int lane_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // Hogwild lane
@@ -67,6 +96,7 @@ __global__ void __launch_bounds__(128) k_async_worker(const AsyncParams p) {
   int32_t *rows = p.batch_rows + (size_t)lane_id * p.batch;
   const int B = p.batch;
   unsigned long long rng = p.seed * 0xD1342543DE82EF95ull + 0x632BE59BD9B4E019ull * (unsigned long long)(lane_id + 1);
+  const int half_bits = dsgd_feistel_half_bits((uint64_t)p.n_assigned);
 
   for (;;) {
     if (*p.stop) break;
@@ -84,19 +114,11 @@ __global__ void __launch_bounds__(128) k_async_worker(const AsyncParams p) {
       if (lane == 0) rows[0] = p.assigned[mix64(rng) % (unsigned long long)p.n_assigned];
     } else {
       // Random.shuffle(assignedSamples.indices) take batchSize map data: POSITIONS 0..n-1 index `data` directly
-      // (quirk Q6), drawn without replacement
-      if (lane == 0) {
-        for (int b = 0; b < B; ++b) {
-          int32_t pos;
-          bool dup;
-          do {
-            pos = (int32_t)(mix64(rng) % (unsigned long long)p.n_assigned);
-            dup = false;
-            for (int k = 0; k < b; ++k) dup |= (rows[k] == pos);
-          } while (dup);
-          rows[b] = pos;
-        }
-      }
+      // (quirk Q6), drawn without replacement: the first B images of this iteration's permutation
+      unsigned long long key = 0;
+      if (lane == 0) key = mix64(rng);
+      key = __shfl_sync(0xffffffffu, key, 0);
+      for (int b = lane; b < B; b += 32) rows[b] = (int32_t)dsgd_feistel((uint32_t)b, half_bits, key, (uint32_t)p.n_assigned);
     }
     __syncwarp();
 
@@ -105,49 +127,68 @@ __global__ void __launch_bounds__(128) k_async_worker(const AsyncParams p) {
     const double c = p.lambda * 2.0 * S;
     const bool add_c = (c != 0.0) && (fabs(c) > kEps);
 
-    // ---- 3. backward per sample against the current replica, summed into the lane's scratch ----
-    for (int b = 0; b < B; ++b) {
-      const int32_t r = rows[b];
-      const int64_t s0 = (int64_t)p.rp16[r] * 2, s1 = (int64_t)p.rp16[r + 1] * 2;
-      const double y = (double)p.label[r];
-      double dot = 0.0;
-      for (int64_t k = s0 + lane; k < s1; k += 32) {
-        const uint2 pr = p.pairs[k];
-        dot += filt(filt((double)__uint_as_float(pr.y)) * __ldcg(&w[pr.x]));
-      }
-      dot = warp_sum(dot);
-      if (!(y * dot < 0.0)) {  // SparseSVM.scala:28
-        for (int64_t k = s0 + lane; k < s1; k += 32) {
+    // ---- 3. backward per sample against the current replica, summed into the lane's scratch.  Row b + 1 (bounds, label,
+    //         first 128 pairs: nothing that depends on the weights) is requested before row b is worked on ----
+    {
+      AsyncBatchRow cur = async_fetch_batch_row(p, rows, 0, B, lane);
+      for (int b = 0; b < B; ++b) {
+        const AsyncBatchRow nxt = async_fetch_batch_row(p, rows, b + 1, B, lane);
+        double wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) wv[u] = (cur.pre[u].y << 1) ? __ldcg(&w[cur.pre[u].x]) : 0.0;
+        double dot = 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dot += filt(filt((double)__uint_as_float(cur.pre[u].y)) * wv[u]);
+        for (int64_t k = cur.s0 + 128 + lane; k < cur.s1; k += 32) {   // rows longer than 128 pairs
           const uint2 pr = p.pairs[k];
-          const double gv = filt(filt((double)__uint_as_float(pr.y)) * y);
-          if (gv != 0.0) scratch[pr.x] = filt(scratch[pr.x] + gv);  // Vec.sum: left fold, filter after each +
+          dot += filt(filt((double)__uint_as_float(pr.y)) * __ldcg(&w[pr.x]));
         }
+        dot = warp_sum(dot);
+        if (!(cur.y * dot < 0.0)) {  // SparseSVM.scala:28
+          // Vec.sum: left fold, filter after each +.  A column occurs once per row (unique-column rows) or in consecutive
+          // pairs of the same lane stride; the read-modify-write below is per lane, in pair order, as before
+          auto add_pair = [&](const uint2 pr) {
+            const double gv = filt(filt((double)__uint_as_float(pr.y)) * cur.y);
+            if (gv != 0.0) scratch[pr.x] = filt(scratch[pr.x] + gv);
+          };
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (cur.s0 + lane + 32 * u < cur.s1) add_pair(cur.pre[u]);
+          for (int64_t k = cur.s0 + 128 + lane; k < cur.s1; k += 32) add_pair(p.pairs[k]);
+        }
+        __syncwarp();
+        cur = nxt;
       }
-      __syncwarp();
     }
 
     // ---- 4. delta = lr * regularize(sum / B, w) on the summed support; apply to every replica ----
     double sd = 0.0;  // sum_j delta_j * d_j
-    for (int b = 0; b < B; ++b) {
-      const int32_t r = rows[b];
-      const int64_t s0 = (int64_t)p.rp16[r] * 2, s1 = (int64_t)p.rp16[r + 1] * 2;
-      for (int64_t k = s0 + lane; k < s1; k += 32) {
-        const uint2 pr = p.pairs[k];
-        // a padding pair repeats the row's last column with val == 0: only the real pair may claim the key
-        if (filt((double)__uint_as_float(pr.y)) == 0.0) continue;
-        const double v = scratch[pr.x];
-        if (v != 0.0) {
-          scratch[pr.x] = 0.0;                        // claim the key: later duplicates of the column see 0
-          double m = filt(v / (double)B);             // Vec.mean = sum / size (math/Vec.scala:139)
-          if (m != 0.0 && add_c) m = filt(m + c);     // regularize on the surviving keys
-          const double delta = filt(m * p.lr);        // learningRate * (...)
-          if (delta != 0.0) {
-            for (int q = 0; q < p.n_replicas; ++q) red_add_f64_sys(&p.replica[q][pr.x], -delta);
-            sd += delta * p.d[pr.x];
+    {
+      AsyncBatchRow cur = async_fetch_batch_row(p, rows, 0, B, lane);
+      for (int b = 0; b < B; ++b) {
+        const AsyncBatchRow nxt = async_fetch_batch_row(p, rows, b + 1, B, lane);
+        auto apply_pair = [&](const uint2 pr) {
+          // a padding pair repeats the row's last column with val == 0: only the real pair may claim the key
+          if (filt((double)__uint_as_float(pr.y)) == 0.0) return;
+          const double v = scratch[pr.x];
+          if (v != 0.0) {
+            scratch[pr.x] = 0.0;                        // claim the key: later duplicates of the column see 0
+            double m = filt(v / (double)B);             // Vec.mean = sum / size (math/Vec.scala:139)
+            if (m != 0.0 && add_c) m = filt(m + c);     // regularize on the surviving keys
+            const double delta = filt(m * p.lr);        // learningRate * (...)
+            if (delta != 0.0) {
+              for (int q = 0; q < p.n_replicas; ++q) red_add_f64_sys(&p.replica[q][pr.x], -delta);
+              sd += delta * p.d[pr.x];
+            }
           }
-        }
+        };
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (cur.s0 + lane + 32 * u < cur.s1) apply_pair(cur.pre[u]);
+        for (int64_t k = cur.s0 + 128 + lane; k < cur.s1; k += 32) apply_pair(p.pairs[k]);
+        __syncwarp();
+        cur = nxt;
       }
-      __syncwarp();
     }
     sd = warp_sum(sd);
     if (lane == 0) {

@@ -374,3 +374,9 @@ int64_t dsgd_draw_epoch(uint64_t seed, int64_t epoch, int32_t n_groups, const in
   }
   return failed ? -3 : steps;
 }
+
+/* ---- the async worker's without-replacement batch draw (dsgd_feistel.h), exported for the tests -------------------------- */
+#include "dsgd_feistel.h"
+uint32_t dsgd_feistel_pos(uint32_t x, uint64_t n, uint64_t key) {
+  return dsgd_feistel(x, dsgd_feistel_half_bits(n), key, (uint32_t)n);
+}

@@ -164,6 +164,8 @@ def host_lib():
         h.dsgd_rcv1_write.argtypes = [C.c_char_p, C.c_char_p, _i64, _vp, _vp, _vp, _vp, _i64]
         h.dsgd_draw_epoch.restype = C.c_int64
         h.dsgd_draw_epoch.argtypes = [C.c_uint64, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _i64]
+        h.dsgd_feistel_pos.restype = C.c_uint32
+        h.dsgd_feistel_pos.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64]
         _host = h
     return _host
 

@@ -287,3 +287,22 @@ def test_master_async_loop_matches_the_literal_restatement(case):
     else:
         assert ref["best_grad"] == "Vec.zeros(1)"       # the reference would hand back its initial bestGrad; see master.py
     assert state.end is not None and state.updates == 1
+
+
+def test_async_batch_draw_is_a_permutation():
+    """The async worker draws a batch as the first B images of a keyed permutation of [0, n) (csrc/dsgd_feistel.h, the same
+    source nvcc compiles into k_async_worker): every position once, whatever n and key -- `shuffle take batchSize`
+    (core/Slave.scala:86-88) never repeats a sample inside a batch."""
+    from distributed_sgd_b200.native import host_lib
+    h = host_lib()
+    for n, key in [(1, 5), (2, 1), (3, 77), (17, 123456789), (256, 2**63 + 11), (1000, 42), (4097, 7), (70000, 99)]:
+        img = np.array([h.dsgd_feistel_pos(x, n, key) for x in range(n)], dtype=np.int64)
+        assert img.min() == 0 and img.max() == n - 1 and len(np.unique(img)) == n, (n, key)
+    # different keys give different orders; the first few images are not the identity
+    a = [h.dsgd_feistel_pos(x, 560000, 1) for x in range(64)]
+    b = [h.dsgd_feistel_pos(x, 560000, 2) for x in range(64)]
+    assert a != b and a != list(range(64)) and len(set(a)) == 64
+    # rough uniformity of the first image over keys
+    first = np.array([h.dsgd_feistel_pos(0, 1000, k) for k in range(4000)])
+    hist = np.bincount(first // 100, minlength=10)
+    assert hist.min() > 300 and hist.max() < 500, hist
