@@ -1252,6 +1252,7 @@ static int async_launch(dsgd_ctx *ctx, const double *w0, const int32_t *assigned
   AsyncParams ap;
   ap.rp16 = ctx->rp16; ap.pairs = ctx->pairs; ap.label = ctx->label; ap.d = ctx->d; ap.dim = ctx->dim;
   ap.assigned = assigned; ap.n_assigned = n_assigned; ap.replay = replay; ap.batch = batch; ap.lr = lr; ap.lambda = ctx->lambda;
+  ap.rows_unique = ctx->rows_unique ? 1 : 0;
   int nr = 0;
   ap.replica[nr++] = ctx->w;
   for (int r = 0; r < ctx->world && r < kMaxReplicas - 1; ++r)

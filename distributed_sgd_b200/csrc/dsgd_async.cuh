@@ -50,6 +50,7 @@ struct AsyncParams {
   volatile int *stop;       // raised by dsgd_stop_async
   unsigned long long *claimed;  // next iteration number to claim (lanes race for iterations)
   unsigned long long *done;     // iterations finished by this worker
+  int rows_unique;              // every row's columns are distinct (checked when the rows were loaded)
 };
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long &s) {
@@ -151,9 +152,23 @@ __global__ void __launch_bounds__(128) k_async_worker(const AsyncParams p) {
             const double gv = filt(filt((double)__uint_as_float(pr.y)) * cur.y);
             if (gv != 0.0) scratch[pr.x] = filt(scratch[pr.x] + gv);
           };
+          if (p.rows_unique) {
+            // distinct columns inside a row: the lane's four read-modify-writes are independent -- all four scratch entries
+            // are requested before the first is used (one L2 round trip instead of four dependent ones)
+            double gv[4], sv[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (cur.s0 + lane + 32 * u < cur.s1) add_pair(cur.pre[u]);
+            for (int u = 0; u < 4; ++u) {
+              gv[u] = (cur.s0 + lane + 32 * u < cur.s1) ? filt(filt((double)__uint_as_float(cur.pre[u].y)) * cur.y) : 0.0;
+              sv[u] = (gv[u] != 0.0) ? scratch[cur.pre[u].x] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (gv[u] != 0.0) scratch[cur.pre[u].x] = filt(sv[u] + gv[u]);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (cur.s0 + lane + 32 * u < cur.s1) add_pair(cur.pre[u]);
+          }
           for (int64_t k = cur.s0 + 128 + lane; k < cur.s1; k += 32) add_pair(p.pairs[k]);
         }
         __syncwarp();
@@ -182,9 +197,32 @@ __global__ void __launch_bounds__(128) k_async_worker(const AsyncParams p) {
             }
           }
         };
+        if (p.rows_unique) {
+          double v4[4], d4[4];
+          bool live[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (cur.s0 + lane + 32 * u < cur.s1) apply_pair(cur.pre[u]);
+          for (int u = 0; u < 4; ++u) {   // the lane's four entries and their dimSparsity factors: requested together
+            live[u] = (cur.s0 + lane + 32 * u < cur.s1) && filt((double)__uint_as_float(cur.pre[u].y)) != 0.0;
+            v4[u] = live[u] ? scratch[cur.pre[u].x] : 0.0;
+            d4[u] = live[u] ? __ldg(&p.d[cur.pre[u].x]) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (v4[u] != 0.0) {
+              scratch[cur.pre[u].x] = 0.0;                  // claim the key (the next rows of the batch see 0)
+              double m = filt(v4[u] / (double)B);
+              if (m != 0.0 && add_c) m = filt(m + c);
+              const double delta = filt(m * p.lr);
+              if (delta != 0.0) {
+                for (int q = 0; q < p.n_replicas; ++q) red_add_f64_sys(&p.replica[q][cur.pre[u].x], -delta);
+                sd += delta * d4[u];
+              }
+            }
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (cur.s0 + lane + 32 * u < cur.s1) apply_pair(cur.pre[u]);
+        }
         for (int64_t k = cur.s0 + 128 + lane; k < cur.s1; k += 32) apply_pair(p.pairs[k]);
         __syncwarp();
         cur = nxt;
