@@ -208,7 +208,8 @@ int dsgd_async_running(dsgd_ctx *ctx, int *running);
 /* Device time of the last finished async loop (CUDA events on the loop's stream), for benchmarks. */
 int dsgd_async_elapsed_ms(dsgd_ctx *ctx, float *elapsed_ms);
 /* SlaveImpl.updateGrad / AsyncMasterGrpcImpl.updateGrad (core/Slave.scala:177-185; core/MasterAsync.scala:
- * 164-177): weights -= delta for a sparse delta given as (idx, val) pairs.  which selects the replica. */
+ * 164-177): weights -= delta for a sparse delta given as (idx, val) pairs, applied to this context's own replica (a host-side
+ * sender -- e.g. a gRPC colleague -- uses it; GPU peers write the replica directly over NVLink). */
 int dsgd_update_grad(dsgd_ctx *ctx, const int32_t *idx, const double *val, int64_t nnz);
 /* GradState.updates (core/ml/GradState.scala:8; core/MasterAsync.scala:165): updates the master replica has
  * received if this ctx hosts or has imported it, else the updates this worker has made. */
