@@ -415,3 +415,146 @@ int dsgd_oracle_dim_sparsity(const dsgd_oracle_csr *a, int64_t n_train, double *
   free(df);
   return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * ALL-CORES CONTEXT (not the reference's parallelism: the reference serves one gradient request on ONE pool thread,
+ * core/Slave.scala:142).  One logical worker whose batch is split over T threads, to show what the same arithmetic does
+ * when a CPU box throws every core at a single worker's step: rows in parallel (each thread adds its y*x entries to a
+ * shared accumulator with compare-and-swap, filter after every addition), c and ||w||^2 as per-thread partial sums combined
+ * in thread order, the update applied by whichever thread touched a column first; three spin barriers per step.
+ * Summation order inside a batch differs from the serial left fold, so results agree with dsgd_oracle_sync_steps to
+ * rounding (tests/test_oracle_c_vs_literal.py), not to the bit.  Used by bench.py for the `all_cores` context figure only.
+ * ------------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  volatile int count;
+  volatile int sense;
+  int n;
+} spin_barrier;
+
+static void spin_wait(spin_barrier *b, int *local_sense) {
+  *local_sense = !*local_sense;
+  if (__atomic_add_fetch(&b->count, 1, __ATOMIC_ACQ_REL) == b->n) {
+    b->count = 0;
+    __atomic_store_n(&b->sense, *local_sense, __ATOMIC_RELEASE);
+  } else {
+    while (__atomic_load_n(&b->sense, __ATOMIC_ACQUIRE) != *local_sense) __builtin_ia32_pause();
+  }
+}
+
+typedef struct {
+  const dsgd_oracle_csr *a;
+  double lambda, lr;
+  const double *d;
+  double *w;
+  const int32_t *idx;
+  int64_t n_steps, batch;
+  double *losses_out;
+  double *g;              /* shared accumulator, dense */
+  uint8_t *mark;          /* shared first-touch marks */
+  double *part;           /* [T][4]: partial w.d, partial ||w||^2, partial hinge, pad */
+  spin_barrier *bar;
+  int32_t *touched;       /* this thread's first-touched columns (capacity dim) */
+  int T, t;
+} mt_arg;
+
+static inline void atomic_add_filt(double *p, double v) {
+  uint64_t *q = (uint64_t *)p;
+  uint64_t old = __atomic_load_n(q, __ATOMIC_RELAXED);
+  for (;;) {
+    double o, nv;
+    memcpy(&o, &old, 8);
+    nv = filt(o + v);
+    uint64_t nb;
+    memcpy(&nb, &nv, 8);
+    if (__atomic_compare_exchange_n(q, &old, nb, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) return;
+  }
+}
+
+static void *mt_thread(void *p) {
+  mt_arg *g = (mt_arg *)p;
+  const dsgd_oracle_csr *a = g->a;
+  const int T = g->T, t = g->t;
+  const int32_t dim = a->dim;
+  const int32_t j0 = (int32_t)((int64_t)dim * t / T), j1 = (int32_t)((int64_t)dim * (t + 1) / T);
+  const int64_t r0 = g->batch * t / T, r1 = g->batch * (t + 1) / T;
+  int sense = 0;
+  for (int64_t s = 0; s < g->n_steps; ++s) {
+    /* partial sums over this thread's column range: c = 2 lambda (w . d), ||w||^2 */
+    double sd = 0.0, sn = 0.0;
+    for (int32_t j = j0; j < j1; ++j) { sd += filt(g->w[j] * g->d[j]); sn += g->w[j] * g->w[j]; }
+    g->part[4 * t + 0] = sd; g->part[4 * t + 1] = sn;
+    spin_wait(g->bar, &sense);
+    double wd = 0.0, nrm = 0.0;
+    for (int k = 0; k < T; ++k) { wd += g->part[4 * k + 0]; nrm += g->part[4 * k + 1]; }
+    const double c = g->lambda * 2.0 * wd;
+    /* this thread's rows of the batch */
+    const int32_t *idx = g->idx + s * g->batch;
+    int32_t nt = 0;
+    double h = 0.0;
+    for (int64_t i = r0; i < r1; ++i) {
+      const int64_t r = idx[i];
+      const double y = (double)a->label[r];
+      const double dot = row_dot(a, r, g->w);
+      const double pr = signum(dot) * -1.0;
+      const double l = 1.0 - y * pr;
+      h += l > 0.0 ? l : 0.0;
+      if (y * dot < 0.0) continue;
+      for (int64_t p2 = a->row_ptr[r]; p2 < a->row_ptr[r + 1]; ++p2) {
+        const int32_t j = a->col[p2];
+        const double gv = filt(filt((double)a->val[p2]) * y);
+        if (gv == 0.0) continue;
+        if (!__atomic_exchange_n(&g->mark[j], 1, __ATOMIC_RELAXED)) g->touched[nt++] = j;
+        atomic_add_filt(&g->g[j], gv);
+      }
+    }
+    g->part[4 * t + 2] = h;
+    spin_wait(g->bar, &sense);   /* the batch sum is complete; w is still w_before */
+    if (t == 0 && g->losses_out) {
+      double hs = 0.0;
+      for (int k = 0; k < T; ++k) hs += g->part[4 * k + 2];
+      g->losses_out[s] = g->lambda * nrm + hs / (double)g->batch;
+    }
+    /* regularize on the support, mean over the (one) worker, update -- for the columns this thread touched first */
+    const int add_c = (c != 0.0 && fabs(c) > EPS);
+    for (int32_t q = 0; q < nt; ++q) {
+      const int32_t j = g->touched[q];
+      double v = g->g[j];
+      if (v != 0.0 && add_c) v = filt(v + c);
+      const double step = filt(filt(v / 1.0) * g->lr);
+      g->w[j] = filt(g->w[j] - step);
+      g->g[j] = 0.0;
+      g->mark[j] = 0;
+    }
+    spin_wait(g->bar, &sense);   /* w_after is complete before anybody reads it */
+  }
+  return NULL;
+}
+
+int dsgd_oracle_sync_steps_allcores(const dsgd_oracle_csr *a, double lambda, const double *d, double *w, const int32_t *idx,
+                                    int64_t batch, double lr, int64_t n_steps, double *losses_out, int32_t threads) {
+  if (batch <= 0 || threads <= 0) return -3;
+  if (check_idx(a, idx, batch * n_steps)) return -2;
+  const int T = threads;
+  spin_barrier bar = {0, 0, T};
+  double *g = (double *)calloc((size_t)a->dim, sizeof(double));
+  uint8_t *mark = (uint8_t *)calloc((size_t)a->dim, 1);
+  double *part = (double *)calloc((size_t)T * 4, sizeof(double));
+  mt_arg *args = (mt_arg *)calloc((size_t)T, sizeof(mt_arg));
+  pthread_t *tids = (pthread_t *)calloc((size_t)T, sizeof(pthread_t));
+  int rc = (g && mark && part && args && tids) ? 0 : -1;
+  for (int t = 0; t < T && rc == 0; ++t) {
+    mt_arg m = {a, lambda, lr, d, w, idx, n_steps, batch, losses_out, g, mark, part, &bar, NULL, T, t};
+    m.touched = (int32_t *)malloc(sizeof(int32_t) * (size_t)a->dim);
+    if (!m.touched) rc = -1;
+    args[t] = m;
+  }
+  if (rc == 0) {
+    for (int t = 1; t < T; ++t) pthread_create(&tids[t], NULL, mt_thread, &args[t]);
+    mt_thread(&args[0]);
+    for (int t = 1; t < T; ++t) pthread_join(tids[t], NULL);
+  }
+  for (int t = 0; t < T; ++t)
+    if (args) free(args[t].touched);
+  free(g); free(mark); free(part); free(args); free(tids);
+  return rc;
+}

@@ -62,6 +62,12 @@ int dsgd_oracle_sync_steps(const dsgd_oracle_csr *a, double lambda, const double
                            const int32_t *idx, const int32_t *counts, int32_t n_workers, double lr,
                            int64_t n_steps, double *losses_out, int32_t threads);
 
+/* ALL-CORES CONTEXT: one logical worker, its batch split over `threads` threads (rows in parallel, shared accumulator).
+ * NOT the reference's parallelism (one thread per gradient request, core/Slave.scala:142); agrees with the serial form
+ * to rounding.  bench.py reports it beside the one-thread-per-worker baseline. */
+int dsgd_oracle_sync_steps_allcores(const dsgd_oracle_csr *a, double lambda, const double *d, double *w, const int32_t *idx,
+                                    int64_t batch, double lr, int64_t n_steps, double *losses_out, int32_t threads);
+
 /* Async worker iteration: delta = lr * regularize(mean_i backward(w_snapshot, x_i, y_i), w_snapshot)
  * (core/Slave.scala:92-99).  delta_out dense[dim]. The caller applies w -= delta to every replica
  * (core/Slave.scala:101-105,177-185; core/ml/GradState.scala:8). */

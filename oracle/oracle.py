@@ -41,8 +41,8 @@ def lib():
         if not os.path.exists(_LIB_PATH):
             build()
         _lib = C.CDLL(_LIB_PATH)
-        for name in ("forward", "loss_acc", "gradient", "sync_step", "sync_steps", "async_delta", "async_run",
-                     "dim_sparsity"):
+        for name in ("forward", "loss_acc", "gradient", "sync_step", "sync_steps", "sync_steps_allcores", "async_delta",
+                     "async_run", "dim_sparsity"):
             getattr(_lib, "dsgd_oracle_" + name).restype = C.c_int
     return _lib
 
@@ -130,6 +130,17 @@ class Oracle:
         _check(lib().dsgd_oracle_sync_steps(C.byref(self._csr), C.c_double(self.lam), _p(self.d), _p(w), _p(idx),
                                             _p(counts), C.c_int32(len(counts)), C.c_double(lr), C.c_int64(n_steps),
                                             _p(losses), C.c_int32(threads)), "sync_steps")
+        return w, losses
+
+    def sync_steps_allcores(self, w, idx, batch: int, lr: float, n_steps: int, threads: int):
+        """ONE worker, its batch split over `threads` threads (context figure, not the reference's parallelism)."""
+        w = self._w(w).copy()
+        idx = self._idx(idx)
+        assert len(idx) == batch * n_steps
+        losses = np.zeros(n_steps, dtype=np.float64)
+        _check(lib().dsgd_oracle_sync_steps_allcores(C.byref(self._csr), C.c_double(self.lam), _p(self.d), _p(w), _p(idx),
+                                                     C.c_int64(batch), C.c_double(lr), C.c_int64(n_steps), _p(losses),
+                                                     C.c_int32(threads)), "sync_steps_allcores")
         return w, losses
 
     def async_delta(self, w_snapshot, idx, lr: float) -> np.ndarray:

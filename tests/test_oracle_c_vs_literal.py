@@ -88,6 +88,26 @@ def test_sync_steps_trajectory(K, threads):
     assert losses[0] == 1.0  # KA1
 
 
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_all_cores_context_form_agrees_with_the_serial_one(threads):
+    """bench.py's `all_cores` context figure splits ONE worker's batch over T threads; it must compute the same
+    trajectory as the one-thread form (to rounding: the batch sum is associated differently), supports included."""
+    rng = np.random.default_rng(55)
+    dim, n = 300, 2000
+    rp, col, val, lab = random_csr(rng, n, dim, max_nnz=12, dup_values=True)
+    lam, lr, B, steps = 0.01, 0.5, 64, 40
+    orc = Oracle(rp, col, val, lab, dim, lam)
+    orc.set_dim_sparsity(orc.dim_sparsity(n))
+    idx = np.stack([rng.choice(n, size=B, replace=False) for _ in range(steps)]).astype(np.int32).reshape(-1)
+    w0 = rng.standard_normal(dim) * (rng.random(dim) < 0.5) * 0.1
+    w1, l1 = orc.sync_steps(w0, idx, [B], lr, n_steps=steps)
+    w2, l2 = orc.sync_steps_allcores(w0, idx, B, lr, steps, threads)
+    np.testing.assert_allclose(l2, l1, rtol=1e-12)
+    np.testing.assert_allclose(w2, w1, rtol=1e-10, atol=1e-14)
+    if threads == 1:
+        assert np.array_equal(w1, w2) and np.array_equal(l1, l2)
+
+
 def test_async_delta_and_run():
     rng = np.random.default_rng(7)
     dim, n = 24, 50
