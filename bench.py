@@ -445,10 +445,11 @@ def rpc_seam_record(ctx, data, n_train, d, B=256, reps=200):
             "api": "dsgd_gradient / dsgd_forward (C ABI), weights passed with the request like GradientRequest.weights"}
 
 
-def fit_record(ctx, group, data, n_train, rank, world, B, epochs=3):
+def fit_record(ctx, group, data, n_train, rank, world, B, epochs=8):
     """samples/s through MasterSync.fit (the reference's public API for this path, core/Master.scala:120-218), everything
     inside the timed region: per-epoch batch draws on the host, H2D of the ids, the step loop, train/test loss and accuracy
-    after every epoch, the weight read-back."""
+    after every epoch, the weight read-back.  (8 epochs: the first epoch's draw cannot overlap anything -- the draw of epoch
+    e + 1 runs on a host thread during epoch e -- and a real fit has tens of epochs; application.conf's default is 100.)"""
     from distributed_sgd_b200 import MasterSync, Slave, SparseSVM
     train, test = data.split_at(n_train)
     model = SparseSVM(LAMBDA)
