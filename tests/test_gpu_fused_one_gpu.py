@@ -6,7 +6,7 @@ box runs the multi-rank path for real: trajectories against the oracle's K-worke
 bit-identical replicas, several launches in a row (global step counter, receive parities), short last batches.
 K stops at 3 here: four spinning kernels sharing one GPU hit the device-side watchdog in 2 of 9 sessions (CUDA does not
 promise co-scheduling of independent kernels; cooperative launch is per kernel) -- four and eight ranks are checked on real
-GPUs by bench.py's parity record (profiles/r2_multi_gpu.md).
+GPUs by bench.py's parity record and whole-run replays (profiles/r2_multi_gpu.md).  A watchdog time-out is retried once.
 """
 import threading
 
@@ -38,8 +38,27 @@ def _run_ranks(fns):
     assert not any(t.is_alive() for t in th), "a rank hangs"
 
 
+def _retry_once_if_not_coscheduled(attempt):
+    """K spinning kernels sharing ONE GPU need all their CTAs resident at once; CUDA does not promise that for independent
+    plain launches (on real multi-GPU boxes every rank has its own GPU and a cooperative launch).  A run that ends in the
+    device-side watchdog is repeated once with fresh contexts; a second time-out fails the test."""
+    from distributed_sgd_b200.native import DsgdError, ERR_TIMEOUT
+    try:
+        return attempt()
+    except DsgdError as e:
+        if getattr(e, "code", None) == ERR_TIMEOUT:
+            import warnings
+            warnings.warn("fused ranks were not co-scheduled on the shared GPU (watchdog); retrying once")
+            return attempt()
+        raise
+
+
 @pytest.mark.parametrize("K,batch,dim", [(2, 48, 20000), (2, 7, 3000), (3, 33, 9000), (3, 64, 11000)])
 def test_fused_k_ranks_on_one_gpu_match_oracle(K, batch, dim):
+    _retry_once_if_not_coscheduled(lambda: _fused_k_ranks(K, batch, dim))
+
+
+def _fused_k_ranks(K, batch, dim):
     import torch
     from distributed_sgd_b200.utils import synthetic_rcv1
     sms = torch.cuda.get_device_properties(0).multi_processor_count
@@ -73,7 +92,12 @@ def test_fused_k_ranks_on_one_gpu_match_oracle(K, batch, dim):
             out[r] = (np.concatenate(ls), ctx.get_weights())
         return run
 
-    _run_ranks([rank_fn(r) for r in range(K)])
+    try:
+        _run_ranks([rank_fn(r) for r in range(K)])
+    except BaseException:
+        for c in ctxs:
+            c.close()
+        raise
     for r in range(K):
         losses, w = out[r]
         np.testing.assert_allclose(losses, losses_ref, rtol=1e-12, atol=0)
