@@ -29,6 +29,8 @@ Keys of the JSON line (one line on stdout, rank 0):
                exposes them, the hardware NVLink tx/rx counters over the timed region.
   cpu_baseline the fp64 CPU oracle (array restatement of the Scala path -- the reference itself needs a
                JVM, which this image lacks) timed on this host on a bounded sample of the same workload.
+               `cores` = 1: one thread per worker, like the reference (core/Slave.scala:142).  `all_cores` beside it is
+               CONTEXT: one worker's batch split over the best of 4-64 host threads (not how the reference runs).
 --impl reference times that CPU restatement as the reference arm.
 """
 from __future__ import annotations
