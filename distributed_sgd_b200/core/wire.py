@@ -7,14 +7,20 @@ lines of the .proto (:5,8-11 and the field options) do not affect the wire forma
 call on the worker's `NativeCtx`; vectors cross the wire as `Sparse{map<int32,double>, size}` with the reference's
 1-based feature keys (column c <-> key c + 1, utils/Dataset.scala:30; key == size is legal, quirk Q11).
 
-Divergence, stated: in async mode the reference slave forwards every delta to its colleague slaves over gRPC
-(core/Slave.scala:104-105).  A GPU worker pushes deltas to GPU peers through NVLink instead; colleagues registered
-over gRPC (`RegisterSlave`) are recorded but not pushed to.  Sync mode (`Forward`, `Gradient`) is complete.
+Async mode: the reference slave forwards every delta to its colleague slaves and to the master over gRPC
+(core/Slave.scala:104-105).  A GPU worker writes its deltas into GPU peers' replicas through NVLink; for colleagues that are
+NOT GPU peers (slaves registered with `RegisterSlave`, a master given as `master_target`) the worker loop also adds every delta
+to an OUTBOX accumulator on the device (dsgd_async_outbox_enable) and `AsyncRelay` forwards the difference since its last read
+as one `UpdateGrad` message per period.  Divergence, stated: one message per period carrying the SUM of that period's deltas,
+not one message per iteration -- the receivers' `w -= delta` additions commute, the master's update COUNTER however advances
+by one per message, so a reference master's stop rule (`updates >= N * maxEpochs`, core/MasterAsync.scala:83,171) sees periods,
+not iterations.
 """
 from __future__ import annotations
 
+import threading
 from concurrent import futures
-from typing import Dict, Optional, Tuple
+from typing import Callable, Dict, List, Optional, Tuple
 
 import numpy as np
 
@@ -116,26 +122,104 @@ def dense_to_sparse(M: Messages, a: np.ndarray, dim: int):
     return sp
 
 
+class AsyncRelay:
+    """core/Slave.scala:104-105 for colleagues reached over the host: reads the worker's outbox (sum of -delta since it was
+    enabled) every `period` seconds and sends the difference since the last read to every sender as one GradUpdate."""
+
+    def __init__(self, ctx, dim: int, period: float = 0.05):
+        self.ctx, self.dim, self.period = ctx, dim, period
+        self.M = Messages()
+        self.senders: Dict[object, Callable] = {}
+        self.last = np.zeros(dim)
+        self.sent = 0
+        self.errors: List[str] = []
+        self._lock = threading.Lock()
+        self._stop = threading.Event()
+        self._thread: Optional[threading.Thread] = None
+
+    def add(self, key, send: Callable):
+        with self._lock:
+            self.senders[key] = send
+
+    def remove(self, key):
+        with self._lock:
+            self.senders.pop(key, None)
+
+    def flush(self) -> int:
+        """Forwards what the worker has applied since the previous flush; returns the number of non-zero entries sent."""
+        with self._lock:
+            acc = self.ctx.async_outbox_read()
+            diff = acc - self.last                 # = -(sum of the deltas of the period)
+            self.last = acc
+            nz = np.flatnonzero(diff)
+            if nz.size == 0:
+                return 0
+            msg = self.M.GradUpdate(gradUpdate=dense_to_sparse(self.M, -diff, self.dim))   # receivers do w -= delta
+            for key, send in list(self.senders.items()):
+                try:
+                    send(msg)
+                except Exception as e:  # the reference does not await these futures either (core/Slave.scala:104-105)
+                    self.errors.append(f"{key}: {type(e).__name__}: {e}")
+            self.sent += 1
+            return int(nz.size)
+
+    def start(self):
+        self._stop.clear()
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
+
+    def _loop(self):
+        while not self._stop.wait(self.period):
+            self.flush()
+
+    def stop(self):
+        """Ends the periodic loop and forwards what is left (call after the worker loop has stopped)."""
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=5.0)
+            self._thread = None
+        self.flush()
+
+
 class SlaveServicer:
     """Handlers of service `epfl.distributed.Slave` (proto.proto:37-49) over one device context."""
 
-    def __init__(self, ctx, n_train: int, is_async: bool, concurrency: int = 1, seed: int = 0):
+    def __init__(self, ctx, n_train: int, is_async: bool, concurrency: int = 1, seed: int = 0,
+                 master_target: Optional[str] = None, relay_period: float = 0.05):
         self.ctx, self.n_train, self.is_async = ctx, n_train, is_async
         self.dim = ctx.dim
         self.concurrency, self.seed = concurrency, seed
         self.colleagues: Dict[Tuple[str, int], bool] = {}
+        self.master_target, self.relay_period = master_target, relay_period
+        self.relay: Optional[AsyncRelay] = None
+        self._stubs: Dict[object, object] = {}
         self.M = Messages()
-        import threading
         self._ctx_lock = threading.Lock()
 
-    # registration bookkeeping (core/Slave.scala:115-127)
+    # registration bookkeeping (core/Slave.scala:115-127); a colleague that registers while the loop runs is sent to from the
+    # next period on, like the reference's `slaves` map
     def RegisterSlave(self, node, context=None):
         self.colleagues[(node.host, node.port)] = True
+        if self.relay is not None:
+            self._attach((node.host, node.port))
         return self.M.Ack()
 
     def UnregisterSlave(self, node, context=None):
         self.colleagues.pop((node.host, node.port), None)
+        if self.relay is not None:
+            self.relay.remove((node.host, node.port))
+        stub = self._stubs.pop((node.host, node.port), None)
+        if stub is not None:
+            stub.close()
         return self.M.Ack()
+
+    def _attach(self, key):
+        if key == "master":
+            stub = MasterStub(self.master_target)
+        else:
+            stub = SlaveStub(f"{key[0]}:{key[1]}")
+        self._stubs[key] = stub
+        self.relay.add(key, stub.UpdateGrad)
 
     def _samples(self, samples) -> np.ndarray:
         idx = np.fromiter(samples, dtype=np.int64, count=len(samples))
@@ -166,14 +250,31 @@ class SlaveServicer:
         idx = self._samples(request.samples)
         w = sparse_to_dense(request.weights, self.dim)
         with self._ctx_lock:
+            relay = None
+            if self.colleagues or self.master_target:      # somebody this worker cannot reach over NVLink
+                self.ctx.async_outbox_enable()
+                relay = AsyncRelay(self.ctx, self.dim, self.relay_period)
             self.ctx.start_async(w, idx, request.batchSize, request.learningRate, concurrency=self.concurrency,
                                  max_updates=0, seed=self.seed)
+            if relay is not None:
+                self.relay = relay
+                for key in list(self.colleagues):
+                    self._attach(key)
+                if self.master_target:
+                    self._attach("master")
+                relay.start()
         return self.M.Ack()
 
     def StopAsync(self, request, context=None):           # core/Slave.scala:187-195
         if not self.is_async:
             raise RuntimeError("Cannot stop async computation: slave is in synchronous mode.")
         self.ctx.stop_async()
+        if self.relay is not None:
+            self.relay.stop()                              # forwards the rest
+            self.relay = None
+            for stub in self._stubs.values():
+                stub.close()
+            self._stubs.clear()
         return self.M.Ack()
 
     def UpdateGrad(self, request, context=None):          # core/Slave.scala:177-185
@@ -238,3 +339,49 @@ class SlaveStub:
 
     def close(self):
         self.channel.close()
+
+
+_MASTER_METHODS = {"RegisterSlave": ("Node", "Ack"), "UnregisterSlave": ("Node", "Ack"), "UpdateGrad": ("GradUpdate", "Ack")}
+
+
+class MasterStub:
+    """Client side of service `epfl.distributed.Master` (proto.proto:13-19): what a slave holds as `masterStub`
+    (core/Slave.scala:21-22) -- registration and, in async mode, the deltas (core/Slave.scala:105)."""
+
+    def __init__(self, target: str):
+        import grpc
+        self.M = Messages()
+        self.channel = grpc.insecure_channel(target)
+        for name, (req, rep) in _MASTER_METHODS.items():
+            setattr(self, name, self.channel.unary_unary(
+                f"/{PACKAGE}.Master/{name}",
+                request_serializer=getattr(self.M, req).SerializeToString,
+                response_deserializer=getattr(self.M, rep).FromString))
+
+    def close(self):
+        self.channel.close()
+
+
+def serve_master(handlers: Dict[str, Callable], port: int, host: str = "127.0.0.1", max_workers: int = 8):
+    """A `Master` service endpoint with the given handlers (name -> fn(request) -> reply); methods without a handler answer
+    Ack.  Enough for a Python-side master to receive registrations and async deltas from slaves (core/Master.scala:222-253;
+    core/MasterAsync.scala:164-177).  Returns (server, bound_port)."""
+    import grpc
+    M = Messages()
+    table = {}
+    for name, (req, rep) in _MASTER_METHODS.items():
+        fn = handlers.get(name, lambda request: M.Ack())
+
+        def handler(request, context, fn=fn):
+            try:
+                out = fn(request)
+                return out if out is not None else M.Ack()
+            except Exception as e:
+                context.abort(grpc.StatusCode.UNKNOWN, f"{type(e).__name__}: {e}")
+        table[name] = grpc.unary_unary_rpc_method_handler(handler, request_deserializer=getattr(M, req).FromString,
+                                                          response_serializer=getattr(M, rep).SerializeToString)
+    server = grpc.server(futures.ThreadPoolExecutor(max_workers=max_workers))
+    server.add_generic_rpc_handlers((grpc.method_handlers_generic_handler(f"{PACKAGE}.Master", table),))
+    bound = server.add_insecure_port(f"{host}:{port}")
+    server.start()
+    return server, bound

@@ -82,6 +82,7 @@ struct dsgd_ctx {
   cudaStream_t astream = nullptr;   // the worker loop
   cudaStream_t stream2 = nullptr;   // service calls that must not queue behind anything
   double *m_w = nullptr;            // master replica hosted by this ctx (dsgd_async_host_master)
+  double *outbox = nullptr;         // dsgd_async_outbox_enable: running sum of -delta of THIS worker (a replica-shaped block)
   double *peer_w[kMaxReplicas] = {};  // [r] = replica of rank r, [world] = master replica; nullptr: not attached
   bool peer_ipc[kMaxReplicas] = {};
   int *a_stop = nullptr;
@@ -277,7 +278,7 @@ extern "C" int dsgd_destroy(dsgd_ctx *ctx) {
     if (ctx->peer_x[r] && ctx->peer_x_ipc[r]) cudaIpcCloseMemHandle(ctx->peer_x[r]);
   if (ctx->xblk) cudaFree(ctx->xblk);
   if (ctx->x_llw) cudaFree(ctx->x_llw);
-  void *aptrs[] = {ctx->m_w, ctx->a_stop, ctx->a_cnt, ctx->a_scratch, ctx->a_rows, ctx->a_assigned, ctx->a_replay, ctx->u_idx, ctx->u_val};
+  void *aptrs[] = {ctx->m_w, ctx->outbox, ctx->a_stop, ctx->a_cnt, ctx->a_scratch, ctx->a_rows, ctx->a_assigned, ctx->a_replay, ctx->u_idx, ctx->u_val};
   for (void *q : aptrs) if (q) cudaFree(q);
   if (ctx->a_ev0) { cudaEventDestroy(ctx->a_ev0); cudaEventDestroy(ctx->a_ev1); }
   if (ctx->astream) cudaStreamDestroy(ctx->astream);
@@ -1260,6 +1261,10 @@ static int async_launch(dsgd_ctx *ctx, const double *w0, const int32_t *assigned
   ap.master_slot = -1;
   double *master = ctx->m_w ? ctx->m_w : (ctx->world < kMaxReplicas ? ctx->peer_w[ctx->world] : nullptr);
   if (master) { ap.master_slot = nr; ap.replica[nr++] = master; }
+  if (ctx->outbox) {   // colleagues reached over the host: one more target of every delta, relayed by the host in batches
+    NEED(nr < kMaxReplicas, DSGD_ERR_INVALID, "dsgd_start_async: no replica slot left for the outbox");
+    ap.replica[nr++] = ctx->outbox;
+  }
   for (int q = nr; q < kMaxReplicas; ++q) ap.replica[q] = nullptr;
   ap.n_replicas = nr;
   ap.scratch = ctx->a_scratch; ap.batch_rows = ctx->a_rows; ap.n_lanes = lanes; ap.max_updates = max_updates; ap.seed = seed;
@@ -1400,6 +1405,26 @@ extern "C" int dsgd_async_updates(dsgd_ctx *ctx, int64_t *count) {
   CU(cudaMemcpyAsync(&v, src, sizeof v, cudaMemcpyDeviceToHost, ctx->stream2));
   CU(cudaStreamSynchronize(ctx->stream2));
   *count = (int64_t)v;
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_async_outbox_enable(dsgd_ctx *ctx) {
+  if (!ctx) return DSGD_ERR_INVALID;
+  NEED(ctx->flags & DSGD_FLAG_ASYNC, DSGD_ERR_STATE, "dsgd_async_outbox_enable: ctx is in synchronous mode");
+  NEED(!ctx->a_running, DSGD_ERR_STATE, "dsgd_async_outbox_enable: async computation is running");
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->outbox) CU(cudaMalloc(&ctx->outbox, sizeof(double) * (size_t)(ctx->dim + kReplicaPad)));
+  CU(cudaMemsetAsync(ctx->outbox, 0, sizeof(double) * (size_t)(ctx->dim + kReplicaPad), ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return DSGD_OK;
+}
+
+extern "C" int dsgd_async_outbox_read(dsgd_ctx *ctx, double *acc_out) {
+  if (!ctx || !acc_out) return DSGD_ERR_INVALID;
+  NEED(ctx->outbox, DSGD_ERR_STATE, "dsgd_async_outbox_read: the outbox is not enabled");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(acc_out, ctx->outbox, sizeof(double) * (size_t)ctx->dim, cudaMemcpyDeviceToHost, ctx->stream2));
+  CU(cudaStreamSynchronize(ctx->stream2));
   return DSGD_OK;
 }
 

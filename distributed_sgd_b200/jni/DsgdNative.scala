@@ -46,6 +46,8 @@ object DsgdNative {
   @native def updateGrad(ctx: Long, idx: Array[Int], value: Array[Double]): Int
   @native def asyncUpdates(ctx: Long, out: Array[Long]): Int
   @native def asyncMasterWeights(ctx: Long, out: Array[Double]): Int
+  @native def asyncOutboxEnable(ctx: Long): Int
+  @native def asyncOutboxRead(ctx: Long, out: Array[Double]): Int
 
   /** Vec (keys are the reference's 1-based feature ids) -> dense array in the ABI's 0-based column space. */
   def densify(v: Vec, dim: Int): Array[Double] = {

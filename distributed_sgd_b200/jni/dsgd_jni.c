@@ -250,4 +250,14 @@ FN(asyncMasterWeights)(JNIEnv *env, jobject self, jlong h, jdoubleArray out) {
   back_Double(env, out, b, rc);
   return rc;
 }
+FN(asyncOutboxEnable)(JNIEnv *env, jobject self, jlong h) {
+  (void)env; (void)self;
+  return dsgd_async_outbox_enable(CTX(h));            /* deltas for colleagues reached over gRPC, core/Slave.scala:104-105 */
+}
+FN(asyncOutboxRead)(JNIEnv *env, jobject self, jlong h, jdoubleArray out) {
+  buf_t b = out_Double(env, out);
+  int rc = b.bad ? DSGD_ERR_NOMEM : (b.n < 1 ? DSGD_ERR_INVALID : dsgd_async_outbox_read(CTX(h), b.p));
+  back_Double(env, out, b, rc);
+  return rc;
+}
 #endif /* DSGD_HAVE_JNI */

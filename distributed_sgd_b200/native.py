@@ -117,6 +117,8 @@ ABI = {
     "dsgd_async_replay": [_vp, _vp, _vp, _i32, _i64, _f64],
     "dsgd_async_running": [_vp, C.POINTER(C.c_int)],
     "dsgd_async_master_weights": [_vp, _vp],
+    "dsgd_async_outbox_enable": [_vp],
+    "dsgd_async_outbox_read": [_vp, _vp],
     "dsgd_async_elapsed_ms": [_vp, C.POINTER(C.c_float)],
     "dsgd_start_async": [_vp, _vp, _vp, _i64, _i32, _f64, _i32, _i64, _u64],
     "dsgd_stop_async": [_vp],
@@ -431,6 +433,17 @@ class NativeCtx:
     def async_master_weights(self) -> np.ndarray:
         out = np.zeros(self.dim, dtype=np.float64)
         self._ck(self._l.dsgd_async_master_weights(self._h, _ptr(out)))
+        return out
+
+    def async_outbox_enable(self):
+        """One more target of every delta of this worker: the accumulator a host relay forwards to colleagues that are not GPU
+        peers (core/Slave.scala:104-105).  Call before start_async."""
+        self._ck(self._l.dsgd_async_outbox_enable(self._h))
+
+    def async_outbox_read(self) -> np.ndarray:
+        """Sum of -delta since async_outbox_enable (safe while the loop runs)."""
+        out = np.zeros(self.dim, dtype=np.float64)
+        self._ck(self._l.dsgd_async_outbox_read(self._h, _ptr(out)))
         return out
 
     def ipc_import(self, peer_rank: int, handle: bytes):

@@ -216,6 +216,13 @@ int dsgd_update_grad(dsgd_ctx *ctx, const int32_t *idx, const double *val, int64
 int dsgd_async_updates(dsgd_ctx *ctx, int64_t *count);
 /* Snapshot of the master replica (gradState.single().grad, core/MasterAsync.scala:109). */
 int dsgd_async_master_weights(dsgd_ctx *ctx, double *w_out);
+/* Colleagues that are NOT GPU peers (reference JVM slaves or a JVM master reached over gRPC, core/Slave.scala:104-105): the
+ * worker loop adds every -delta it applies to one more replica-shaped accumulator, the OUTBOX.  The host reads it while the
+ * loop runs and forwards the difference since its last read as ONE updateGrad message (w -= sum of the deltas of the period:
+ * the reference sends one message per iteration; Hogwild's additions commute).  Enable before dsgd_start_async (zeroes the
+ * accumulator); acc_out[dim] = sum of -delta since then.  dsgd_async_outbox_read is safe while the loop runs. */
+int dsgd_async_outbox_enable(dsgd_ctx *ctx);
+int dsgd_async_outbox_read(dsgd_ctx *ctx, double *acc_out);
 
 #ifdef __cplusplus
 }

@@ -160,3 +160,66 @@ def test_master_async_fit_single_gpu(synth):
     assert master.local_loss_accuracy(state.grad, test_data=True)[1] > 0.55
     assert not slave.ctx.async_running()
     slave.stop()
+
+
+@pytest.mark.parametrize("batch", [1, 8])
+def test_outbox_accumulates_exactly_what_the_worker_applied(synth, batch):
+    """dsgd_async_outbox_*: the accumulator a host relay forwards to colleagues that are not GPU peers
+    (core/Slave.scala:104-105) receives every -delta the worker applies to its own replica: after a recorded run,
+    outbox == w_final - w0 up to the rounding of two sums that start from different values."""
+    rng = np.random.default_rng(40 + batch)
+    ctx, orc = make_pair(synth, lam=1e-3, n_train=4000, is_async=True)
+    n_updates = 200
+    idx = np.stack([rng.choice(4000, size=batch, replace=False) for _ in range(n_updates)]).astype(np.int32)
+    w0 = rng.standard_normal(synth.dim) * (rng.random(synth.dim) < 0.2) * 0.05
+    with pytest.raises(Exception):
+        ctx.async_outbox_read()                                     # not enabled yet
+    ctx.async_outbox_enable()
+    assert not ctx.async_outbox_read().any()
+    ctx.async_replay(w0, idx.reshape(-1), batch, 0.5)
+    w, out = ctx.get_weights(), ctx.async_outbox_read()
+    w_ref = orc.async_run(w0, idx.reshape(-1), batch, 0.5)
+    np.testing.assert_allclose(w, w_ref, rtol=1e-9, atol=1e-13)     # the outbox does not disturb the run
+    assert np.any(out != 0)
+    np.testing.assert_allclose(out, w - w0, rtol=1e-12, atol=1e-15)
+    ctx.close()
+
+
+def test_async_deltas_relayed_to_a_grpc_colleague(synth):
+    """The wire service with a colleague that is not a GPU peer: the colleague's replica (a plain numpy vector here) follows
+    the GPU worker's through the relayed UpdateGrad messages."""
+    from distributed_sgd_b200.core import wire
+
+    class Colleague:
+        dim = synth.dim
+
+        def __init__(self, w0):
+            self.w = w0.copy()
+            self.n = 0
+
+        def update_grad(self, idx, val):
+            self.w[idx] -= val                                      # core/Slave.scala:180
+            self.n += 1
+
+    w0 = np.zeros(synth.dim)
+    col = Colleague(w0)
+    cserver, cport = wire.serve_slave(wire.SlaveServicer(col, n_train=4000, is_async=True), 0)
+    ctx, _ = make_pair(synth, lam=1e-5, n_train=4000, is_async=True)
+    srv = wire.SlaveServicer(ctx, n_train=4000, is_async=True, relay_period=0.02)
+    M = srv.M
+    try:
+        srv.RegisterSlave(M.Node(host="127.0.0.1", port=cport))
+        srv.StartAsync(M.StartAsyncRequest(weights=M.Sparse(size=synth.dim), samples=list(range(4000)), batchSize=1,
+                                           learningRate=0.1))
+        t0 = time.time()
+        while ctx.async_updates() < 3000 and time.time() - t0 < 30:
+            time.sleep(0.01)
+        relay = srv.relay
+        srv.StopAsync(M.Empty())
+        assert ctx.async_updates() >= 3000 and relay.sent >= 1 and not relay.errors
+        w = ctx.get_weights()
+        assert np.any(w != 0)
+        np.testing.assert_allclose(col.w, w, rtol=1e-10, atol=1e-14)   # same deltas, summed per period instead of one by one
+    finally:
+        cserver.stop(0)
+    ctx.close()

@@ -110,3 +110,67 @@ def test_service_round_trip_over_localhost():
         stub.close()
     finally:
         server.stop(0)
+
+
+class FakeAsyncCtx(FakeCtx):
+    """A worker whose outbox (sum of -delta since it was enabled) follows a script, one state per read."""
+
+    def __init__(self, states):
+        super().__init__()
+        self.states, self.reads, self.enabled = [np.asarray(s, dtype=float) for s in states], 0, False
+
+    def async_outbox_enable(self):
+        self.enabled = True
+        self.calls.append(("outbox_enable",))
+
+    def async_outbox_read(self):
+        s = self.states[min(self.reads, len(self.states) - 1)]
+        self.reads += 1
+        return s.copy()
+
+
+def test_async_deltas_reach_colleagues_that_are_not_gpu_peers():
+    """core/Slave.scala:104-105: every delta goes to the colleague slaves and to the master.  For colleagues reached over
+    gRPC the GPU worker's outbox is forwarded in periods: the receivers must end up with w -= (sum of all deltas)."""
+    # outbox states = -(sum of deltas so far): three periods, the last read repeats (nothing new)
+    states = [[0, -0.5, 0, 0, 0.25, 0], [0, -0.5, 0, 0, 0.25, 0], [1.0, -0.75, 0, 0, 0.25, 0], [1.0, -0.75, 0, 0, 0.25, -2.0]]
+    worker = FakeAsyncCtx(states)
+    srv = wire.SlaveServicer(worker, n_train=10, is_async=True, relay_period=3600.0)     # flushed by hand below
+    colleague_ctx = FakeCtx()
+    colleague = wire.SlaveServicer(colleague_ctx, n_train=10, is_async=True)
+    cserver, cport = wire.serve_slave(colleague, 0)
+    got_master = []
+    mserver, mport = wire.serve_master({"UpdateGrad": lambda req: got_master.append(wire.sparse_to_dense(req.gradUpdate, 6))}, 0)
+    srv.master_target = f"127.0.0.1:{mport}"
+    M = srv.M
+    try:
+        srv.RegisterSlave(M.Node(host="127.0.0.1", port=cport))
+        w = M.Sparse(size=6)
+        srv.StartAsync(M.StartAsyncRequest(weights=w, samples=[0, 1], batchSize=1, learningRate=0.5))
+        assert worker.enabled and [c[0] for c in worker.calls] == ["outbox_enable", "start_async"]
+        relay = srv.relay
+        assert relay.flush() == 2          # {1: 0.5, 4: -0.25} as deltas (w -= delta)
+        assert relay.flush() == 0          # nothing new: no message
+        assert relay.flush() == 2
+        srv.StopAsync(M.Empty())           # final flush forwards the rest
+        assert srv.relay is None and relay.sent == 3 and not relay.errors
+        sent = [np.zeros(6) for _ in range(3)]
+        ups = [c for c in colleague_ctx.calls if c[0] == "update_grad"]
+        assert len(ups) == 3 and len(got_master) == 3
+        for k, (_, idx, val) in enumerate(ups):
+            sent[k][idx] = val
+            assert np.array_equal(sent[k], got_master[k])
+        assert np.array_equal(sent[0], [0, 0.5, 0, 0, -0.25, 0])
+        assert np.allclose(sum(sent), -np.asarray(states[-1]), rtol=0, atol=1e-15)      # telescopes to the whole outbox
+    finally:
+        cserver.stop(0)
+        mserver.stop(0)
+
+
+def test_async_without_colleagues_needs_no_outbox():
+    worker = FakeAsyncCtx([[0] * 6])
+    srv = wire.SlaveServicer(worker, n_train=10, is_async=True)
+    M = srv.M
+    srv.StartAsync(M.StartAsyncRequest(weights=M.Sparse(size=6), samples=[0], batchSize=1, learningRate=0.5))
+    assert not worker.enabled and srv.relay is None
+    srv.StopAsync(M.Empty())
